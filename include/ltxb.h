@@ -1,0 +1,165 @@
+/*
+ * ltxb — C ABI of the B200-native LTX-2 DiT denoise-step kernels (sm_100a).
+ *
+ * The reference (CharafChnioune/mlx-video) has NO native / FFI layer on this path: the hot path is
+ * Python over MLX library ops (ltx_core/loader/kernels.py:1-3 is an empty
+ * "custom kernels" stub).  Each entry point below therefore replaces one MLX library op *call site*
+ * of the reference, cited per function.  The Python host (mlx-video_b200/) binds these with ctypes
+ * (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says "host"; no torch types cross this boundary;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no host sync, no
+ *     allocation inside the library (scratch, if any, is passed by the caller);
+ *   - row-major matrices, leading dimensions (`ld*`) in ELEMENTS;
+ *   - bf16 = __nv_bfloat16 storage, "f32" = float;
+ *   - return value 0 = ok, negative = error (LTXB_ERR_*); ltxb_last_error() gives the message of
+ *     the last failure on the calling thread.
+ */
+#ifndef LTXB_H_
+#define LTXB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTXB_OK 0
+#define LTXB_ERR_BAD_ARG (-1)     /* null pointer, misaligned pointer, negative size           */
+#define LTXB_ERR_UNSUPPORTED (-2) /* shape outside what the kernels are built for              */
+#define LTXB_ERR_CUDA (-3)        /* a CUDA runtime / driver call failed, see ltxb_last_error  */
+#define LTXB_ERR_NO_DEVICE (-4)   /* no sm_100 device visible                                  */
+
+const char* ltxb_last_error(void);
+/* ABI version of this header; bump on any signature change. */
+int ltxb_abi_version(void);
+/* 0 if a compute-capability 10.x device is current, LTXB_ERR_NO_DEVICE otherwise. */
+int ltxb_device_check(void);
+/* Make `device` current for the library's (statically linked) CUDA runtime on the calling thread.
+ * Call once per thread before the first launch when the host framework uses a device other than 0. */
+int ltxb_set_device(int32_t device);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  nn.Linear  (attention.py:91-93,100,123-126,142; feed_forward.py:31,33; ltx.py:130,292,301;
+ *                 adaln.py:27,130-132; text_projection.py:18,20)
+ *
+ *   acc[m,n] = sum_k A[m,k] * W[n,k]         A: bf16 [M,K] (lda)   W: bf16 [N,K] (ldw), i.e. the
+ *                                            (out,in) weight layout of nn.Linear
+ * followed by a fused epilogue:
+ *   LTXB_EPI_BIAS_BF16      out bf16 = acc + bias
+ *   LTXB_EPI_GELU_BF16      out bf16 = gelu_tanh(acc + bias)     (feed_forward.py:12, text_projection.py:19)
+ *   LTXB_EPI_SILU_BF16      out bf16 = silu(acc + bias)          (adaln.py:26,131)
+ *   LTXB_EPI_BIAS_F32       out f32  = acc + bias
+ *   LTXB_EPI_RESID_GATE_F32 out f32  = resid + (acc + bias) * g  (transformer.py:254,257-261,347)
+ *        g = 1                                  when gate == NULL (attn2, un-gated)
+ *        g = gate_table[n] + gate[grow, n]      otherwise, grow = gate_row_index ? gate_row_index[m]
+ *                                                                                : m / gate_row_div
+ * tcgen05/TMEM tensor-core kernel fed by TMA; persistent over output tiles.
+ * Requirements: K % 64 == 0, N % 16 == 0, lda/ldw/ldo multiples of 8, 16-byte aligned pointers.
+ * block_n: N extent of one output tile (multiple of 16, 32..256) or 0 = choose for wave efficiency.
+ * cta_pair: 1 = cta_group::2 (two SMs share one 256-row tile), 0 = single CTA, -1 = choose.
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+  LTXB_EPI_BIAS_BF16 = 0,
+  LTXB_EPI_GELU_BF16 = 1,
+  LTXB_EPI_SILU_BF16 = 2,
+  LTXB_EPI_BIAS_F32 = 3,
+  LTXB_EPI_RESID_GATE_F32 = 4,
+  LTXB_EPI_COUNT = 5
+};
+
+typedef struct ltxb_epilogue {
+  int32_t mode;                  /* LTXB_EPI_*                                       */
+  int32_t gate_row_div;          /* >= 1; rows of `gate` = ceil(M / gate_row_div)    */
+  const float* bias;             /* [N] or NULL                                      */
+  const float* resid;            /* RESID_GATE: f32 [M, ldr]; may alias out          */
+  int64_t ldr;
+  const float* gate;             /* RESID_GATE: f32 [*, gate_ld] or NULL             */
+  int64_t gate_ld;
+  const int32_t* gate_row_index; /* optional [M]                                     */
+  const float* gate_table;       /* [N] added to gate, or NULL                       */
+} ltxb_epilogue;
+
+int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int32_t M,
+                   int32_t N, int32_t K, const ltxb_epilogue* epi, int32_t block_n, int32_t cta_pair,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3 + AdaLN modulate   rms_norm(x) * (1 + scale) + shift   (utils.py:398-400; transformer.py:253,
+ *                       257,315-325,346)   x f32 [R, D] (ldx) -> out bf16 [R, D] (ldo)
+ *   scale[r,:] = table_scale[:] + mod[mrow(r), scale_off : scale_off + D]   (get_ada_values,
+ *   shift[r,:] = table_shift[:] + mod[mrow(r), shift_off : shift_off + D]    transformer.py:135-177)
+ *   mrow(r) = row_index ? row_index[r] : r / row_div.   mod == NULL -> plain weightless rms_norm.
+ * One warp-shuffle reduction per row, 128-bit loads/stores. D % 8 == 0, D <= 16384.
+ * ---------------------------------------------------------------------------------------------- */
+int ltxb_rmsnorm_modulate(const float* x, int64_t ldx, void* out, int64_t ldo, int32_t R, int32_t D, float eps,
+                          const float* mod, int64_t ld_mod, int32_t scale_off, int32_t shift_off,
+                          const float* table_scale, const float* table_shift, int32_t row_div,
+                          const int32_t* row_index, void* stream);
+
+/* K6  nn.LayerNorm(affine=False) then x*(1+scale)+shift  (ltx.py:300,432-457)
+ *   scale/shift[r,:] = table_*[:] + emb[mrow(r), :]   (emb = embedded_timestep f32 [*, D]) */
+int ltxb_layernorm_modulate(const float* x, int64_t ldx, void* out, int64_t ldo, int32_t R, int32_t D, float eps,
+                            const float* emb, int64_t ld_emb, const float* table_scale,
+                            const float* table_shift, int32_t row_div, const int32_t* row_index,
+                            void* stream);
+
+/* x f32 [R,D] += y bf16 [R,D] * g   (transformer.py:254,347 when the projection ran un-fused)
+ *   g as in LTXB_EPI_RESID_GATE_F32 (gate NULL -> 1). */
+int ltxb_gate_residual(float* x, int64_t ldx, const void* y, int64_t ldy, int32_t R, int32_t D, const float* gate,
+                       int64_t gate_ld, int32_t gate_off, const float* gate_table, int32_t row_div,
+                       const int32_t* row_index, void* stream);
+
+/* K3w + K4  q_norm / k_norm (nn.RMSNorm over the FULL inner dim, learned weight; attention.py:96-97,
+ *           129-130) followed by split RoPE per head (rope.py:109-172; attention.py:133-136), in place.
+ *   x bf16 [B*T, D] (ldx), D = H * dh, dh in {64,128};  weight f32 [D];
+ *   cos/sin f32 [B_pe, H, T, dh/2] (B_pe == 1 broadcasts) or NULL for no rotation (attn2). */
+int ltxb_qknorm_rope(void* x, int64_t ldx, int32_t B, int32_t T, int32_t H, int32_t dh, const float* weight,
+                     float eps, const float* cos_tab, const float* sin_tab, int32_t B_pe, void* stream);
+
+/* a5  sinusoidal timestep features  (utils.py:486-526 with adaln.py:66: dim 256, flip_sin_to_cos,
+ *     shift 0):  out bf16 [n, dim] = [cos(t*scale*f_i) | sin(t*scale*f_i)], f_i = exp(-ln(1e4) i/(dim/2)). */
+int ltxb_timestep_embed(const float* t, int32_t n, float scale, int32_t dim, void* out, int64_t ldo, void* stream);
+
+/* a4  RoPE table  (rope.py:419-529, SPLIT layout):  cos/sin f32 [B, H, T, dim/(2H)].
+ *   positions f32 [B, n_axes, T, 2] ([start,end) bounds; middle = (start+end)/2 when use_middle, else start),
+ *   max_pos f32 [n_axes] (host), freq f32 [nfreq] (device; theta^linspace(0,1,nfreq) * pi/2, built on
+ *   the host exactly as the reference does), nfreq = dim / (2 n_axes); left pad = dim/2 - nfreq*n_axes. */
+int ltxb_rope_table(const float* positions, int32_t B, int32_t n_axes, int32_t T, const float* max_pos_host,
+                    const float* freq, int32_t nfreq, int32_t dim, int32_t H, int32_t use_middle, float* cos_out,
+                    float* sin_out, void* stream);
+
+/* elementwise helpers around the GEMMs */
+int ltxb_silu_bf16(const void* x, void* out, int64_t n, void* stream);        /* adaln.py:26 */
+int ltxb_cast_f32_to_bf16(const float* x, void* out, int64_t n, void* stream);
+int ltxb_cast_bf16_to_f32(const void* x, float* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  scaled_dot_product_attention  (attention.py:13-53 -> mx.fast.scaled_dot_product_attention)
+ *   O[b,tq,h,:] = softmax_k(Q[b,tq,h,:] . K[b,tk,h,:] * scale + kv_bias[b,tk]) V[b,tk,h,:]
+ *   Q bf16 [B*Tq, *] (ldq), head h at columns [h*dh, (h+1)*dh); K, V likewise with Tk rows per batch;
+ *   O bf16 [B*Tq, H*dh] (ldo).  Non-causal.  kv_bias f32 [B, Tk] additive or NULL
+ *   (ltx.py:91-107 turns a 0/1 context mask into (m-1)*1e9).  dh in {64,128}.
+ * FlashAttention-style online softmax; both contractions on tcgen05 with TMEM accumulators, TMA loads.
+ * ---------------------------------------------------------------------------------------------- */
+int ltxb_attention_fwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                       int64_t ldo, int32_t B, int32_t Tq, int32_t Tk, int32_t H, int32_t dh, float scale,
+                       const float* kv_bias, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a21/a22 sampler-side elementwise (utils.py:404-440; generate.py:1255,1283,1288-1301)
+ *   CFG combine + to_denoised + fp32 Euler in one pass over the latent:
+ *     v  = v_pos + (cfg_scale - 1) (v_pos - v_neg)           (v_neg NULL -> v = v_pos)
+ *     x0 = x - sigma_tok * v ; if mask: x0 = x0*mask + clean*(1-mask)
+ *     x' = x0 + sigma_next * (x - x0) / sigma
+ *   x, v_*, clean: f32 [n_tok, C];  sigma_tok f32 [n_tok] or NULL (-> sigma); mask f32 [n_tok] or NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int ltxb_euler_step(float* x, const float* v_pos, const float* v_neg, float cfg_scale, const float* sigma_tok,
+                    float sigma, float sigma_next, const float* mask, const float* clean, int64_t n_tok,
+                    int32_t C, float* x0_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTXB_H_ */

@@ -1,0 +1,90 @@
+// Library-level plumbing of the C ABI: last-error string, device check, TMA tensor-map encoding.
+#include "common.cuh"
+
+#include <cstring>
+#include <mutex>
+
+namespace ltxb {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
+  auto fn = encode_fn();
+  if (fn == nullptr) return set_error(LTXB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+                  gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(LTXB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu, box %u x %u)",
+                     static_cast<int>(r), rank, static_cast<unsigned long long>(dims[0]),
+                     static_cast<unsigned long long>(rank > 1 ? dims[1] : 1), box[0], rank > 1 ? box[1] : 1);
+  return LTXB_OK;
+}
+
+int num_sms() {
+  static int sms = -1;
+  if (sms < 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    sms = v;
+  }
+  return sms;
+}
+
+}  // namespace ltxb
+
+extern "C" const char* ltxb_last_error(void) { return ltxb::g_err; }
+
+extern "C" int ltxb_abi_version(void) { return 1; }
+
+extern "C" int ltxb_device_check(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return ltxb::set_error(LTXB_ERR_NO_DEVICE, "no CUDA device is visible");
+  }
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10)
+    return ltxb::set_error(LTXB_ERR_NO_DEVICE, "device %d is compute capability %d.x; this library is sm_100a only", dev,
+                           major);
+  return LTXB_OK;
+}
+
+extern "C" int ltxb_set_device(int32_t device) {
+  LTXB_CUDA(cudaSetDevice(device));
+  return LTXB_OK;
+}

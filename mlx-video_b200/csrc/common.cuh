@@ -1,0 +1,44 @@
+// Host-side plumbing shared by the C-ABI entry points: error reporting, argument checks,
+// TMA tensor-map encoding through the driver entry point (no link-time libcuda dependency, so the
+// library loads on a box without a GPU driver).
+#pragma once
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include "../../include/ltxb.h"
+
+namespace ltxb {
+
+int set_error(int code, const char* fmt, ...);
+
+#define LTXB_CHECK_ARG(cond, ...)                                 \
+  do {                                                            \
+    if (!(cond)) return ::ltxb::set_error(LTXB_ERR_BAD_ARG, __VA_ARGS__); \
+  } while (0)
+#define LTXB_CHECK_SUPPORTED(cond, ...)                               \
+  do {                                                                \
+    if (!(cond)) return ::ltxb::set_error(LTXB_ERR_UNSUPPORTED, __VA_ARGS__); \
+  } while (0)
+#define LTXB_CUDA(call)                                                                            \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return ::ltxb::set_error(LTXB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                               __FILE__, __LINE__);                                                \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// bf16 tensor map, 128-byte swizzle, zero OOB fill. dims/strides innermost-first; strides in bytes for
+// dims 1..rank-1. box innermost extent must be 64 elements (128 B = the swizzle span).
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box);
+
+int num_sms();
+
+}  // namespace ltxb

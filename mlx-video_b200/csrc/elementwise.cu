@@ -1,0 +1,532 @@
+// Memory-bound pieces of the LTX-2 DiT block: AdaLN modulate, norms, gate+residual, QK-norm+RoPE,
+// timestep features, RoPE tables, sampler step.  All are 128-bit vectorised, one row per CTA where a
+// row statistic is needed (warp-shuffle + one smem hop), grid-stride otherwise.  HBM roofline kernels:
+// algorithmic bytes per element are stated next to each entry point in DESIGN.md.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace ltxb {
+
+constexpr int kRowThreads = 256;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the whole block (blockDim.x multiple of 32, <= 1024). `red` is 32 floats of smem.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect `red` against the previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < nwarps) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+__device__ __forceinline__ void load8_ldg(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+__device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 w = *reinterpret_cast<const uint4*>(p);
+  const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(u[i] << 16);
+    v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 w;
+  w.x = pack_bf16x2(v[0], v[1]);
+  w.y = pack_bf16x2(v[2], v[3]);
+  w.z = pack_bf16x2(v[4], v[5]);
+  w.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = w;
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// rms_norm / layer_norm + AdaLN modulate.  kLayerNorm=false: x*rsqrt(mean(x^2)+eps);  true: LayerNorm.
+// mod_scale / mod_shift point at the first column of the scale / shift slice of the modulation row.
+// ------------------------------------------------------------------------------------------------
+template <int kChunks, bool kLayerNorm>
+__global__ void __launch_bounds__(kRowThreads)
+norm_modulate_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out, long long ldo,
+                     int D, float eps, const float* __restrict__ mod_scale, const float* __restrict__ mod_shift,
+                     long long ld_mod, const float* __restrict__ table_scale, const float* __restrict__ table_shift,
+                     int row_div, const int* __restrict__ row_index) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  const float* xr = x + row * ldx;
+  float v[kChunks][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < kChunks; ++j) {
+    const int c = (threadIdx.x + j * kRowThreads) * 8;
+    if (c < D) {
+      load8(xr + c, v[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += kLayerNorm ? v[j][i] : v[j][i] * v[j][i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
+    }
+  }
+  s = block_sum(s, red);
+  float mean = 0.f, rstd;
+  if constexpr (kLayerNorm) {
+    mean = s / static_cast<float>(D);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < kChunks; ++j) {
+      const int c = (threadIdx.x + j * kRowThreads) * 8;
+      if (c < D) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = v[j][i] - mean;
+          q += d * d;
+        }
+      }
+    }
+    q = block_sum(q, red);
+    rstd = rsqrtf(q / static_cast<float>(D) + eps);
+  } else {
+    rstd = rsqrtf(s / static_cast<float>(D) + eps);
+  }
+  const bool has_mod = (mod_scale != nullptr) || (table_scale != nullptr);
+  long long mrow = 0;
+  if (mod_scale != nullptr) mrow = row_index != nullptr ? row_index[row] : row / row_div;
+  __nv_bfloat16* orow = out + row * ldo;
+#pragma unroll
+  for (int j = 0; j < kChunks; ++j) {
+    const int c = (threadIdx.x + j * kRowThreads) * 8;
+    if (c >= D) continue;
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = (v[j][i] - mean) * rstd;
+    if (has_mod) {
+      float sc[8], sh[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sc[i] = 0.f, sh[i] = 0.f;
+      if (table_scale != nullptr) {
+        load8_ldg(table_scale + c, sc);
+        load8_ldg(table_shift + c, sh);
+      }
+      if (mod_scale != nullptr) {
+        float a[8], b[8];
+        load8_ldg(mod_scale + mrow * ld_mod + c, a);
+        load8_ldg(mod_shift + mrow * ld_mod + c, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sc[i] += a[i], sh[i] += b[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = fmaf(y[i], 1.0f + sc[i], sh[i]);
+    }
+    store8_bf16(orow + c, y);
+  }
+}
+
+template <bool kLayerNorm>
+static int launch_norm_modulate(const float* x, long long ldx, void* out, long long ldo, int R, int D, float eps,
+                                const float* mod_scale, const float* mod_shift, long long ld_mod,
+                                const float* table_scale, const float* table_shift, int row_div,
+                                const int* row_index, cudaStream_t s) {
+  const int chunks = (D / 8 + kRowThreads - 1) / kRowThreads;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+#define LTXB_LAUNCH_NM(C)                                                                                        \
+  norm_modulate_kernel<C, kLayerNorm><<<R, kRowThreads, 0, s>>>(x, ldx, o, ldo, D, eps, mod_scale, mod_shift, ld_mod, \
+                                                                 table_scale, table_shift, row_div, row_index)
+  if (chunks <= 1) LTXB_LAUNCH_NM(1);
+  else if (chunks <= 2) LTXB_LAUNCH_NM(2);
+  else if (chunks <= 4) LTXB_LAUNCH_NM(4);
+  else LTXB_LAUNCH_NM(8);
+#undef LTXB_LAUNCH_NM
+  LTXB_CUDA(cudaGetLastError());
+  return LTXB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// x += y * g
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gate_residual_kernel(float* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ y, long long ldy,
+                     long long R, int D, const float* __restrict__ gate, long long gate_ld,
+                     const float* __restrict__ gate_table, int row_div, const int* __restrict__ row_index) {
+  const int cpr = D / 8;
+  const long long total = R * cpr;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const long long row = i / cpr;
+    const int c = static_cast<int>(i - row * cpr) * 8;
+    float xv[8], yv[8];
+    load8(x + row * ldx + c, xv);
+    load8_bf16(y + row * ldy + c, yv);
+    if (gate != nullptr) {
+      const long long grow = row_index != nullptr ? row_index[row] : row / row_div;
+      float g[8];
+      load8_ldg(gate + grow * gate_ld + c, g);
+      if (gate_table != nullptr) {
+        float t[8];
+        load8_ldg(gate_table + c, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] += t[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) xv[k] = fmaf(yv[k], g[k], xv[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) xv[k] += yv[k];
+    }
+    store8(x + row * ldx + c, xv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// full-width RMSNorm with weight, then split RoPE per head, in place on bf16.
+// thread j owns elements [8j', 8j'+8) of the first half and the matching 8 of the second half of a head.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+qknorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int T, int H, int dh, const float* __restrict__ weight,
+                   float eps, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, int B_pe) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  const int half = dh / 2;
+  const int tph = half / 8;  // threads per head
+  const int nthr = H * tph;
+  const bool active = threadIdx.x < nthr;
+  const int h = active ? threadIdx.x / tph : 0;
+  const int off = active ? (threadIdx.x % tph) * 8 : 0;
+  __nv_bfloat16* p1 = x + row * ldx + h * dh + off;
+  __nv_bfloat16* p2 = p1 + half;
+  float a[8], b[8];
+  float s = 0.f;
+  if (active) {
+    load8_bf16(p1, a);
+    load8_bf16(p2, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i] * a[i] + b[i] * b[i];
+  }
+  s = block_sum(s, red);
+  if (!active) return;
+  const float rstd = rsqrtf(s / static_cast<float>(H * dh) + eps);
+  float w1[8], w2[8];
+  load8_ldg(weight + h * dh + off, w1);
+  load8_ldg(weight + h * dh + half + off, w2);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] *= rstd * w1[i], b[i] *= rstd * w2[i];
+  if (cos_tab != nullptr) {
+    const long long bb = (B_pe == 1) ? 0 : row / T;
+    const long long t = row % T;
+    const long long tab = ((bb * H + h) * T + t) * half + off;
+    float c[8], sn[8];
+    load8_ldg(cos_tab + tab, c);
+    load8_ldg(sin_tab + tab, sn);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float f = a[i] * c[i] - sn[i] * b[i];
+      const float g = b[i] * c[i] + sn[i] * a[i];
+      a[i] = f, b[i] = g;
+    }
+  }
+  store8_bf16(p1, a);
+  store8_bf16(p2, b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sinusoidal timestep features (flip_sin_to_cos=True, downscale_freq_shift=0, max_period=1e4)
+// ------------------------------------------------------------------------------------------------
+__global__ void timestep_embed_kernel(const float* __restrict__ t, int n, float scale, int dim,
+                                      __nv_bfloat16* __restrict__ out, long long ldo) {
+  const int half = dim / 2;
+  const long long total = static_cast<long long>(n) * half;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(blockDim.x) * gridDim.x) {
+    const long long r = i / half;
+    const int k = static_cast<int>(i - r * half);
+    const float ex = __fdiv_rn(__fmul_rn(-9.210340371976184f, static_cast<float>(k)), static_cast<float>(half));
+    const float arg = __fmul_rn(__fmul_rn(t[r], scale), expf(ex));
+    float sv, cv;
+    sincosf(arg, &sv, &cv);
+    out[r * ldo + k] = __float2bfloat16_rn(cv);
+    out[r * ldo + half + k] = __float2bfloat16_rn(sv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE cos/sin table, SPLIT layout (B, H, T, dim/2/H), left-padded with cos=1 / sin=0.
+// ------------------------------------------------------------------------------------------------
+struct RopeAxes {
+  float max_pos[4];
+};
+__global__ void rope_table_kernel(const float* __restrict__ pos, int n_axes, int T, RopeAxes ax,
+                                  const float* __restrict__ freq, int nfreq, int dim, int H, int use_middle,
+                                  float* __restrict__ cos_out, float* __restrict__ sin_out) {
+  const int half = dim / 2;
+  const int hd2 = half / H;
+  const int pad = half - nfreq * n_axes;
+  const long long bt = blockIdx.x;  // b*T + t
+  const long long b = bt / T, t = bt % T;
+  __shared__ float s_axis[4];
+  if (threadIdx.x < n_axes) {
+    const float* pp = pos + ((b * n_axes + threadIdx.x) * T + t) * 2;
+    const float start = pp[0], end = pp[1];
+    const float mid = use_middle ? __fdiv_rn(__fadd_rn(start, end), 2.0f) : start;
+    const float frac = __fdiv_rn(mid, ax.max_pos[threadIdx.x]);
+    s_axis[threadIdx.x] = __fadd_rn(__fmul_rn(frac, 2.0f), -1.0f);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < half; j += blockDim.x) {
+    float c = 1.f, s = 0.f;
+    if (j >= pad) {
+      const int jj = j - pad;
+      const int fi = jj / n_axes, axis = jj - fi * n_axes;
+      const float ang = __fmul_rn(s_axis[axis], freq[fi]);
+      sincosf(ang, &s, &c);
+    }
+    const int h = j / hd2, w = j - h * hd2;
+    const long long o = ((b * H + h) * T + t) * hd2 + w;
+    cos_out[o] = c;
+    sin_out[o] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small elementwise helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void silu_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n8,
+                                 long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(blockDim.x) * gridDim.x) {
+    float v[8];
+    load8_bf16(x + i * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = v[k] / (1.0f + __expf(-v[k]));
+    store8_bf16(out + i * 8, v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (long long i = n8 * 8; i < n; ++i) {
+      const float v = __bfloat162float(x[i]);
+      out[i] = __float2bfloat16_rn(v / (1.0f + __expf(-v)));
+    }
+  }
+}
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n8,
+                                     long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(blockDim.x) * gridDim.x) {
+    float v[8];
+    load8(x + i * 8, v);
+    store8_bf16(out + i * 8, v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n8 * 8; i < n; ++i) out[i] = __float2bfloat16_rn(x[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long n8,
+                                     long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(blockDim.x) * gridDim.x) {
+    float v[8];
+    load8_bf16(x + i * 8, v);
+    store8(out + i * 8, v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n8 * 8; i < n; ++i) out[i] = __bfloat162float(x[i]);
+}
+
+// CFG combine + to_denoised + mask blend + fp32 Euler (utils.py:404-440; generate.py:1255-1301)
+__global__ void euler_step_kernel(float* __restrict__ x, const float* __restrict__ v_pos,
+                                  const float* __restrict__ v_neg, float cfg_scale,
+                                  const float* __restrict__ sigma_tok, float sigma, float sigma_next,
+                                  const float* __restrict__ mask, const float* __restrict__ clean, long long n_tok,
+                                  int C, float* __restrict__ x0_out) {
+  const long long total = n_tok * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(blockDim.x) * gridDim.x) {
+    const long long tok = i / C;
+    float v = v_pos[i];
+    if (v_neg != nullptr) v = v + (cfg_scale - 1.0f) * (v - v_neg[i]);
+    const float xs = x[i];
+    const float st = sigma_tok != nullptr ? sigma_tok[tok] : sigma;
+    float x0 = xs - st * v;
+    if (mask != nullptr) {
+      const float m = mask[tok];
+      x0 = x0 * m + clean[i] * (1.0f - m);
+    }
+    if (x0_out != nullptr) x0_out[i] = x0;
+    x[i] = x0 + sigma_next * (xs - x0) / sigma;
+  }
+}
+
+static int grid_for(long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = 148ll * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace ltxb
+
+using namespace ltxb;
+
+extern "C" int ltxb_rmsnorm_modulate(const float* x, int64_t ldx, void* out, int64_t ldo, int32_t R, int32_t D,
+                                     float eps, const float* mod, int64_t ld_mod, int32_t scale_off,
+                                     int32_t shift_off, const float* table_scale, const float* table_shift,
+                                     int32_t row_div, const int32_t* row_index, void* stream) {
+  LTXB_CHECK_ARG(x && out, "ltxb_rmsnorm_modulate: null pointer");
+  if (R == 0) return LTXB_OK;
+  LTXB_CHECK_ARG(R > 0 && D > 0, "ltxb_rmsnorm_modulate: bad shape R=%d D=%d", R, D);
+  LTXB_CHECK_SUPPORTED(D % 8 == 0 && D <= 8 * 8 * kRowThreads, "ltxb_rmsnorm_modulate: D=%d must be a multiple of 8, <= 16384", D);
+  LTXB_CHECK_ARG(aligned16(x) && aligned16(out) && ldx % 4 == 0 && ldo % 8 == 0, "ltxb_rmsnorm_modulate: misaligned x/out");
+  LTXB_CHECK_ARG((table_scale == nullptr) == (table_shift == nullptr), "ltxb_rmsnorm_modulate: tables come in pairs");
+  if (mod) {
+    LTXB_CHECK_ARG(aligned16(mod) && ld_mod % 4 == 0 && scale_off % 4 == 0 && shift_off % 4 == 0,
+                   "ltxb_rmsnorm_modulate: modulation rows must be 16-byte aligned");
+    LTXB_CHECK_ARG(row_index || row_div >= 1, "ltxb_rmsnorm_modulate: row_div must be >= 1");
+  }
+  return launch_norm_modulate<false>(x, ldx, out, ldo, R, D, eps, mod ? mod + scale_off : nullptr,
+                                     mod ? mod + shift_off : nullptr, ld_mod, table_scale, table_shift,
+                                     row_div > 0 ? row_div : 1, row_index, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ltxb_layernorm_modulate(const float* x, int64_t ldx, void* out, int64_t ldo, int32_t R, int32_t D,
+                                       float eps, const float* emb, int64_t ld_emb, const float* table_scale,
+                                       const float* table_shift, int32_t row_div, const int32_t* row_index,
+                                       void* stream) {
+  LTXB_CHECK_ARG(x && out, "ltxb_layernorm_modulate: null pointer");
+  if (R == 0) return LTXB_OK;
+  LTXB_CHECK_ARG(R > 0 && D > 0, "ltxb_layernorm_modulate: bad shape R=%d D=%d", R, D);
+  LTXB_CHECK_SUPPORTED(D % 8 == 0 && D <= 8 * 8 * kRowThreads, "ltxb_layernorm_modulate: D=%d must be a multiple of 8, <= 16384", D);
+  LTXB_CHECK_ARG(aligned16(x) && aligned16(out) && ldx % 4 == 0 && ldo % 8 == 0, "ltxb_layernorm_modulate: misaligned x/out");
+  LTXB_CHECK_ARG((table_scale == nullptr) == (table_shift == nullptr), "ltxb_layernorm_modulate: tables come in pairs");
+  if (emb) {
+    LTXB_CHECK_ARG(aligned16(emb) && ld_emb % 4 == 0, "ltxb_layernorm_modulate: emb rows must be 16-byte aligned");
+    LTXB_CHECK_ARG(row_index || row_div >= 1, "ltxb_layernorm_modulate: row_div must be >= 1");
+  }
+  // scale and shift both add the SAME embedded_timestep row (ltx.py:443-451)
+  return launch_norm_modulate<true>(x, ldx, out, ldo, R, D, eps, emb, emb, ld_emb, table_scale, table_shift,
+                                    row_div > 0 ? row_div : 1, row_index, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ltxb_gate_residual(float* x, int64_t ldx, const void* y, int64_t ldy, int32_t R, int32_t D,
+                                  const float* gate, int64_t gate_ld, int32_t gate_off, const float* gate_table,
+                                  int32_t row_div, const int32_t* row_index, void* stream) {
+  LTXB_CHECK_ARG(x && y, "ltxb_gate_residual: null pointer");
+  if (R == 0) return LTXB_OK;
+  LTXB_CHECK_ARG(R > 0 && D > 0 && D % 8 == 0, "ltxb_gate_residual: bad shape R=%d D=%d (D %% 8 == 0)", R, D);
+  LTXB_CHECK_ARG(aligned16(x) && aligned16(y) && ldx % 4 == 0 && ldy % 8 == 0, "ltxb_gate_residual: misaligned x/y");
+  if (gate) {
+    LTXB_CHECK_ARG(aligned16(gate) && gate_ld % 4 == 0 && gate_off % 4 == 0, "ltxb_gate_residual: misaligned gate");
+    LTXB_CHECK_ARG(row_index || row_div >= 1, "ltxb_gate_residual: row_div must be >= 1");
+  }
+  const long long work = static_cast<long long>(R) * (D / 8);
+  gate_residual_kernel<<<grid_for(work, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, ldx, reinterpret_cast<const __nv_bfloat16*>(y), ldy, R, D, gate ? gate + gate_off : nullptr, gate_ld,
+      gate_table, row_div > 0 ? row_div : 1, row_index);
+  LTXB_CUDA(cudaGetLastError());
+  return LTXB_OK;
+}
+
+extern "C" int ltxb_qknorm_rope(void* x, int64_t ldx, int32_t B, int32_t T, int32_t H, int32_t dh,
+                                const float* weight, float eps, const float* cos_tab, const float* sin_tab,
+                                int32_t B_pe, void* stream) {
+  LTXB_CHECK_ARG(x && weight, "ltxb_qknorm_rope: null pointer");
+  if (B == 0 || T == 0) return LTXB_OK;
+  LTXB_CHECK_ARG(B > 0 && T > 0 && H > 0, "ltxb_qknorm_rope: bad shape B=%d T=%d H=%d", B, T, H);
+  LTXB_CHECK_SUPPORTED(dh == 64 || dh == 128, "ltxb_qknorm_rope: head dim %d not in {64,128}", dh);
+  LTXB_CHECK_SUPPORTED(H * (dh / 16) <= 1024, "ltxb_qknorm_rope: H*dh=%d too wide", H * dh);
+  LTXB_CHECK_ARG(aligned16(x) && ldx % 8 == 0 && aligned16(weight), "ltxb_qknorm_rope: misaligned x/weight");
+  LTXB_CHECK_ARG((cos_tab == nullptr) == (sin_tab == nullptr), "ltxb_qknorm_rope: cos/sin come in pairs");
+  if (cos_tab) LTXB_CHECK_ARG(aligned16(cos_tab) && aligned16(sin_tab) && (B_pe == 1 || B_pe == B), "ltxb_qknorm_rope: bad rope table");
+  const int nthr = ((H * (dh / 16) + 31) / 32) * 32;
+  qknorm_rope_kernel<<<B * T, nthr, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(x), ldx, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe);
+  LTXB_CUDA(cudaGetLastError());
+  return LTXB_OK;
+}
+
+extern "C" int ltxb_timestep_embed(const float* t, int32_t n, float scale, int32_t dim, void* out, int64_t ldo,
+                                   void* stream) {
+  LTXB_CHECK_ARG(t && out, "ltxb_timestep_embed: null pointer");
+  if (n == 0) return LTXB_OK;
+  LTXB_CHECK_ARG(n > 0 && dim > 0 && dim % 2 == 0 && ldo >= dim, "ltxb_timestep_embed: bad shape n=%d dim=%d", n, dim);
+  const long long work = static_cast<long long>(n) * (dim / 2);
+  timestep_embed_kernel<<<grid_for(work, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      t, n, scale, dim, reinterpret_cast<__nv_bfloat16*>(out), ldo);
+  LTXB_CUDA(cudaGetLastError());
+  return LTXB_OK;
+}
+
+extern "C" int ltxb_rope_table(const float* positions, int32_t B, int32_t n_axes, int32_t T,
+                               const float* max_pos_host, const float* freq, int32_t nfreq, int32_t dim, int32_t H,
+                               int32_t use_middle, float* cos_out, float* sin_out, void* stream) {
+  LTXB_CHECK_ARG(positions && max_pos_host && freq && cos_out && sin_out, "ltxb_rope_table: null pointer");
+  if (B == 0 || T == 0) return LTXB_OK;
+  LTXB_CHECK_ARG(B > 0 && T > 0, "ltxb_rope_table: bad shape B=%d T=%d", B, T);
+  LTXB_CHECK_SUPPORTED(n_axes >= 1 && n_axes <= 4, "ltxb_rope_table: n_axes=%d not in [1,4]", n_axes);
+  LTXB_CHECK_ARG(dim % 2 == 0 && H > 0 && (dim / 2) % H == 0, "ltxb_rope_table: dim=%d not divisible into %d heads", dim, H);
+  LTXB_CHECK_ARG(nfreq >= 1 && nfreq * n_axes <= dim / 2, "ltxb_rope_table: nfreq=%d x %d axes exceeds dim/2=%d", nfreq, n_axes, dim / 2);
+  RopeAxes ax{};
+  for (int i = 0; i < n_axes; ++i) ax.max_pos[i] = max_pos_host[i];
+  rope_table_kernel<<<B * T, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(positions, n_axes, T, ax, freq, nfreq, dim,
+                                                                                 H, use_middle, cos_out, sin_out);
+  LTXB_CUDA(cudaGetLastError());
+  return LTXB_OK;
+}
+
+extern "C" int ltxb_silu_bf16(const void* x, void* out, int64_t n, void* stream) {
+  LTXB_CHECK_ARG(x && out && n >= 0, "ltxb_silu_bf16: bad argument");
+  if (n == 0) return LTXB_OK;
+  LTXB_CHECK_ARG(aligned16(x) && aligned16(out), "ltxb_silu_bf16: misaligned");
+  silu_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), n / 8, n);
+  LTXB_CUDA(cudaGetLastError());
+  return LTXB_OK;
+}
+
+extern "C" int ltxb_cast_f32_to_bf16(const float* x, void* out, int64_t n, void* stream) {
+  LTXB_CHECK_ARG(x && out && n >= 0, "ltxb_cast_f32_to_bf16: bad argument");
+  if (n == 0) return LTXB_OK;
+  LTXB_CHECK_ARG(aligned16(x) && aligned16(out), "ltxb_cast_f32_to_bf16: misaligned");
+  cast_f32_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(out), n / 8, n);
+  LTXB_CUDA(cudaGetLastError());
+  return LTXB_OK;
+}
+
+extern "C" int ltxb_cast_bf16_to_f32(const void* x, float* out, int64_t n, void* stream) {
+  LTXB_CHECK_ARG(x && out && n >= 0, "ltxb_cast_bf16_to_f32: bad argument");
+  if (n == 0) return LTXB_OK;
+  LTXB_CHECK_ARG(aligned16(x) && aligned16(out), "ltxb_cast_bf16_to_f32: misaligned");
+  cast_bf16_f32_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), out, n / 8, n);
+  LTXB_CUDA(cudaGetLastError());
+  return LTXB_OK;
+}
+
+extern "C" int ltxb_euler_step(float* x, const float* v_pos, const float* v_neg, float cfg_scale,
+                               const float* sigma_tok, float sigma, float sigma_next, const float* mask,
+                               const float* clean, int64_t n_tok, int32_t C, float* x0_out, void* stream) {
+  LTXB_CHECK_ARG(x && v_pos && n_tok >= 0 && C > 0, "ltxb_euler_step: bad argument");
+  LTXB_CHECK_ARG(sigma != 0.0f, "ltxb_euler_step: sigma must be non-zero (generate.py:1293-1301 divides by it)");
+  LTXB_CHECK_ARG((mask == nullptr) || (clean != nullptr), "ltxb_euler_step: mask needs clean latents");
+  if (n_tok == 0) return LTXB_OK;
+  euler_step_kernel<<<grid_for(n_tok * C, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, v_pos, v_neg, cfg_scale, sigma_tok, sigma, sigma_next, mask, clean, n_tok, C, x0_out);
+  LTXB_CUDA(cudaGetLastError());
+  return LTXB_OK;
+}

@@ -1,0 +1,463 @@
+// K1: out = epilogue(A[M,K] . W[N,K]^T) — bf16 operands, fp32 accumulation in TMEM.
+//
+// Replaces every nn.Linear call site on the LTX-2 DiT path of the reference (mlx_video/models/ltx/
+// attention.py:91-93,100,123-126,142; feed_forward.py:31,33; ltx.py:130,292,301; adaln.py:27,130-132;
+// text_projection.py:18,20), with the elementwise op that follows it fused into the epilogue.
+//
+// Design (B200 / sm_100a):
+//   * persistent kernel, one CTA (or one CTA pair, cta_group::2) per SM (pair), static tile striding,
+//     M-fastest tile order so concurrently resident tiles share the same W panels in L2;
+//   * warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+TMEM alloc),
+//     warps 2..5 = epilogue (TMEM -> registers -> global);
+//   * smem ring of `num_stages` {A 128x64, W (BN/ctas)x64} bf16 tiles, 128-byte swizzle, filled by
+//     cp.async.bulk.tensor, consumed by tcgen05.mma straight from smem descriptors;
+//   * two TMEM accumulators (2 x BN fp32 columns) so the epilogue of tile i overlaps the main loop of
+//     tile i+1;
+//   * BN is a runtime value (multiple of 16, <= 256): the host picks it per problem so that the tile
+//     count fills whole waves of 148 SMs (e.g. M=1280, N=4096: BN=144 in pair mode -> 145 tiles on 74
+//     pairs = 96 % wave efficiency instead of 54 % at BN=256).
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace ltxb {
+
+constexpr int kBlockM = 128;  // rows of the output tile owned by ONE CTA (TMEM lanes)
+constexpr int kBlockK = 64;   // 64 bf16 = 128 B = one swizzle span
+constexpr int kUmmaK = 16;
+constexpr int kMaxStages = 8;
+constexpr int kGemmThreads = 192;
+constexpr int kSmemHeader = 1024;  // barriers + tmem pointer live in front of the tile ring
+constexpr int kTmemCols = 512;
+constexpr uint32_t kAccStride = 256;  // TMEM column stride between the two accumulators
+
+struct GemmParams {
+  int M, N, K;
+  int block_n;
+  int num_stages;
+  int num_m_tiles;  // in units of kBlockM * ctas rows
+  int num_n_tiles;
+  // epilogue
+  const float* bias;
+  void* out;
+  long long ldo;
+  const float* resid;
+  long long ldr;
+  const float* gate;
+  long long gate_ld;
+  int gate_row_div;
+  const int* gate_row_index;
+  const float* gate_table;
+};
+
+struct GemmSmemHeader {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(GemmSmemHeader) <= kSmemHeader, "header overflow");
+
+// Apply the fused epilogue to `n` (16 or 32) consecutive accumulator columns of one output row.
+template <int kEpi, int kCols>
+__device__ __forceinline__ void epilogue_store(const GemmParams& p, const uint32_t* acc, long long row, int col,
+                                               long long grow) {
+  float v[kCols];
+#pragma unroll
+  for (int i = 0; i < kCols; ++i) v[i] = __uint_as_float(acc[i]);
+  if (p.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+    for (int i = 0; i < kCols / 4; ++i) {
+      const float4 b = __ldg(b4 + i);
+      v[4 * i + 0] += b.x;
+      v[4 * i + 1] += b.y;
+      v[4 * i + 2] += b.z;
+      v[4 * i + 3] += b.w;
+    }
+  }
+  if constexpr (kEpi == LTXB_EPI_GELU_BF16) {
+#pragma unroll
+    for (int i = 0; i < kCols; ++i) v[i] = gelu_tanh(v[i]);
+  } else if constexpr (kEpi == LTXB_EPI_SILU_BF16) {
+#pragma unroll
+    for (int i = 0; i < kCols; ++i) v[i] = silu(v[i]);
+  }
+  if constexpr (kEpi == LTXB_EPI_BIAS_BF16 || kEpi == LTXB_EPI_GELU_BF16 || kEpi == LTXB_EPI_SILU_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col;
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int i = 0; i < kCols / 8; ++i) {
+      uint4 w;
+      w.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+      w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+      w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+      w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+      o4[i] = w;
+    }
+  } else if constexpr (kEpi == LTXB_EPI_BIAS_F32) {
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col);
+#pragma unroll
+    for (int i = 0; i < kCols / 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {  // LTXB_EPI_RESID_GATE_F32
+    const float4* r4 = reinterpret_cast<const float4*>(p.resid + row * p.ldr + col);
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col);
+    if (p.gate != nullptr) {
+      const float4* g4 = reinterpret_cast<const float4*>(p.gate + grow * p.gate_ld + col);
+      const float4* t4 = reinterpret_cast<const float4*>(p.gate_table != nullptr ? p.gate_table + col : nullptr);
+#pragma unroll
+      for (int i = 0; i < kCols / 4; ++i) {
+        const float4 r = r4[i];
+        float4 g = __ldg(g4 + i);
+        if (p.gate_table != nullptr) {
+          const float4 t = __ldg(t4 + i);
+          g.x += t.x, g.y += t.y, g.z += t.z, g.w += t.w;
+        }
+        o4[i] = make_float4(fmaf(v[4 * i], g.x, r.x), fmaf(v[4 * i + 1], g.y, r.y), fmaf(v[4 * i + 2], g.z, r.z),
+                            fmaf(v[4 * i + 3], g.w, r.w));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kCols / 4; ++i) {
+        const float4 r = r4[i];
+        o4[i] = make_float4(v[4 * i] + r.x, v[4 * i + 1] + r.y, v[4 * i + 2] + r.z, v[4 * i + 3] + r.w);
+      }
+    }
+  }
+}
+
+template <int kCtas, int kEpi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128-byte swizzle needs 1024-byte aligned tiles; the dynamic smem base is the same in every CTA.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  GemmSmemHeader* hdr = reinterpret_cast<GemmSmemHeader*>(smem);
+  uint8_t* tiles = smem + kSmemHeader;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kCtas == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = (cta_rank == 0);
+  const int num_clusters = gridDim.x / kCtas;
+  const int cluster_id = blockIdx.x / kCtas;
+
+  const int bn = p.block_n;
+  const int bn_load = bn / kCtas;  // W rows this CTA stages per k-block
+  const uint32_t a_bytes = kBlockM * kBlockK * 2;
+  const uint32_t w_bytes = bn_load * kBlockK * 2;
+  const uint32_t stage_bytes = a_bytes + w_bytes;
+  const int num_stages = p.num_stages;
+  const int num_kb = p.K / kBlockK;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < num_stages; ++s) {
+        mbar_init(&hdr->full[s], 1);
+        mbar_init(&hdr->empty[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&hdr->tmem_full[a], 1);
+        mbar_init(&hdr->tmem_empty[a], 4 * kCtas);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<kCtas>(&hdr->tmem_base, kTmemCols);
+  }
+  tc_fence_before_sync();
+  if constexpr (kCtas == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&hdr->tmem_base);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_tile = tile % p.num_m_tiles;
+        const int n_tile = tile / p.num_m_tiles;
+        const int m0 = (m_tile * kCtas + static_cast<int>(cta_rank)) * kBlockM;
+        const int n0 = n_tile * bn + static_cast<int>(cta_rank) * bn_load;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&hdr->empty[stage], phase ^ 1);
+          uint8_t* sa = tiles + static_cast<size_t>(stage) * stage_bytes;
+          uint8_t* sw = sa + a_bytes;
+          if constexpr (kCtas == 1) {
+            mbar_arrive_expect_tx(&hdr->full[stage], stage_bytes);
+            tma_load_2d(sa, &tmap_a, &hdr->full[stage], kb * kBlockK, m0);
+            tma_load_2d(sw, &tmap_w, &hdr->full[stage], kb * kBlockK, n0);
+          } else {
+            // both CTAs of the pair report their bytes on the LEADER's barrier
+            if (is_leader) mbar_arrive_expect_tx(&hdr->full[stage], stage_bytes * 2);
+            const uint32_t bar = mapa_u32(smem_u32(&hdr->full[stage]), 0);
+            tma_load_2d_pair(sa, &tmap_a, bar, kb * kBlockK, m0);
+            tma_load_2d_pair(sw, &tmap_w, bar, kb * kBlockK, n0);
+          }
+          if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
+        }
+      }
+      // tail: wait until every fill has been consumed, so neither CTA of a pair retires while
+      // commit arrivals for its barriers are still in flight
+      for (int s = 0; s < num_stages; ++s) {
+        mbar_wait(&hdr->empty[stage], phase ^ 1);
+        if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (pair: leader CTA only) =====================
+    if (lane == 0 && is_leader) {
+      const uint32_t idesc = make_idesc_bf16(kBlockM * kCtas, bn, 0, 0);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&hdr->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&hdr->full[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(tiles + static_cast<size_t>(stage) * stage_bytes);
+          const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t wdesc = make_smem_desc_sw128(sa + a_bytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advancing 16 elements (32 B) along K inside the 128-B swizzle span = +2 in the address field
+            umma_bf16_ss<kCtas>(d_tmem, adesc + 2 * k, wdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if constexpr (kCtas == 1) umma_commit(&hdr->empty[stage]); else umma_commit_pair(&hdr->empty[stage], 3);
+          if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
+        }
+        if constexpr (kCtas == 1) umma_commit(&hdr->tmem_full[acc]); else umma_commit_pair(&hdr->tmem_full[acc], 3);
+        if (++acc == 2) acc = 0, acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_tile = tile % p.num_m_tiles;
+      const int n_tile = tile / p.num_m_tiles;
+      const long long row = static_cast<long long>(m_tile * kCtas + static_cast<int>(cta_rank)) * kBlockM + quarter * 32 + lane;
+      const int n0 = n_tile * bn;
+      const bool row_ok = row < p.M;
+      long long grow = 0;
+      if constexpr (kEpi == LTXB_EPI_RESID_GATE_F32) {
+        if (row_ok && p.gate != nullptr)
+          grow = p.gate_row_index != nullptr ? p.gate_row_index[row] : row / p.gate_row_div;
+      }
+      mbar_wait(&hdr->tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccStride;
+      for (int c = 0; c < bn; c += 32) {
+        const bool last = (c + 32 >= bn);
+        if (c + 32 <= bn) {
+          uint32_t r[32];
+          tmem_ld_x32(t_row + c, r);
+          tmem_wait_ld();
+          if (last) {
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (kCtas == 1) mbar_arrive(&hdr->tmem_empty[acc]); else mbar_arrive_remote(&hdr->tmem_empty[acc], 0);
+            }
+          }
+          const int col = n0 + c;
+          if (row_ok) {
+            if (col + 32 <= p.N) {
+              epilogue_store<kEpi, 32>(p, r, row, col, grow);
+            } else if (col + 16 <= p.N) {
+              epilogue_store<kEpi, 16>(p, r, row, col, grow);
+            }
+          }
+        } else {  // 16-column tail of a BN that is not a multiple of 32
+          uint32_t r[16];
+          tmem_ld_x16(t_row + c, r);
+          tmem_wait_ld();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kCtas == 1) mbar_arrive(&hdr->tmem_empty[acc]); else mbar_arrive_remote(&hdr->tmem_empty[acc], 0);
+          }
+          const int col = n0 + c;
+          if (row_ok && col + 16 <= p.N) epilogue_store<kEpi, 16>(p, r, row, col, grow);
+        }
+      }
+      if (++acc == 2) acc = 0, acc_phase ^= 1;
+    }
+  }
+
+  // teardown: nobody may leave while the peer can still read this CTA's smem / TMEM
+  tc_fence_before_sync();
+  if constexpr (kCtas == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<kCtas>(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct TileChoice {
+  int block_n;
+  int ctas;
+  double cost;
+};
+
+// Wave-quantisation model: every SM (pair) runs `waves` tiles back to back; a tile costs ~BN MMA
+// columns plus a fixed prologue/drain. Pick the (BN, ctas) with the fewest total column-steps.
+static TileChoice choose_tile(int M, int N, int sms, int want_bn, int want_pair) {
+  TileChoice best{0, 0, 1e30};
+  for (int ctas = 1; ctas <= 2; ++ctas) {
+    if (want_pair == 0 && ctas == 2) continue;
+    if (want_pair == 1 && ctas == 1) continue;
+    if (want_pair < 0 && ctas == 2 && M <= kBlockM) continue;  // a pair would be half idle
+    const int slots = sms / ctas;
+    const int m_tiles = (M + kBlockM * ctas - 1) / (kBlockM * ctas);
+    for (int bn = 256; bn >= 32; bn -= 16) {
+      if (want_bn > 0 && bn != want_bn) continue;
+      if (want_bn <= 0 && bn < 128 && N >= 128) continue;  // narrow tiles starve on smem/L2 bandwidth
+      if (bn > ((N + 15) / 16) * 16 && bn != 32) continue;
+      const int n_tiles = (N + bn - 1) / bn;
+      const long long tiles = 1ll * m_tiles * n_tiles;
+      const long long waves = (tiles + slots - 1) / slots;
+      double cost = static_cast<double>(waves) * (bn + 12.0);
+      if (ctas == 1) cost *= 1.03;  // pairs halve the W traffic per SM: prefer them on ties
+      if (cost < best.cost) best = TileChoice{bn, ctas, cost};
+    }
+  }
+  return best;
+}
+
+template <int kCtas, int kEpi>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, int grid, size_t smem,
+                       cudaStream_t stream) {
+  auto kernel = gemm_bf16_kernel<kCtas, kEpi>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    LTXB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LTXB_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tw, p));
+  return LTXB_OK;
+}
+
+template <int kCtas>
+static int dispatch_epi(int mode, const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, int grid,
+                        size_t smem, cudaStream_t stream) {
+  switch (mode) {
+    case LTXB_EPI_BIAS_BF16: return launch_gemm<kCtas, LTXB_EPI_BIAS_BF16>(ta, tw, p, grid, smem, stream);
+    case LTXB_EPI_GELU_BF16: return launch_gemm<kCtas, LTXB_EPI_GELU_BF16>(ta, tw, p, grid, smem, stream);
+    case LTXB_EPI_SILU_BF16: return launch_gemm<kCtas, LTXB_EPI_SILU_BF16>(ta, tw, p, grid, smem, stream);
+    case LTXB_EPI_BIAS_F32: return launch_gemm<kCtas, LTXB_EPI_BIAS_F32>(ta, tw, p, grid, smem, stream);
+    case LTXB_EPI_RESID_GATE_F32: return launch_gemm<kCtas, LTXB_EPI_RESID_GATE_F32>(ta, tw, p, grid, smem, stream);
+    default: return set_error(LTXB_ERR_BAD_ARG, "ltxb_gemm_bf16: unknown epilogue mode %d", mode);
+  }
+}
+
+}  // namespace ltxb
+
+using namespace ltxb;
+
+extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
+                              int32_t M, int32_t N, int32_t K, const ltxb_epilogue* epi, int32_t block_n,
+                              int32_t cta_pair, void* stream) {
+  LTXB_CHECK_ARG(A && W && out && epi, "ltxb_gemm_bf16: null pointer");
+  LTXB_CHECK_ARG(M > 0 && N > 0 && K > 0, "ltxb_gemm_bf16: non-positive shape M=%d N=%d K=%d", M, N, K);
+  LTXB_CHECK_ARG(aligned16(A) && aligned16(W) && aligned16(out), "ltxb_gemm_bf16: pointers must be 16-byte aligned");
+  LTXB_CHECK_SUPPORTED(K % kBlockK == 0, "ltxb_gemm_bf16: K=%d must be a multiple of %d", K, kBlockK);
+  LTXB_CHECK_SUPPORTED(N % 16 == 0, "ltxb_gemm_bf16: N=%d must be a multiple of 16", N);
+  LTXB_CHECK_SUPPORTED(lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0 && lda >= K && ldw >= K && ldo >= N,
+                       "ltxb_gemm_bf16: leading dimensions must be multiples of 8 and cover the row");
+  LTXB_CHECK_ARG(epi->mode >= 0 && epi->mode < LTXB_EPI_COUNT, "ltxb_gemm_bf16: bad epilogue mode %d", epi->mode);
+  LTXB_CHECK_ARG(block_n == 0 || (block_n >= 32 && block_n <= 256 && block_n % 16 == 0),
+                 "ltxb_gemm_bf16: block_n=%d must be 0 or a multiple of 16 in [32,256]", block_n);
+  if (epi->bias) LTXB_CHECK_ARG(aligned16(epi->bias), "ltxb_gemm_bf16: bias must be 16-byte aligned");
+  if (epi->mode == LTXB_EPI_RESID_GATE_F32) {
+    LTXB_CHECK_ARG(epi->resid && aligned16(epi->resid) && epi->ldr % 4 == 0 && epi->ldr >= N,
+                   "ltxb_gemm_bf16: residual epilogue needs a 16-byte aligned f32 resid with ldr %% 4 == 0");
+    if (epi->gate) {
+      LTXB_CHECK_ARG(aligned16(epi->gate) && epi->gate_ld % 4 == 0, "ltxb_gemm_bf16: gate must be 16-byte aligned");
+      LTXB_CHECK_ARG(epi->gate_row_index || epi->gate_row_div >= 1, "ltxb_gemm_bf16: gate_row_div must be >= 1");
+      if (epi->gate_table) LTXB_CHECK_ARG(aligned16(epi->gate_table), "ltxb_gemm_bf16: gate_table misaligned");
+    }
+  }
+  if (epi->mode == LTXB_EPI_BIAS_F32 || epi->mode == LTXB_EPI_RESID_GATE_F32)
+    LTXB_CHECK_SUPPORTED(ldo % 4 == 0, "ltxb_gemm_bf16: f32 output needs ldo %% 4 == 0");
+
+  const int sms = num_sms();
+  if (sms <= 0) return set_error(LTXB_ERR_NO_DEVICE, "ltxb_gemm_bf16: no CUDA device");
+  static const int env_pair = [] { const char* e = getenv("LTXB_GEMM_PAIR"); return e ? atoi(e) : -1; }();
+  static const int env_bn = [] { const char* e = getenv("LTXB_GEMM_BN"); return e ? atoi(e) : 0; }();
+  if (cta_pair < 0) cta_pair = env_pair;
+  if (block_n == 0) block_n = env_bn;
+  const TileChoice tc = choose_tile(M, N, sms, block_n, cta_pair);
+  if (tc.block_n == 0) return set_error(LTXB_ERR_UNSUPPORTED, "ltxb_gemm_bf16: no tile for M=%d N=%d", M, N);
+  const int ctas = tc.ctas;
+  const int bn = tc.block_n;
+  if (ctas == 2) LTXB_CHECK_SUPPORTED(bn % 16 == 0 && (bn / 2) % 8 == 0, "pair mode needs block_n %% 16 == 0");
+
+  GemmParams p{};
+  p.M = M, p.N = N, p.K = K;
+  p.block_n = bn;
+  p.num_m_tiles = (M + kBlockM * ctas - 1) / (kBlockM * ctas);
+  p.num_n_tiles = (N + bn - 1) / bn;
+  const size_t stage_bytes = static_cast<size_t>(kBlockM + bn / ctas) * kBlockK * 2;
+  const size_t budget = 232448 - 1024 /*alignment slack*/ - kSmemHeader;
+  p.num_stages = static_cast<int>(std::min<size_t>(kMaxStages, budget / stage_bytes));
+  const size_t smem = 1024 + kSmemHeader + p.num_stages * stage_bytes;
+  p.bias = epi->bias;
+  p.out = out;
+  p.ldo = ldo;
+  p.resid = epi->resid;
+  p.ldr = epi->ldr;
+  p.gate = epi->gate;
+  p.gate_ld = epi->gate_ld;
+  p.gate_row_div = epi->gate_row_div > 0 ? epi->gate_row_div : 1;
+  p.gate_row_index = epi->gate_row_index;
+  p.gate_table = epi->gate_table;
+
+  CUtensorMap ta, tw;
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
+    const uint32_t box[2] = {kBlockK, kBlockM};
+    int rc = encode_tmap_bf16(&ta, A, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    const uint32_t box[2] = {kBlockK, static_cast<uint32_t>(bn / ctas)};
+    int rc = encode_tmap_bf16(&tw, W, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int clusters = std::min(num_tiles, sms / ctas);
+  const int grid = clusters * ctas;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (ctas == 2) return dispatch_epi<2>(epi->mode, ta, tw, p, grid, smem, s);
+  return dispatch_epi<1>(epi->mode, ta, tw, p, grid, smem, s);
+}

@@ -1,0 +1,278 @@
+"""Tensor-level wrappers over the C ABI: torch tensors in, raw device pointers + the current CUDA
+stream out.  PyTorch is used for memory and streams only; all arithmetic happens in ``libltxb.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import Epilogue, check, lib
+
+_device_set: set = set()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _prep(t: torch.Tensor) -> None:
+    """Fail loudly on anything that is not a CUDA tensor; bind the library to the tensor's device."""
+    if not t.is_cuda:
+        raise _lib.LtxbError("ltxb ops need CUDA tensors; there is no CPU fallback on this path")
+    idx = t.device.index
+    if idx not in _device_set:
+        check(lib.ltxb_set_device(idx), "ltxb_set_device")
+        check(lib.ltxb_device_check(), "ltxb_device_check")
+        _device_set.clear()
+        _device_set.add(idx)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _rows(t: torch.Tensor) -> int:
+    return t.numel() // t.shape[-1]
+
+
+def _ld(t: torch.Tensor) -> int:
+    """Leading dimension of a (possibly sliced) 2-D-viewable tensor whose last dim is contiguous."""
+    assert t.stride(-1) == 1, "last dimension must be contiguous"
+    if t.dim() == 1:
+        return t.shape[0]
+    ld = t.stride(-2)
+    # all leading dims must collapse onto a single row stride
+    expect = ld
+    for d in range(t.dim() - 2, -1, -1):
+        if t.shape[d] != 1:
+            assert t.stride(d) == expect, f"tensor with strides {t.stride()} is not a strided 2-D view"
+        expect *= t.shape[d]
+    return ld
+
+
+def gemm(
+    a: torch.Tensor,
+    w: torch.Tensor,
+    bias: Optional[torch.Tensor],
+    out: torch.Tensor,
+    mode: int = _lib.EPI_BIAS_BF16,
+    resid: Optional[torch.Tensor] = None,
+    gate: Optional[torch.Tensor] = None,
+    gate_table: Optional[torch.Tensor] = None,
+    gate_row_div: int = 1,
+    gate_row_index: Optional[torch.Tensor] = None,
+    block_n: int = 0,
+    cta_pair: int = -1,
+) -> torch.Tensor:
+    """out = epilogue(a @ w.T).  a: bf16 [..., K]; w: bf16 [N, K] (nn.Linear layout); see ltxb.h."""
+    _prep(a)
+    M, K = _rows(a), a.shape[-1]
+    N = w.shape[0]
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape[1] == K
+    assert _rows(out) == M and out.shape[-1] == N
+    if mode in (_lib.EPI_BIAS_F32, _lib.EPI_RESID_GATE_F32):
+        assert out.dtype == torch.float32
+    else:
+        assert out.dtype == torch.bfloat16
+    epi = Epilogue()
+    epi.mode = mode
+    epi.gate_row_div = gate_row_div
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+        epi.bias = bias.data_ptr()
+    if mode == _lib.EPI_RESID_GATE_F32:
+        assert resid is not None and resid.dtype == torch.float32
+        epi.resid = resid.data_ptr()
+        epi.ldr = _ld(resid)
+        if gate is not None:
+            assert gate.dtype == torch.float32 and gate.shape[-1] == N
+            epi.gate = gate.data_ptr()
+            epi.gate_ld = _ld(gate)
+            epi.gate_row_index = _ptr(gate_row_index)
+            if gate_table is not None:
+                assert gate_table.dtype == torch.float32 and gate_table.numel() == N
+                epi.gate_table = gate_table.data_ptr()
+    rc = lib.ltxb_gemm_bf16(a.data_ptr(), _ld(a), w.data_ptr(), _ld(w), out.data_ptr(), _ld(out), M, N, K,
+                            C.byref(epi), block_n, cta_pair, _stream())
+    check(rc, "ltxb_gemm_bf16")
+    return out
+
+
+def rmsnorm_modulate(
+    x: torch.Tensor,
+    out: torch.Tensor,
+    eps: float,
+    mod: Optional[torch.Tensor] = None,
+    scale_off: int = 0,
+    shift_off: int = 0,
+    table_scale: Optional[torch.Tensor] = None,
+    table_shift: Optional[torch.Tensor] = None,
+    row_div: int = 1,
+    row_index: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    _prep(x)
+    assert x.dtype == torch.float32 and out.dtype == torch.bfloat16
+    R, D = _rows(x), x.shape[-1]
+    rc = lib.ltxb_rmsnorm_modulate(x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), R, D, eps, _ptr(mod),
+                                   0 if mod is None else _ld(mod), scale_off, shift_off, _ptr(table_scale),
+                                   _ptr(table_shift), row_div, _ptr(row_index), _stream())
+    check(rc, "ltxb_rmsnorm_modulate")
+    return out
+
+
+def layernorm_modulate(
+    x: torch.Tensor,
+    out: torch.Tensor,
+    eps: float,
+    emb: Optional[torch.Tensor],
+    table_scale: Optional[torch.Tensor],
+    table_shift: Optional[torch.Tensor],
+    row_div: int = 1,
+    row_index: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    _prep(x)
+    assert x.dtype == torch.float32 and out.dtype == torch.bfloat16
+    R, D = _rows(x), x.shape[-1]
+    rc = lib.ltxb_layernorm_modulate(x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), R, D, eps, _ptr(emb),
+                                     0 if emb is None else _ld(emb), _ptr(table_scale), _ptr(table_shift), row_div,
+                                     _ptr(row_index), _stream())
+    check(rc, "ltxb_layernorm_modulate")
+    return out
+
+
+def gate_residual(
+    x: torch.Tensor,
+    y: torch.Tensor,
+    gate: Optional[torch.Tensor] = None,
+    gate_off: int = 0,
+    gate_table: Optional[torch.Tensor] = None,
+    row_div: int = 1,
+    row_index: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    _prep(x)
+    assert x.dtype == torch.float32 and y.dtype == torch.bfloat16
+    R, D = _rows(x), x.shape[-1]
+    rc = lib.ltxb_gate_residual(x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), R, D, _ptr(gate),
+                                0 if gate is None else _ld(gate), gate_off, _ptr(gate_table), row_div, _ptr(row_index),
+                                _stream())
+    check(rc, "ltxb_gate_residual")
+    return x
+
+
+def qknorm_rope(
+    x: torch.Tensor,
+    B: int,
+    T: int,
+    H: int,
+    dh: int,
+    weight: torch.Tensor,
+    eps: float,
+    cos: Optional[torch.Tensor] = None,
+    sin: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """In place on a bf16 [B*T, H*dh] (strided) view."""
+    _prep(x)
+    assert x.dtype == torch.bfloat16 and weight.dtype == torch.float32
+    b_pe = 1
+    if cos is not None:
+        assert cos.dtype == torch.float32 and sin.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous()
+        assert cos.shape[1:] == (H, T, dh // 2), f"rope table {tuple(cos.shape)} vs (B,{H},{T},{dh // 2})"
+        b_pe = cos.shape[0]
+    rc = lib.ltxb_qknorm_rope(x.data_ptr(), _ld(x), B, T, H, dh, weight.data_ptr(), eps, _ptr(cos), _ptr(sin), b_pe,
+                              _stream())
+    check(rc, "ltxb_qknorm_rope")
+    return x
+
+
+def timestep_embed(t: torch.Tensor, scale: float, dim: int, out: torch.Tensor) -> torch.Tensor:
+    _prep(t)
+    assert t.dtype == torch.float32 and t.is_contiguous() and out.dtype == torch.bfloat16
+    rc = lib.ltxb_timestep_embed(t.data_ptr(), t.numel(), scale, dim, out.data_ptr(), _ld(out), _stream())
+    check(rc, "ltxb_timestep_embed")
+    return out
+
+
+def rope_table(positions: torch.Tensor, max_pos, freq: torch.Tensor, dim: int, H: int, use_middle: bool):
+    _prep(positions)
+    assert positions.dtype == torch.float32 and positions.is_contiguous() and positions.dim() == 4
+    B, n_axes, T, two = positions.shape
+    assert two == 2 and len(max_pos) == n_axes
+    half = dim // 2
+    cos = torch.empty((B, H, T, half // H), dtype=torch.float32, device=positions.device)
+    sin = torch.empty_like(cos)
+    mp = (C.c_float * n_axes)(*[float(v) for v in max_pos])
+    rc = lib.ltxb_rope_table(positions.data_ptr(), B, n_axes, T, mp, freq.data_ptr(), freq.numel(), dim, H,
+                             1 if use_middle else 0, cos.data_ptr(), sin.data_ptr(), _stream())
+    check(rc, "ltxb_rope_table")
+    return cos, sin
+
+
+def silu_bf16(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _prep(x)
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and x.is_contiguous() and out.is_contiguous()
+    check(lib.ltxb_silu_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "ltxb_silu_bf16")
+    return out
+
+
+def cast_f32_to_bf16(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _prep(x)
+    assert x.dtype == torch.float32 and out.dtype == torch.bfloat16 and x.is_contiguous() and out.is_contiguous()
+    check(lib.ltxb_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "ltxb_cast_f32_to_bf16")
+    return out
+
+
+def cast_bf16_to_f32(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _prep(x)
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+    check(lib.ltxb_cast_bf16_to_f32(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "ltxb_cast_bf16_to_f32")
+    return out
+
+
+def attention(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    out: torch.Tensor,
+    B: int,
+    Tq: int,
+    Tk: int,
+    H: int,
+    dh: int,
+    scale: float,
+    kv_bias: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """q: bf16 [B*Tq, H*dh] view, k/v: bf16 [B*Tk, H*dh] views (row-strided), out: bf16 [B*Tq, H*dh]."""
+    _prep(q)
+    assert q.dtype == k.dtype == v.dtype == out.dtype == torch.bfloat16
+    if kv_bias is not None:
+        assert kv_bias.dtype == torch.float32 and kv_bias.is_contiguous() and kv_bias.shape == (B, Tk)
+    rc = lib.ltxb_attention_fwd(q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out.data_ptr(),
+                                _ld(out), B, Tq, Tk, H, dh, scale, _ptr(kv_bias), _stream())
+    check(rc, "ltxb_attention_fwd")
+    return out
+
+
+def euler_step(
+    x: torch.Tensor,
+    v_pos: torch.Tensor,
+    sigma: float,
+    sigma_next: float,
+    v_neg: Optional[torch.Tensor] = None,
+    cfg_scale: float = 1.0,
+    sigma_tok: Optional[torch.Tensor] = None,
+    mask: Optional[torch.Tensor] = None,
+    clean: Optional[torch.Tensor] = None,
+    x0_out: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """In-place sampler step on f32 [n_tok, C] latents (CFG combine + to_denoised + mask blend + Euler)."""
+    _prep(x)
+    for t in (x, v_pos, v_neg, sigma_tok, mask, clean, x0_out):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    n_tok, Cc = _rows(x), x.shape[-1]
+    rc = lib.ltxb_euler_step(x.data_ptr(), v_pos.data_ptr(), _ptr(v_neg), cfg_scale, _ptr(sigma_tok), sigma, sigma_next,
+                             _ptr(mask), _ptr(clean), n_tok, Cc, _ptr(x0_out), _stream())
+    check(rc, "ltxb_euler_step")
+    return x
