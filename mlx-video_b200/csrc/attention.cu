@@ -288,6 +288,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
   }
 
+  __syncwarp();
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) {

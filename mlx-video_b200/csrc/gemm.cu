@@ -297,6 +297,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 
   // teardown: nobody may leave while the peer can still read this CTA's smem / TMEM
+  __syncwarp();
   tc_fence_before_sync();
   if constexpr (kCtas == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
