@@ -122,6 +122,13 @@ int ltxb_qknorm_rope(void* x, int64_t ldx, int32_t B, int32_t T, int32_t H, int3
  *     shift 0):  out bf16 [n, dim] = [cos(t*scale*f_i) | sin(t*scale*f_i)], f_i = exp(-ln(1e4) i/(dim/2)). */
 int ltxb_timestep_embed(const float* t, int32_t n, float scale, int32_t dim, void* out, int64_t ldo, void* stream);
 
+/* F7 dedupe of per-token timesteps (generate.py:604-606,653,793 build timesteps = sigma * mask, so at most
+ *   F+1 distinct values exist):  values f32 [cap] = the distinct entries of t[0..n) (unused slots 0),
+ *   index i32 [n] = slot of each token, count i32 [1] = slots used.  More than `cap` distinct values:
+ *   count = cap+1 and all values are NaN (the forward then yields NaN; hosts check `count`). */
+int ltxb_timestep_groups(const float* t, int32_t n, int32_t cap, float* values, int32_t* index, int32_t* count,
+                         void* stream);
+
 /* a4  RoPE table  (rope.py:419-529, SPLIT layout):  cos/sin f32 [B, H, T, dim/(2H)].
  *   positions f32 [B, n_axes, T, 2] ([start,end) bounds; middle = (start+end)/2 when use_middle, else start),
  *   max_pos f32 [n_axes] (host), freq f32 [nfreq] (device; theta^linspace(0,1,nfreq) * pi/2, built on

@@ -371,6 +371,53 @@ __global__ void euler_step_kernel(float* __restrict__ x, const float* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Group equal per-token timesteps (at most F+1 distinct values over B*T tokens), so that
+// AdaLN-single (adaln.py:29-47) runs on `cap` rows instead of B*T.  Single CTA; slot table in smem,
+// claimed with atomicCAS on the float bit pattern.  Slot ORDER depends on thread timing, which is
+// harmless: every token's row is computed from that token's own value.  More than `cap` distinct
+// values: count = cap + 1 and every value is poisoned with NaN so the forward fails loudly.
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned kEmptySlot = 0xFFFFFFFFu;  // a NaN pattern no real timestep carries
+__global__ void __launch_bounds__(1024)
+timestep_groups_kernel(const float* __restrict__ t, int n, int cap, float* __restrict__ values,
+                       int* __restrict__ index, int* __restrict__ count) {
+  extern __shared__ unsigned slots[];
+  __shared__ int overflow;
+  for (int i = threadIdx.x; i < cap; i += blockDim.x) slots[i] = kEmptySlot;
+  if (threadIdx.x == 0) overflow = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float v = t[i];
+    if (v == 0.0f) v = 0.0f;  // -0 and +0 share a slot
+    const unsigned bits = __float_as_uint(v);
+    int slot = -1;
+    for (int s = 0; s < cap; ++s) {
+      unsigned cur = reinterpret_cast<volatile unsigned*>(slots)[s];
+      if (cur == kEmptySlot) cur = atomicCAS(&slots[s], kEmptySlot, bits);
+      if (cur == kEmptySlot || cur == bits) {
+        slot = s;
+        break;
+      }
+    }
+    if (slot < 0) overflow = 1, slot = 0;
+    index[i] = slot;
+  }
+  __syncthreads();
+  int used = 0;
+  for (int i = threadIdx.x; i < cap; i += blockDim.x) {
+    const unsigned b = slots[i];
+    values[i] = overflow ? __uint_as_float(0x7FC00000u) : (b == kEmptySlot ? 0.0f : __uint_as_float(b));
+    used += (b != kEmptySlot);
+  }
+  __shared__ int total;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  atomicAdd(&total, used);
+  __syncthreads();
+  if (threadIdx.x == 0) *count = overflow ? cap + 1 : total;
+}
+
 static int grid_for(long long work_items, int threads) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = 148ll * 16;
@@ -527,6 +574,16 @@ extern "C" int ltxb_euler_step(float* x, const float* v_pos, const float* v_neg,
   if (n_tok == 0) return LTXB_OK;
   euler_step_kernel<<<grid_for(n_tok * C, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, v_pos, v_neg, cfg_scale, sigma_tok, sigma, sigma_next, mask, clean, n_tok, C, x0_out);
+  LTXB_CUDA(cudaGetLastError());
+  return LTXB_OK;
+}
+
+extern "C" int ltxb_timestep_groups(const float* t, int32_t n, int32_t cap, float* values, int32_t* index,
+                                    int32_t* count, void* stream) {
+  LTXB_CHECK_ARG(t && values && index && count, "ltxb_timestep_groups: null pointer");
+  LTXB_CHECK_ARG(n >= 0 && cap >= 1 && cap <= 4096, "ltxb_timestep_groups: bad n=%d / cap=%d (1..4096)", n, cap);
+  timestep_groups_kernel<<<1, 1024, cap * sizeof(unsigned), reinterpret_cast<cudaStream_t>(stream)>>>(t, n, cap, values,
+                                                                                                    index, count);
   LTXB_CUDA(cudaGetLastError());
   return LTXB_OK;
 }

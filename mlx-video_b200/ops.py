@@ -14,6 +14,33 @@ from ._lib import Epilogue, check, lib
 _device_set: set = set()
 
 
+launches = 0          # kernels launched through this module since import (bench.py reports the delta)
+_profile = None       # optional list: when set, every launch is bracketed by CUDA events -> (name, flops_or_bytes, start, end)
+
+
+def profile(enable: bool):
+    """Per-launch CUDA-event timing on the launching stream (bench.py's roofline leg). Returns the record list."""
+    global _profile
+    _profile = [] if enable else None
+    return _profile
+
+
+def _call(name: str, work: float, *args) -> None:
+    """One C-ABI call == one kernel launch on torch's current stream."""
+    global launches
+    launches += 1
+    fn = getattr(lib, name)
+    if _profile is None:
+        check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    check(rc, name)
+    _profile.append((name, work, e0, e1))
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -95,9 +122,8 @@ def gemm(
             if gate_table is not None:
                 assert gate_table.dtype == torch.float32 and gate_table.numel() == N
                 epi.gate_table = gate_table.data_ptr()
-    rc = lib.ltxb_gemm_bf16(a.data_ptr(), _ld(a), w.data_ptr(), _ld(w), out.data_ptr(), _ld(out), M, N, K,
+    _call("ltxb_gemm_bf16", 2.0 * M * N * K, a.data_ptr(), _ld(a), w.data_ptr(), _ld(w), out.data_ptr(), _ld(out), M, N, K,
                             C.byref(epi), block_n, cta_pair, _stream())
-    check(rc, "ltxb_gemm_bf16")
     return out
 
 
@@ -116,10 +142,9 @@ def rmsnorm_modulate(
     _prep(x)
     assert x.dtype == torch.float32 and out.dtype == torch.bfloat16
     R, D = _rows(x), x.shape[-1]
-    rc = lib.ltxb_rmsnorm_modulate(x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), R, D, eps, _ptr(mod),
+    _call("ltxb_rmsnorm_modulate", 0.0, x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), R, D, eps, _ptr(mod),
                                    0 if mod is None else _ld(mod), scale_off, shift_off, _ptr(table_scale),
                                    _ptr(table_shift), row_div, _ptr(row_index), _stream())
-    check(rc, "ltxb_rmsnorm_modulate")
     return out
 
 
@@ -136,10 +161,9 @@ def layernorm_modulate(
     _prep(x)
     assert x.dtype == torch.float32 and out.dtype == torch.bfloat16
     R, D = _rows(x), x.shape[-1]
-    rc = lib.ltxb_layernorm_modulate(x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), R, D, eps, _ptr(emb),
+    _call("ltxb_layernorm_modulate", 0.0, x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), R, D, eps, _ptr(emb),
                                      0 if emb is None else _ld(emb), _ptr(table_scale), _ptr(table_shift), row_div,
                                      _ptr(row_index), _stream())
-    check(rc, "ltxb_layernorm_modulate")
     return out
 
 
@@ -155,10 +179,9 @@ def gate_residual(
     _prep(x)
     assert x.dtype == torch.float32 and y.dtype == torch.bfloat16
     R, D = _rows(x), x.shape[-1]
-    rc = lib.ltxb_gate_residual(x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), R, D, _ptr(gate),
+    _call("ltxb_gate_residual", 0.0, x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), R, D, _ptr(gate),
                                 0 if gate is None else _ld(gate), gate_off, _ptr(gate_table), row_div, _ptr(row_index),
                                 _stream())
-    check(rc, "ltxb_gate_residual")
     return x
 
 
@@ -181,17 +204,15 @@ def qknorm_rope(
         assert cos.dtype == torch.float32 and sin.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous()
         assert cos.shape[1:] == (H, T, dh // 2), f"rope table {tuple(cos.shape)} vs (B,{H},{T},{dh // 2})"
         b_pe = cos.shape[0]
-    rc = lib.ltxb_qknorm_rope(x.data_ptr(), _ld(x), B, T, H, dh, weight.data_ptr(), eps, _ptr(cos), _ptr(sin), b_pe,
+    _call("ltxb_qknorm_rope", 0.0, x.data_ptr(), _ld(x), B, T, H, dh, weight.data_ptr(), eps, _ptr(cos), _ptr(sin), b_pe,
                               _stream())
-    check(rc, "ltxb_qknorm_rope")
     return x
 
 
 def timestep_embed(t: torch.Tensor, scale: float, dim: int, out: torch.Tensor) -> torch.Tensor:
     _prep(t)
     assert t.dtype == torch.float32 and t.is_contiguous() and out.dtype == torch.bfloat16
-    rc = lib.ltxb_timestep_embed(t.data_ptr(), t.numel(), scale, dim, out.data_ptr(), _ld(out), _stream())
-    check(rc, "ltxb_timestep_embed")
+    _call("ltxb_timestep_embed", 0.0, t.data_ptr(), t.numel(), scale, dim, out.data_ptr(), _ld(out), _stream())
     return out
 
 
@@ -204,30 +225,29 @@ def rope_table(positions: torch.Tensor, max_pos, freq: torch.Tensor, dim: int, H
     cos = torch.empty((B, H, T, half // H), dtype=torch.float32, device=positions.device)
     sin = torch.empty_like(cos)
     mp = (C.c_float * n_axes)(*[float(v) for v in max_pos])
-    rc = lib.ltxb_rope_table(positions.data_ptr(), B, n_axes, T, mp, freq.data_ptr(), freq.numel(), dim, H,
+    _call("ltxb_rope_table", 0.0, positions.data_ptr(), B, n_axes, T, mp, freq.data_ptr(), freq.numel(), dim, H,
                              1 if use_middle else 0, cos.data_ptr(), sin.data_ptr(), _stream())
-    check(rc, "ltxb_rope_table")
     return cos, sin
 
 
 def silu_bf16(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     _prep(x)
     assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and x.is_contiguous() and out.is_contiguous()
-    check(lib.ltxb_silu_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "ltxb_silu_bf16")
+    _call("ltxb_silu_bf16", 0.0, x.data_ptr(), out.data_ptr(), x.numel(), _stream())
     return out
 
 
 def cast_f32_to_bf16(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     _prep(x)
     assert x.dtype == torch.float32 and out.dtype == torch.bfloat16 and x.is_contiguous() and out.is_contiguous()
-    check(lib.ltxb_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "ltxb_cast_f32_to_bf16")
+    _call("ltxb_cast_f32_to_bf16", 0.0, x.data_ptr(), out.data_ptr(), x.numel(), _stream())
     return out
 
 
 def cast_bf16_to_f32(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     _prep(x)
     assert x.dtype == torch.bfloat16 and out.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
-    check(lib.ltxb_cast_bf16_to_f32(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "ltxb_cast_bf16_to_f32")
+    _call("ltxb_cast_bf16_to_f32", 0.0, x.data_ptr(), out.data_ptr(), x.numel(), _stream())
     return out
 
 
@@ -249,9 +269,8 @@ def attention(
     assert q.dtype == k.dtype == v.dtype == out.dtype == torch.bfloat16
     if kv_bias is not None:
         assert kv_bias.dtype == torch.float32 and kv_bias.is_contiguous() and kv_bias.shape == (B, Tk)
-    rc = lib.ltxb_attention_fwd(q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out.data_ptr(),
+    _call("ltxb_attention_fwd", 4.0 * B * H * Tq * Tk * dh, q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out.data_ptr(),
                                 _ld(out), B, Tq, Tk, H, dh, scale, _ptr(kv_bias), _stream())
-    check(rc, "ltxb_attention_fwd")
     return out
 
 
@@ -272,7 +291,18 @@ def euler_step(
     for t in (x, v_pos, v_neg, sigma_tok, mask, clean, x0_out):
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
     n_tok, Cc = _rows(x), x.shape[-1]
-    rc = lib.ltxb_euler_step(x.data_ptr(), v_pos.data_ptr(), _ptr(v_neg), cfg_scale, _ptr(sigma_tok), sigma, sigma_next,
+    _call("ltxb_euler_step", 0.0, x.data_ptr(), v_pos.data_ptr(), _ptr(v_neg), cfg_scale, _ptr(sigma_tok), sigma, sigma_next,
                              _ptr(mask), _ptr(clean), n_tok, Cc, _ptr(x0_out), _stream())
-    check(rc, "ltxb_euler_step")
     return x
+
+
+def timestep_groups(t: torch.Tensor, cap: int):
+    """Device-side dedupe of per-token timesteps: returns (values f32 [cap], index i32 [n], count i32 [1])."""
+    _prep(t)
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    n = t.numel()
+    values = torch.empty(cap, dtype=torch.float32, device=t.device)
+    index = torch.empty(n, dtype=torch.int32, device=t.device)
+    count = torch.empty(1, dtype=torch.int32, device=t.device)
+    _call("ltxb_timestep_groups", 0.0, t.data_ptr(), n, cap, values.data_ptr(), index.data_ptr(), count.data_ptr(), _stream())
+    return values, index, count

@@ -1,0 +1,298 @@
+"""GPU parity: the sm_100a path (through the C ABI) against the oracle and the committed golden vectors.
+
+Tolerance (BASELINE.json north_star): bf16 output within relative-L2 <= 1e-2 and cosine >= 0.999 of the
+fp32 reference forward on identical weights and inputs; RoPE position indexing bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import ltx_oracle as O
+import mlx_video_b200 as M
+from conftest import cosine, rel_l2
+from mlx_video_b200 import sampler
+from test_oracle_golden import CASES
+
+pytestmark = pytest.mark.gpu
+REL_L2_TOL, COS_TOL = 1e-2, 0.999
+DEV = "cuda:0"
+
+
+def product_config(cfg: O.OracleConfig) -> M.LTXModelConfig:
+    d = {k: getattr(cfg, k) for k in cfg.__dataclass_fields__}
+    d["model_type"] = d["model_type"].value
+    d["rope_type"] = d["rope_type"].value
+    return M.LTXModelConfig.from_dict(d)
+
+
+def build(cfg: O.OracleConfig, tensors, **kw) -> M.LTXModel:
+    model = M.LTXModel(product_config(cfg), device=DEV, **kw)
+    model.load_weights(tensors, strict=True)
+    return model
+
+
+def bf16_round(tensors):
+    """The GPU model stores weights in bf16; give the oracle the SAME (rounded) weights so the comparison
+    measures the arithmetic, not the storage rounding."""
+    out = {}
+    for k, v in tensors.items():
+        out[k] = v.to(torch.bfloat16).float() if (k.endswith(".weight") and not k.endswith("_norm.weight")) else v
+    return out
+
+
+def to_dev(m: O.Modality, dtype=torch.float32):
+    if m is None:
+        return None
+    return M.Modality(latent=m.latent.to(DEV, dtype), timesteps=m.timesteps.to(DEV), positions=m.positions.to(DEV),
+                      context=m.context.to(DEV, dtype), enabled=m.enabled,
+                      context_mask=None if m.context_mask is None else m.context_mask.to(DEV))
+
+
+def assert_close(got, want, what):
+    r, c = rel_l2(got.float(), want), cosine(got.float(), want)
+    assert torch.isfinite(got.float()).all(), f"{what}: non-finite output"
+    assert r <= REL_L2_TOL and c >= COS_TOL, f"{what}: rel_l2={r:.3e} cos={c:.6f}"
+    return r
+
+
+def golden_modalities(g):
+    def mod(p):
+        if p + "latent" not in g:
+            return None
+        cm = torch.from_numpy(g[p + "context_mask"]) if p + "context_mask" in g else None
+        return O.Modality(torch.from_numpy(g[p + "latent"]), torch.from_numpy(g[p + "timesteps"]),
+                          torch.from_numpy(g[p + "positions"]), torch.from_numpy(g[p + "context"]), True, cm)
+    return mod("v_"), mod("a_")
+
+
+@pytest.mark.parametrize("dedupe", [True, False])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_model_against_reference_golden(golden, name, dedupe):
+    """Outputs of the REFERENCE's own code (golden fixtures) vs the CUDA model on the same weights/inputs."""
+    g = golden(f"model_{name}")
+    mt, L = CASES[name]
+    cfg = O.small_config(mt, num_layers=L)
+    model = build(cfg, O.init_params(cfg, seed=int(g["seed"])), dedupe_timesteps=dedupe)
+    video, audio = golden_modalities(g)
+    vx, ax = model(video=to_dev(video), audio=to_dev(audio))
+    model.check_timestep_groups()
+    if video is not None:
+        assert vx.shape == g["v_out"].shape and vx.dtype == torch.float32
+        assert_close(vx, torch.from_numpy(g["v_out"]), f"{name} video")
+    else:
+        assert vx is None
+    if audio is not None:
+        assert_close(ax, torch.from_numpy(g["a_out"]), f"{name} audio")
+    else:
+        assert ax is None
+
+
+def test_block_against_reference_golden(golden):
+    g = golden("block_video")
+    cfg = O.small_config(O.LTXModelType.VideoOnly, num_layers=1)
+    model = build(cfg, O.init_params(cfg, seed=int(g["seed"])))
+    t = lambda k, dt=torch.float32: torch.from_numpy(g[k]).to(DEV, dt)  # noqa: E731
+    args = M.TransformerArgs(x=t("x_in"), context=t("context", torch.bfloat16), context_mask=None, timesteps=t("timesteps"),
+                             embedded_timestep=torch.zeros(1, 1, 512, device=DEV), positional_embeddings=(t("cos"), t("sin")))
+    x_before = args.x.clone()
+    out, none = model.transformer_blocks[0](video=args, audio=None)
+    assert none is None and torch.equal(args.x, x_before), "block must not mutate its input (reference value semantics)"
+    assert_close(out.x, torch.from_numpy(g["x_out"]), "block")
+
+
+def test_production_width_block_vs_oracle():
+    """BASELINE config 1: ONE LTX-2 block at production width (D=4096, 32x128 heads), 512x512x33 ->
+    16x16x5 = 1280 tokens, 128 text tokens, sigma 0.725, seed 0."""
+    cfg = O.OracleConfig(num_layers=1)
+    tensors = bf16_round(O.init_params(cfg, seed=0))
+    g = torch.Generator().manual_seed(1)
+    T, Tc, D = 1280, 128, 4096
+    x = torch.randn(1, T, D, generator=g)
+    ctx = torch.randn(1, Tc, D, generator=g).to(torch.bfloat16).float()
+    ts = 0.1 * torch.randn(1, 1, 6 * D, generator=g)
+    pos = torch.from_numpy(O.create_position_grid(1, 5, 16, 16))
+    pe = O.precompute_freqs_cis(pos, D, 10000.0, [20, 2048, 2048], True, 32, O.LTXRopeType.SPLIT, True)
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    oracle = O.OracleLTXModel(cfg, tensors)
+    want, _ = oracle.block(0, O.TransformerArgs(x, ctx, None, ts.expand(1, T, 6 * D), None, pe, None, None, None, True), None)
+    model = build(cfg, tensors)
+    args = M.TransformerArgs(x=x.to(DEV), context=ctx.to(DEV, torch.bfloat16), context_mask=None, timesteps=ts.to(DEV),
+                             embedded_timestep=torch.zeros(1, 1, D, device=DEV),
+                             positional_embeddings=(pe[0].to(DEV), pe[1].to(DEV)))
+    got, _ = model.transformer_blocks[0](video=args, audio=None)
+    r = assert_close(got.x, want.x, "production-width block")
+    # the residual stream dominates x; also require the block's UPDATE (x_out - x_in) to match
+    assert_close(got.x.cpu() - x, want.x - x, "production-width block update")
+    print(f"production block rel_l2={r:.3e}")
+
+
+@pytest.mark.parametrize("mt,L,B,grid,Tc,Ta", [
+    (O.LTXModelType.VideoOnly, 4, 1, (4, 8, 10), 40, 0),     # T=320, ragged vs the 128-row tiles
+    (O.LTXModelType.VideoOnly, 2, 2, (3, 7, 9), 72, 0),      # B=2 (cfg_batch), T=189, Tc not a tile multiple
+    (O.LTXModelType.AudioVideo, 3, 1, (3, 8, 8), 64, 37),    # joint audio+video, Ta=37
+    (O.LTXModelType.AudioVideo, 1, 2, (2, 5, 5), 16, 130),   # audio longer than one KV tile
+])
+def test_model_vs_oracle_seeded(mt, L, B, grid, Tc, Ta):
+    cfg = O.small_config(mt, num_layers=L)
+    tensors = bf16_round(O.init_params(cfg, seed=L * 10 + B))
+    g = torch.Generator().manual_seed(99)
+    F_, H_, W_ = grid
+    T = F_ * H_ * W_
+    ts = torch.full((B, T), 0.725)
+    ts[:, :H_ * W_] = 0.0  # conditioned first frame
+    video = O.Modality(torch.randn(B, T, 128, generator=g), ts, torch.from_numpy(O.create_position_grid(B, F_, H_, W_)),
+                       torch.randn(B, Tc, 256, generator=g))
+    audio = None
+    if mt == O.LTXModelType.AudioVideo:
+        audio = O.Modality(torch.randn(B, Ta, 128, generator=g), torch.full((B, Ta), 0.725),
+                           torch.from_numpy(O.create_audio_position_grid(B, Ta)), torch.randn(B, Tc, 256, generator=g))
+    wv, wa = O.OracleLTXModel(cfg, tensors)(video, audio)
+    model = build(cfg, tensors)
+    gv, ga = model(video=to_dev(video), audio=to_dev(audio))
+    model.check_timestep_groups()
+    assert_close(gv, wv, "video")
+    if audio is not None:
+        assert_close(ga, wa, "audio")
+    # bf16 latents in -> bf16 velocity out (the reference returns the model dtype)
+    gv16, _ = model(video=to_dev(video, torch.bfloat16), audio=to_dev(audio, torch.bfloat16))
+    assert gv16.dtype == torch.bfloat16
+    assert_close(gv16, wv, "video bf16 io")
+
+
+def test_timestep_broadcast_forms_agree():
+    """Modality.timesteps may be (B, T) or (B, 1) (ltx.py:68-73; transformer.py:160-164)."""
+    cfg = O.small_config(O.LTXModelType.VideoOnly, num_layers=2)
+    model = build(cfg, O.init_params(cfg, seed=5))
+    g = torch.Generator().manual_seed(6)
+    B, T = 2, 96
+    base = dict(latent=torch.randn(B, T, 128, generator=g).to(DEV), positions=torch.from_numpy(O.create_position_grid(B, 2, 6, 8)).to(DEV),
+                context=torch.randn(B, 24, 256, generator=g).to(DEV))
+    sig = torch.tensor([[0.9], [0.3]], device=DEV)
+    a, _ = model(video=M.Modality(timesteps=sig, **base))
+    b, _ = model(video=M.Modality(timesteps=sig.expand(B, T).contiguous(), **base))
+    model.dedupe_timesteps = False
+    c, _ = model(video=M.Modality(timesteps=sig.expand(B, T).contiguous(), **base))
+    assert torch.equal(a, b) and torch.equal(a, c), "dedupe / broadcast forms must be bit-identical"
+
+
+def test_timestep_capacity_overflow_is_loud():
+    cfg = O.small_config(O.LTXModelType.VideoOnly, num_layers=1)
+    model = build(cfg, O.init_params(cfg, seed=5), timestep_capacity=4)
+    B, T = 1, 48
+    m = M.Modality(latent=torch.zeros(B, T, 128, device=DEV), timesteps=torch.linspace(0, 1, T, device=DEV).reshape(B, T),
+                   positions=torch.from_numpy(O.create_position_grid(B, 1, 6, 8)).to(DEV), context=torch.zeros(B, 8, 256, device=DEV))
+    out, _ = model(video=m)
+    assert torch.isnan(out).all()
+    with pytest.raises(M.LtxbError):
+        model.check_timestep_groups()
+
+
+def test_rope_table_kernel_vs_oracle(golden):
+    for grid, dim, heads, max_pos, audio in [((1, 5, 16, 16), 4096, 32, [20, 2048, 2048], False), ((2, 3, 4, 6), 512, 4, [20, 2048, 2048], False),
+                                             ((1, 68), 2048, 32, [20], True), ((1, 21), 256, 4, [20], True)]:
+        pos = O.create_audio_position_grid(*grid) if audio else O.create_position_grid(*grid)
+        c, s = M.precompute_freqs_cis(torch.from_numpy(pos).to(DEV), dim, 10000.0, max_pos, True, heads, M.LTXRopeType.SPLIT, True)
+        wc, ws = O.precompute_freqs_cis(torch.from_numpy(pos), dim, 10000.0, max_pos, True, heads, O.LTXRopeType.SPLIT, True)
+        assert c.shape == wc.shape and c.dtype == torch.float32
+        # position -> (head, slot) indexing is exact: the identity pads sit in exactly the same slots ...
+        assert torch.equal(c.cpu() == 1.0, wc == 1.0) or float((c.cpu() - wc).abs().max()) < 1e-6
+        pad = dim // 2 - (dim // (2 * pos.shape[1])) * pos.shape[1]
+        flat_c = c.cpu().permute(0, 2, 1, 3).reshape(c.shape[0], c.shape[2], -1)
+        assert torch.all(flat_c[..., :pad] == 1.0)
+        # ... and the angles agree to fp32 sin/cos rounding (device sincosf vs host libm)
+        assert float((c.cpu() - wc).abs().max()) <= 2e-6 and float((s.cpu() - ws).abs().max()) <= 2e-6
+
+
+def test_sampler_matches_oracle_loop():
+    """denoise_distilled / denoise_dev (CFG, cfg_batch, I2V mask) vs the same loops written with the oracle."""
+    cfg = O.small_config(O.LTXModelType.VideoOnly, num_layers=2)
+    tensors = bf16_round(O.init_params(cfg, seed=21))
+    model = build(cfg, tensors)
+    oracle = O.OracleLTXModel(cfg, tensors)
+    g = torch.Generator().manual_seed(22)
+    b, c, f, h, w = 1, 128, 3, 4, 6
+    lat = torch.randn(b, c, f, h, w, generator=g)
+    pos_np = O.create_position_grid(b, f, h, w)
+    ctx_p, ctx_n = torch.randn(b, 16, 256, generator=g), torch.randn(b, 16, 256, generator=g)
+
+    def oracle_loop(sigmas, cfg_scale=1.0, mask=None, clean=None):
+        x = lat.clone()
+        pe = O.precompute_freqs_cis(torch.from_numpy(pos_np), 512, 10000.0, [20, 2048, 2048], True, 4, O.LTXRopeType.SPLIT, True)
+        tm = torch.ones(b, f * h * w) if mask is None else mask.reshape(b, 1, f, 1, 1).expand(b, 1, f, h, w).reshape(b, -1)
+        for i in range(len(sigmas) - 1):
+            s, sn = float(sigmas[i]), float(sigmas[i + 1])
+            flat = x.reshape(b, c, -1).transpose(1, 2)
+            mk = lambda ctx: O.Modality(flat, s * tm, torch.from_numpy(pos_np), ctx, True, None, pe)  # noqa: E731
+            v, _ = oracle(mk(ctx_p), None)
+            if cfg_scale != 1.0:
+                vn, _ = oracle(mk(ctx_n), None)
+                v = O.cfg_combine(v, vn, cfg_scale)
+            v = v.transpose(1, 2).reshape(b, c, f, h, w)
+            den = O.to_denoised(x, v, s)
+            if mask is not None:
+                den = O.apply_denoise_mask(den, clean, mask)
+            x = O.euler_step(x, den, s, sn) if sn > 0 else den
+        return x
+
+    sig = sampler.STAGE_2_SIGMAS
+    got, none = sampler.denoise_distilled(lat.to(DEV), pos_np, ctx_p.to(DEV), model, sig)
+    assert none is None
+    assert_close(got, oracle_loop(sig), "denoise_distilled")
+    sig = sampler.ltx2_scheduler(3, f * h * w)
+    want = oracle_loop(sig, cfg_scale=4.5)
+    for cfg_batch in (False, True):
+        got = sampler.denoise_dev(lat.to(DEV), pos_np, ctx_p.to(DEV), ctx_n.to(DEV), model, sig, cfg_scale=4.5, cfg_batch=cfg_batch)
+        assert_close(got, want, f"denoise_dev cfg_batch={cfg_batch}")
+    mask = torch.ones(b, 1, f, 1, 1)
+    mask[:, :, 0] = 0
+    clean = torch.randn(b, c, f, h, w, generator=g)
+    state = sampler.LatentState(latent=lat.to(DEV), clean_latent=clean.to(DEV), denoise_mask=mask.to(DEV))
+    got, _ = sampler.denoise_distilled(lat.to(DEV), pos_np, ctx_p.to(DEV), model, sampler.STAGE_2_SIGMAS, state=state)
+    want = oracle_loop(sampler.STAGE_2_SIGMAS, mask=mask, clean=clean)
+    assert_close(got, want, "denoise_distilled i2v")
+    assert torch.allclose(got[:, :, 0].cpu(), clean[:, :, 0], atol=1e-6), "conditioned frame must stay clean"
+
+
+def test_x0_model_and_errors():
+    cfg = O.small_config(O.LTXModelType.VideoOnly, num_layers=1)
+    tensors = bf16_round(O.init_params(cfg, seed=8))
+    model = build(cfg, tensors)
+    g = torch.Generator().manual_seed(9)
+    T = 40
+    ts = torch.rand(1, T, generator=g)
+    m = O.Modality(torch.randn(1, T, 128, generator=g), ts, torch.from_numpy(O.create_position_grid(1, 2, 4, 5)), torch.randn(1, 8, 256, generator=g))
+    want, _ = O.x0_model(O.OracleLTXModel(cfg, tensors), m, None)
+    got, none = M.X0Model(model)(video=to_dev(m), audio=None)
+    assert none is None
+    assert_close(got, want, "x0")
+    with pytest.raises(ValueError):  # ltx.py:468-469
+        model(video=None, audio=to_dev(m))
+    with pytest.raises(M.LtxbError):  # CPU tensors: no fallback
+        model(video=M.Modality(m.latent, m.timesteps, m.positions, m.context))
+    with pytest.raises(ValueError):  # strict load, ltx.py:874-881
+        model.load_weights({k: v for k, v in tensors.items() if "attn2" not in k}, strict=True)
+    with pytest.raises(AssertionError):  # rope.py:228
+        M.precompute_freqs_cis(torch.zeros(1, 2, 4, 2, device=DEV), 512, 10000.0, [20, 2048, 2048], True, 4, M.LTXRopeType.SPLIT, True)
+
+
+def test_reference_attention_and_ff_signatures():
+    """Un-fused module calls with the reference's signatures (attention.py:102-110, feed_forward.py:35-40)."""
+    cfg = O.small_config(O.LTXModelType.VideoOnly, num_layers=1)
+    tensors = bf16_round(O.init_params(cfg, seed=12))
+    model = build(cfg, tensors)
+    blk = model.transformer_blocks[0]
+    p = O.Params(tensors).sub("transformer_blocks.0")
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(2, 50, 512, generator=g).to(torch.bfloat16)
+    ctx = torch.randn(2, 20, 512, generator=g).to(torch.bfloat16)
+    pos = torch.from_numpy(O.create_position_grid(2, 2, 5, 5))
+    pe = O.precompute_freqs_cis(pos, 512, 10000.0, [20, 2048, 2048], True, 4, O.LTXRopeType.SPLIT, True)
+    want = O.attention(p.sub("attn1"), x.float(), 4, cfg.rope_type, cfg.norm_eps, pe=pe)
+    got = blk.attn1(x.to(DEV), pe=(pe[0].to(DEV), pe[1].to(DEV)))
+    assert_close(got, want, "attn1")
+    mask = torch.ones(2, 20, dtype=torch.int32)
+    mask[:, 15:] = 0
+    fmask = ((mask.float() - 1) * 1e9).reshape(2, 1, 1, 20)
+    want = O.attention(p.sub("attn2"), x.float(), 4, cfg.rope_type, cfg.norm_eps, context=ctx.float(), mask=fmask)
+    got = blk.attn2(x.to(DEV), context=ctx.to(DEV), mask=fmask.to(DEV))
+    assert_close(got, want, "attn2 masked")
+    assert_close(blk.ff(x.to(DEV)), O.feed_forward(p.sub("ff"), x.float()), "ff")
