@@ -53,7 +53,7 @@ def create_position_grid(batch_size: int, num_frames: int, height: int, width: i
     if causal_fix:
         px[0] = np.clip(px[0] + 1 - temporal_scale, a_min=0, a_max=None)
     px[0] = px[0] / fps
-    return np.ascontiguousarray(np.broadcast_to(px[None], (batch_size, 3, T, 2)), dtype=np.float32)
+    return np.array(np.broadcast_to(px[None], (batch_size, 3, T, 2)), dtype=np.float32, order="C", copy=True)
 
 
 def create_audio_position_grid(batch_size: int, audio_frames: int, sample_rate: int = AUDIO_LATENT_SAMPLE_RATE,
@@ -68,7 +68,7 @@ def create_audio_position_grid(batch_size: int, audio_frames: int, sample_rate: 
         return mel * hop_length / sample_rate
 
     pos = np.stack([seconds(0), seconds(1)], axis=-1)[None, None]
-    return np.ascontiguousarray(np.broadcast_to(pos, (batch_size, 1, audio_frames, 2)), dtype=np.float32)
+    return np.array(np.broadcast_to(pos, (batch_size, 1, audio_frames, 2)), dtype=np.float32, order="C", copy=True)
 
 
 def compute_audio_frames(num_video_frames: int, fps: float) -> int:
