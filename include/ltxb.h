@@ -85,6 +85,15 @@ int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void*
                    int32_t N, int32_t K, const ltxb_epilogue* epi, int32_t block_n, int32_t cta_pair,
                    void* stream);
 
+/* Stream-K scheduling scratch for ltxb_gemm_bf16.  The library never allocates: the host hands it one device
+ * buffer of ltxb_gemm_workspace_bytes() per device (kept until replaced; NULL unregisters).  With a workspace
+ * registered, problems whose tile count leaves a ragged last wave on the 148 SMs (M = 1280 tokens ...) are cut
+ * into equal k-block ranges per SM; tiles cut across SMs are summed in k order by the last contributor to
+ * arrive (bit-reproducible).  Without one, every GEMM runs data-parallel.  GEMMs sharing a workspace must be
+ * issued on one stream. */
+int64_t ltxb_gemm_workspace_bytes(void);
+int ltxb_gemm_set_workspace(void* workspace, int64_t bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K3 + AdaLN modulate   rms_norm(x) * (1 + scale) + shift   (utils.py:398-400; transformer.py:253,
  *                       257,315-325,346)   x f32 [R, D] (ldx) -> out bf16 [R, D] (ldo)

@@ -50,6 +50,52 @@ struct GemmParams {
   int gate_row_div;
   const int* gate_row_index;
   const float* gate_table;
+  // stream-K (sk == 0: data-parallel tile striding)
+  int sk;
+  int total_units;     // num_tiles * (K / kBlockK)
+  float* sk_partials;  // [clusters][2][ctas][kBlockM * block_n] fp32 partial accumulators
+  int* sk_counters;    // [num_tiles][ctas] arrivals per output tile; zero outside a launch
+};
+
+// One unit = one 64-wide k-block of one output tile.  Data-parallel mode hands whole tiles to clusters
+// round-robin; stream-K mode cuts the linear (tile, k-block) space into equal contiguous ranges, one per
+// cluster, so every SM works the same number of k-blocks whatever the tile count (M = 1280 gives 80 tiles
+// for 74 SM pairs: 2 waves data-parallel, 1.08 stream-K).  A tile cut across clusters is finished by
+// whichever contributor arrives last, summing the partials in k order (deterministic, no spinning).
+struct WorkItem {
+  int tile, kb0, kb1;
+};
+__device__ __forceinline__ int sk_unit_begin(int total_units, int slots, int c) {
+  return static_cast<int>((static_cast<long long>(total_units) * c) / slots);
+}
+__device__ __forceinline__ int sk_cluster_of(int total_units, int slots, int unit) {
+  int c = static_cast<int>((static_cast<long long>(unit) * slots) / total_units);
+  while (c + 1 < slots && sk_unit_begin(total_units, slots, c + 1) <= unit) ++c;
+  while (c > 0 && sk_unit_begin(total_units, slots, c) > unit) --c;
+  return c;
+}
+struct WorkIter {
+  int sk, num_kb, num_tiles, stride, tile, u, u_end;
+  __device__ WorkIter(const GemmParams& p, int cluster_id, int num_clusters, int num_kb_)
+      : sk(p.sk), num_kb(num_kb_), num_tiles(p.num_m_tiles * p.num_n_tiles), stride(num_clusters), tile(cluster_id) {
+    u = sk ? sk_unit_begin(p.total_units, num_clusters, cluster_id) : 0;
+    u_end = sk ? sk_unit_begin(p.total_units, num_clusters, cluster_id + 1) : 0;
+  }
+  __device__ __forceinline__ bool next(WorkItem& w) {
+    if (!sk) {
+      if (tile >= num_tiles) return false;
+      w.tile = tile, w.kb0 = 0, w.kb1 = num_kb;
+      tile += stride;
+      return true;
+    }
+    if (u >= u_end) return false;
+    w.tile = u / num_kb;
+    w.kb0 = u - w.tile * num_kb;
+    const int len = min(num_kb - w.kb0, u_end - u);
+    w.kb1 = w.kb0 + len;
+    u += len;
+    return true;
+  }
 };
 
 struct GemmSmemHeader {
@@ -58,8 +104,11 @@ struct GemmSmemHeader {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
+  int sk_arrival;  // stream-K: this CTA's arrival number on the current tile
 };
 static_assert(sizeof(GemmSmemHeader) <= kSmemHeader, "header overflow");
+
+__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // Apply the fused epilogue to `n` (16 or 32) consecutive accumulator columns of one output row.
 template <int kEpi, int kCols>
@@ -183,12 +232,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_tile = tile % p.num_m_tiles;
-        const int n_tile = tile / p.num_m_tiles;
+      WorkIter it(p, cluster_id, num_clusters, num_kb);
+      WorkItem w;
+      while (it.next(w)) {
+        const int m_tile = w.tile % p.num_m_tiles;
+        const int n_tile = w.tile / p.num_m_tiles;
         const int m0 = (m_tile * kCtas + static_cast<int>(cta_rank)) * kBlockM;
         const int n0 = n_tile * bn + static_cast<int>(cta_rank) * bn_load;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&hdr->empty[stage], phase ^ 1);
           uint8_t* sa = tiles + static_cast<size_t>(stage) * stage_bytes;
           uint8_t* sw = sa + a_bytes;
@@ -218,11 +269,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0 && is_leader) {
       const uint32_t idesc = make_idesc_bf16(kBlockM * kCtas, bn, 0, 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      WorkIter it(p, cluster_id, num_clusters, num_kb);
+      WorkItem w;
+      while (it.next(w)) {
         mbar_wait(&hdr->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&hdr->full[stage], phase);
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(tiles + static_cast<size_t>(stage) * stage_bytes);
@@ -231,7 +284,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advancing 16 elements (32 B) along K inside the 128-B swizzle span = +2 in the address field
-            umma_bf16_ss<kCtas>(d_tmem, adesc + 2 * k, wdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss<kCtas>(d_tmem, adesc + 2 * k, wdesc + 2 * k, idesc, (kb != w.kb0 || k != 0) ? 1u : 0u);
           }
           if constexpr (kCtas == 1) umma_commit(&hdr->empty[stage]); else umma_commit_pair(&hdr->empty[stage], 3);
           if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
@@ -243,11 +296,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else {
     // ===================== epilogue warps =====================
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
+    const int row_in_cta = quarter * 32 + lane;
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m_tile = tile % p.num_m_tiles;
-      const int n_tile = tile / p.num_m_tiles;
-      const long long row = static_cast<long long>(m_tile * kCtas + static_cast<int>(cta_rank)) * kBlockM + quarter * 32 + lane;
+    auto release_acc = [&]() {  // all of this warp's TMEM reads of the accumulator have completed
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCtas == 1) mbar_arrive(&hdr->tmem_empty[acc]); else mbar_arrive_remote(&hdr->tmem_empty[acc], 0);
+      }
+    };
+    WorkIter it(p, cluster_id, num_clusters, num_kb);
+    WorkItem w;
+    while (it.next(w)) {
+      const int m_tile = w.tile % p.num_m_tiles;
+      const int n_tile = w.tile / p.num_m_tiles;
+      const long long row = static_cast<long long>(m_tile * kCtas + static_cast<int>(cta_rank)) * kBlockM + row_in_cta;
       const int n0 = n_tile * bn;
       const bool row_ok = row < p.M;
       long long grow = 0;
@@ -255,41 +318,102 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (row_ok && p.gate != nullptr)
           grow = p.gate_row_index != nullptr ? p.gate_row_index[row] : row / p.gate_row_div;
       }
+      const bool partial = (w.kb0 > 0) || (w.kb1 < num_kb);
       mbar_wait(&hdr->tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccStride;
-      for (int c = 0; c < bn; c += 32) {
-        const bool last = (c + 32 >= bn);
-        if (c + 32 <= bn) {
-          uint32_t r[32];
-          tmem_ld_x32(t_row + c, r);
-          tmem_wait_ld();
-          if (last) {
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) {
-              if constexpr (kCtas == 1) mbar_arrive(&hdr->tmem_empty[acc]); else mbar_arrive_remote(&hdr->tmem_empty[acc], 0);
+      if (!partial) {
+        for (int c = 0; c < bn; c += 32) {
+          const bool last = (c + 32 >= bn);
+          const int col = n0 + c;
+          if (c + 32 <= bn) {
+            uint32_t r[32];
+            tmem_ld_x32(t_row + c, r);
+            tmem_wait_ld();
+            if (last) release_acc();
+            if (row_ok) {
+              if (col + 32 <= p.N) {
+                epilogue_store<kEpi, 32>(p, r, row, col, grow);
+              } else if (col + 16 <= p.N) {
+                epilogue_store<kEpi, 16>(p, r, row, col, grow);
+              }
+            }
+          } else {  // 16-column tail of a BN that is not a multiple of 32
+            uint32_t r[16];
+            tmem_ld_x16(t_row + c, r);
+            tmem_wait_ld();
+            release_acc();
+            if (row_ok && col + 16 <= p.N) epilogue_store<kEpi, 16>(p, r, row, col, grow);
+          }
+        }
+      } else {
+        // ---- stream-K: this cluster holds only k-blocks [kb0, kb1) of the tile.
+        // 1. park the fp32 partial in this cluster's slot ([32-col chunk][row][32] so a thread's 128 B are contiguous)
+        const size_t slot_elems = static_cast<size_t>(kBlockM) * bn;
+        auto slot_of = [&](int cluster, bool head) {
+          return p.sk_partials + (static_cast<size_t>(cluster * 2 + (head ? 0 : 1)) * kCtas + cta_rank) * slot_elems;
+        };
+        float* mine = slot_of(cluster_id, w.kb0 > 0);
+        for (int c = 0; c < bn; c += 32) {
+          const bool last = (c + 32 >= bn);
+          float4* dst = reinterpret_cast<float4*>(mine + static_cast<size_t>(c / 32) * (kBlockM * 32) + row_in_cta * 32);
+          if (c + 32 <= bn) {
+            uint32_t r[32];
+            tmem_ld_x32(t_row + c, r);
+            tmem_wait_ld();
+            if (last) release_acc();
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              __stcg(dst + i, make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+          } else {
+            uint32_t r[16];
+            tmem_ld_x16(t_row + c, r);
+            tmem_wait_ld();
+            release_acc();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              __stcg(dst + i, make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+          }
+        }
+        // 2. announce it; the LAST contributor to arrive owns the tile's epilogue
+        __threadfence();
+        epilogue_bar_sync();
+        int* counter = p.sk_counters + w.tile * kCtas + static_cast<int>(cta_rank);
+        if (row_in_cta == 0) hdr->sk_arrival = atomicAdd(counter, 1);
+        epilogue_bar_sync();
+        const int tile_u0 = w.tile * num_kb;
+        const int first_c = sk_cluster_of(p.total_units, num_clusters, tile_u0);
+        const int last_c = sk_cluster_of(p.total_units, num_clusters, tile_u0 + num_kb - 1);
+        if (*reinterpret_cast<volatile int*>(&hdr->sk_arrival) == last_c - first_c) {
+          __threadfence();
+          // 3. sum every contributor's partial in k order (fixed order: bit-reproducible) and finish the tile
+          for (int c = 0; c < bn; c += 32) {
+            const int width = (c + 32 <= bn) ? 32 : 16;
+            float accv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) accv[i] = 0.f;
+            for (int cc = first_c; cc <= last_c; ++cc) {
+              const bool head = sk_unit_begin(p.total_units, num_clusters, cc) > tile_u0;
+              const float4* src = reinterpret_cast<const float4*>(slot_of(cc, head) + static_cast<size_t>(c / 32) * (kBlockM * 32) + row_in_cta * 32);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (i * 4 < width) {
+                  const float4 v = __ldcg(src + i);
+                  accv[4 * i] += v.x, accv[4 * i + 1] += v.y, accv[4 * i + 2] += v.z, accv[4 * i + 3] += v.w;
+                }
+              }
+            }
+            const int col = n0 + c;
+            if (row_ok) {
+              const uint32_t* r = reinterpret_cast<const uint32_t*>(accv);
+              if (width == 32 && col + 32 <= p.N) {
+                epilogue_store<kEpi, 32>(p, r, row, col, grow);
+              } else if (col + 16 <= p.N) {
+                epilogue_store<kEpi, 16>(p, r, row, col, grow);
+              }
             }
           }
-          const int col = n0 + c;
-          if (row_ok) {
-            if (col + 32 <= p.N) {
-              epilogue_store<kEpi, 32>(p, r, row, col, grow);
-            } else if (col + 16 <= p.N) {
-              epilogue_store<kEpi, 16>(p, r, row, col, grow);
-            }
-          }
-        } else {  // 16-column tail of a BN that is not a multiple of 32
-          uint32_t r[16];
-          tmem_ld_x16(t_row + c, r);
-          tmem_wait_ld();
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (kCtas == 1) mbar_arrive(&hdr->tmem_empty[acc]); else mbar_arrive_remote(&hdr->tmem_empty[acc], 0);
-          }
-          const int col = n0 + c;
-          if (row_ok && col + 16 <= p.N) epilogue_store<kEpi, 16>(p, r, row, col, grow);
+          if (row_in_cta == 0) *counter = 0;  // ready for the next launch
         }
       }
       if (++acc == 2) acc = 0, acc_phase ^= 1;
@@ -338,6 +462,46 @@ static TileChoice choose_tile(int M, int N, int sms, int want_bn, int want_pair)
     }
   }
   return best;
+}
+
+// ---- stream-K workspace: registered by the host framework (the library never allocates) -----------
+constexpr int kMaxDevices = 16;
+constexpr long long kSkCounterInts = 1 << 16;                                  // arrivals: [tiles][ctas]
+constexpr long long kSkPartialBytes = 148ll * 2 * kBlockM * 256 * sizeof(float);  // [<=148 CTAs][2 slots][128 x 256] fp32
+struct SkWorkspace {
+  int* counters = nullptr;
+  float* partials = nullptr;
+};
+static SkWorkspace g_sk_ws[kMaxDevices];
+
+struct SkChoice {
+  bool use;
+  int block_n, ctas;
+};
+// Stream-K pays when data-parallel tiling leaves a ragged last wave.  Costs in k-block units per cluster; a cut
+// tile costs its finisher one L2 round trip per contributor (~2 k-blocks each).
+static SkChoice choose_stream_k(int M, int N, int K, int sms, int want_bn, int want_pair, const TileChoice& dp) {
+  SkChoice none{false, 0, 0};
+  if (want_bn > 0) return none;  // an explicit tile request means "run exactly this" (tests, sweeps)
+  const int ctas = (want_pair == 0 || (want_pair < 0 && M <= kBlockM)) ? 1 : 2;
+  const int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
+  if (bn < 32) return none;
+  const int slots = sms / ctas;
+  const int num_kb = K / kBlockK;
+  const long long tiles = 1ll * ((M + kBlockM * ctas - 1) / (kBlockM * ctas)) * ((N + bn - 1) / bn);
+  if (tiles * ctas > kSkCounterInts || tiles * num_kb > (1ll << 30)) return none;
+  const long long units = tiles * num_kb;
+  const long long per = (units + slots - 1) / slots;
+  if (per < 8) return none;  // slivers: the fix-up traffic would dominate
+  const long long contributors = (num_kb + per - 1) / per + 1;
+  const double t_sk = static_cast<double>(per) + 4.0 + 2.0 * static_cast<double>(contributors);
+  // the data-parallel alternative, in the same units (per-tile time is ~independent of BN below 256: the
+  // SS-mode A-operand read paces the MMA)
+  const int dp_slots = sms / dp.ctas;
+  const long long dp_tiles = 1ll * ((M + kBlockM * dp.ctas - 1) / (kBlockM * dp.ctas)) * ((N + dp.block_n - 1) / dp.block_n);
+  const double t_dp = static_cast<double>((dp_tiles + dp_slots - 1) / dp_slots) * num_kb;
+  if (t_sk * 1.02 >= t_dp) return none;
+  return SkChoice{true, bn, ctas};
 }
 
 template <int kCtas, int kEpi>
@@ -416,8 +580,14 @@ extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   if (block_n == 0) block_n = env_bn;
   const TileChoice tc = choose_tile(M, N, sms, block_n, cta_pair);
   if (tc.block_n == 0) return set_error(LTXB_ERR_UNSUPPORTED, "ltxb_gemm_bf16: no tile for M=%d N=%d", M, N);
-  const int ctas = tc.ctas;
-  const int bn = tc.block_n;
+  static const int env_sk = [] { const char* e = getenv("LTXB_GEMM_STREAMK"); return e ? atoi(e) : 1; }();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const SkWorkspace ws = (dev >= 0 && dev < kMaxDevices) ? g_sk_ws[dev] : SkWorkspace{};
+  SkChoice sk{false, 0, 0};
+  if (env_sk && ws.partials != nullptr) sk = choose_stream_k(M, N, K, sms, block_n, cta_pair, tc);
+  const int ctas = sk.use ? sk.ctas : tc.ctas;
+  const int bn = sk.use ? sk.block_n : tc.block_n;
   if (ctas == 2) LTXB_CHECK_SUPPORTED(bn % 16 == 0 && (bn / 2) % 8 == 0, "pair mode needs block_n %% 16 == 0");
 
   GemmParams p{};
@@ -456,9 +626,35 @@ extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
     if (rc) return rc;
   }
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int clusters = std::min(num_tiles, sms / ctas);
+  int clusters = std::min(num_tiles, sms / ctas);
+  if (sk.use) {
+    clusters = sms / ctas;
+    p.sk = 1;
+    p.total_units = num_tiles * (K / kBlockK);
+    p.sk_partials = ws.partials;
+    p.sk_counters = ws.counters;
+  }
   const int grid = clusters * ctas;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (ctas == 2) return dispatch_epi<2>(epi->mode, ta, tw, p, grid, smem, s);
   return dispatch_epi<1>(epi->mode, ta, tw, p, grid, smem, s);
+}
+
+extern "C" int64_t ltxb_gemm_workspace_bytes(void) { return kSkCounterInts * sizeof(int) + kSkPartialBytes; }
+
+extern "C" int ltxb_gemm_set_workspace(void* workspace, int64_t bytes, void* stream) {
+  int dev = 0;
+  LTXB_CUDA(cudaGetDevice(&dev));
+  LTXB_CHECK_SUPPORTED(dev >= 0 && dev < kMaxDevices, "ltxb_gemm_set_workspace: device %d out of range", dev);
+  if (workspace == nullptr) {
+    g_sk_ws[dev] = SkWorkspace{};
+    return LTXB_OK;
+  }
+  LTXB_CHECK_ARG(aligned16(workspace) && bytes >= ltxb_gemm_workspace_bytes(),
+                 "ltxb_gemm_set_workspace: need a 16-byte aligned buffer of at least %lld bytes",
+                 static_cast<long long>(ltxb_gemm_workspace_bytes()));
+  LTXB_CUDA(cudaMemsetAsync(workspace, 0, kSkCounterInts * sizeof(int), reinterpret_cast<cudaStream_t>(stream)));
+  g_sk_ws[dev].counters = reinterpret_cast<int*>(workspace);
+  g_sk_ws[dev].partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kSkCounterInts * sizeof(int));
+  return LTXB_OK;
 }

@@ -45,6 +45,9 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_gemm_workspaces: dict = {}  # device index -> the stream-K scratch buffer registered with the library
+
+
 def _prep(t: torch.Tensor) -> None:
     """Fail loudly on anything that is not a CUDA tensor; bind the library to the tensor's device."""
     if not t.is_cuda:
@@ -55,6 +58,10 @@ def _prep(t: torch.Tensor) -> None:
         check(lib.ltxb_device_check(), "ltxb_device_check")
         _device_set.clear()
         _device_set.add(idx)
+        if idx not in _gemm_workspaces:  # torch owns the memory, the library only borrows it
+            ws = torch.empty(lib.ltxb_gemm_workspace_bytes(), dtype=torch.uint8, device=t.device)
+            check(lib.ltxb_gemm_set_workspace(ws.data_ptr(), ws.numel(), _stream()), "ltxb_gemm_set_workspace")
+            _gemm_workspaces[idx] = ws
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:

@@ -1,0 +1,181 @@
+"""GPU: each C-ABI kernel against a plain PyTorch fp32 reference of the same op (tolerance in each test)."""
+import math
+
+import pytest
+import torch
+
+import mlx_video_b200  # noqa: F401
+from conftest import rel_l2
+from mlx_video_b200 import _lib, ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def gemm_case(M, N, K, mode, pair=-1, bn=0, seed=0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g)
+    acc = a.float() @ w.float().T + bias
+    kw = {}
+    if mode == _lib.EPI_BIAS_BF16:
+        ref, out = acc, torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    elif mode == _lib.EPI_GELU_BF16:
+        ref, out = torch.nn.functional.gelu(acc, approximate="tanh"), torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    elif mode == _lib.EPI_SILU_BF16:
+        ref, out = torch.nn.functional.silu(acc), torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    elif mode == _lib.EPI_BIAS_F32:
+        ref, out = acc, torch.empty(M, N, device=DEV, dtype=torch.float32)
+    else:
+        resid = torch.randn(M, N, device=DEV, generator=g)
+        div = 4
+        gate = torch.randn((M + div - 1) // div, 3 * N, device=DEV, generator=g)
+        table = torch.randn(N, device=DEV, generator=g)
+        gsl = gate[:, N:2 * N]
+        ref = resid + acc * (table + gsl[torch.arange(M, device=DEV) // div])
+        out = resid.clone()
+        kw = dict(resid=out, gate=gsl, gate_table=table, gate_row_div=div)
+    ops.gemm(a, w, bias, out, mode=mode, block_n=bn, cta_pair=pair, **kw)
+    torch.cuda.synchronize()
+    tol = 2e-5 if out.dtype == torch.float32 else 4e-3  # fp32 out: summation order only; bf16 out: output rounding
+    err = rel_l2(out.float(), ref)
+    assert torch.isfinite(out.float()).all() and err <= tol, f"gemm M={M} N={N} K={K} mode={mode} pair={pair} bn={bn}: {err:.3e}"
+    return out
+
+
+# (M, N, K): LTX-2 shapes at T=1280 / Tc=1024 (stream-K territory: ragged last wave), ragged M, tiny M, narrow N
+SHAPES = [(1280, 4096, 4096), (1280, 12288, 4096), (1024, 8192, 4096), (1280, 4096, 16384), (1280, 16384, 4096),
+          (5184, 4096, 4096), (1000, 1024, 512), (68, 2048, 2048), (2, 6144, 1024), (1280, 128, 4096), (1280, 4096, 128),
+          (257, 272, 192), (300, 512, 256), (648, 4096, 4096), (128, 24576, 4096)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_auto_schedule(M, N, K):
+    """block_n=0 / cta_pair=-1: the library picks tile, CTA pairing and data-parallel vs stream-K."""
+    gemm_case(M, N, K, _lib.EPI_BIAS_F32)
+
+
+@pytest.mark.parametrize("mode", [_lib.EPI_BIAS_BF16, _lib.EPI_GELU_BF16, _lib.EPI_SILU_BF16, _lib.EPI_RESID_GATE_F32])
+@pytest.mark.parametrize("M,N,K", [(1280, 4096, 4096), (520, 784, 512), (1280, 12288, 4096)])
+def test_gemm_epilogues(M, N, K, mode):
+    gemm_case(M, N, K, mode)
+    gemm_case(M, N, K, mode, pair=0)
+
+
+@pytest.mark.parametrize("pair,bn", [(0, 128), (1, 128), (0, 256), (1, 256), (1, 144), (0, 48), (1, 224)])
+def test_gemm_explicit_tiles(pair, bn):
+    for M, N, K in [(300, 512, 256), (1280, 4096, 1024), (257, 272, 192)]:
+        gemm_case(M, N, K, _lib.EPI_BIAS_F32, pair=pair, bn=bn)
+
+
+def test_gemm_stream_k_matches_data_parallel_and_is_reproducible():
+    """An explicit block_n forces the data-parallel schedule; auto picks stream-K for this shape.  Both must
+    agree to fp32 summation order, and stream-K must be bit-reproducible run to run (fixed k-order fix-up)."""
+    for M, N, K in [(1280, 4096, 4096), (1280, 4096, 16384), (1024, 8192, 4096)]:
+        sk1 = gemm_case(M, N, K, _lib.EPI_BIAS_F32)
+        sk2 = gemm_case(M, N, K, _lib.EPI_BIAS_F32)
+        dp = gemm_case(M, N, K, _lib.EPI_BIAS_F32, pair=1, bn=256)
+        assert torch.equal(sk1, sk2), "stream-K result differs between two runs"
+        assert rel_l2(sk1, dp) < 2e-6
+    # many back-to-back launches reuse the same scratch + counters
+    outs = [gemm_case(1280, 4096, 4096, _lib.EPI_GELU_BF16, seed=3) for _ in range(5)]
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+
+
+def test_gemm_rejects_bad_shapes():
+    a = torch.zeros(64, 96, device=DEV, dtype=torch.bfloat16)
+    w = torch.zeros(64, 96, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(_lib.LtxbError, match="multiple of 64"):
+        ops.gemm(a, w, None, torch.empty(64, 64, device=DEV, dtype=torch.bfloat16))
+
+
+@pytest.mark.parametrize("B,Tq,Tk,H,dh,bias", [(1, 128, 128, 1, 128, False), (1, 256, 384, 2, 128, False), (2, 200, 72, 3, 128, False),
+                                                (1, 1280, 1280, 32, 128, False), (2, 320, 1024, 4, 128, True), (1, 128, 128, 2, 64, False),
+                                                (1, 300, 68, 32, 64, False), (1, 68, 1280, 32, 64, False), (1, 1280, 1024, 8, 128, False)])
+def test_attention(B, Tq, Tk, H, dh, bias):
+    g = torch.Generator(device=DEV).manual_seed(7)
+    D = H * dh
+    q = torch.randn(B * Tq, D, device=DEV, generator=g).bfloat16()
+    kv = torch.randn(B * Tk, 2 * D, device=DEV, generator=g).bfloat16()
+    k, v = kv[:, :D], kv[:, D:]
+    kb = None
+    if bias:
+        kb = torch.zeros(B, Tk, device=DEV)
+        kb[:, Tk - Tk // 3:] = -1e9
+    out = torch.empty(B * Tq, D, device=DEV, dtype=torch.bfloat16)
+    ops.attention(q, k, v, out, B, Tq, Tk, H, dh, 1.0 / math.sqrt(dh), kb)
+    qh = q.float().view(B, Tq, H, dh).transpose(1, 2)
+    kh = k.float().reshape(B, Tk, H, dh).transpose(1, 2)
+    vh = v.float().reshape(B, Tk, H, dh).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(dh)
+    if kb is not None:
+        s = s + kb[:, None, None, :]
+    ref = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B * Tq, D)
+    err = rel_l2(out.float(), ref)
+    assert err <= 8e-3, f"attention rel_l2 {err:.3e}"  # bf16 P and bf16 output rounding
+    # KAT (iv): softmax rows sum to 1 -> attention of constant V returns that constant
+    ones = torch.ones_like(v)
+    ops.attention(q, k, ones, out, B, Tq, Tk, H, dh, 1.0 / math.sqrt(dh), kb)
+    assert float((out.float() - 1).abs().max()) <= 8e-3
+
+
+def test_rmsnorm_layernorm_modulate():
+    g = torch.Generator(device=DEV).manual_seed(1)
+    for R, D in [(1280, 4096), (68, 2048), (37, 512), (5, 1032)]:
+        x = torch.randn(R, D, device=DEV, generator=g) * 3
+        out = torch.empty(R, D, device=DEV, dtype=torch.bfloat16)
+        ops.rmsnorm_modulate(x, out, 1e-6)
+        ref = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6)
+        assert rel_l2(out.float(), ref) <= 4e-3
+        mod = torch.randn(3, 6 * D, device=DEV, generator=g) * 0.1
+        table = torch.randn(6, D, device=DEV, generator=g) * 0.1
+        idx = torch.randint(0, 3, (R,), device=DEV, generator=g, dtype=torch.int32)
+        ops.rmsnorm_modulate(x, out, 1e-6, mod=mod, scale_off=4 * D, shift_off=3 * D, table_scale=table[4], table_shift=table[3], row_index=idx)
+        sc = table[4] + mod[idx.long(), 4 * D:5 * D]
+        sh = table[3] + mod[idx.long(), 3 * D:4 * D]
+        assert rel_l2(out.float(), ref * (1 + sc) + sh) <= 4e-3
+        emb = torch.randn(3, D, device=DEV, generator=g) * 0.1
+        ops.layernorm_modulate(x, out, 1e-6, emb, table[1], table[0], row_index=idx)
+        ln = torch.nn.functional.layer_norm(x, (D,), eps=1e-6)
+        assert rel_l2(out.float(), ln * (1 + table[1] + emb[idx.long()]) + table[0] + emb[idx.long()]) <= 4e-3
+
+
+def test_qknorm_rope_and_small_kernels():
+    g = torch.Generator(device=DEV).manual_seed(2)
+    for B, T, H, dh in [(1, 320, 32, 128), (2, 68, 32, 64), (1, 77, 4, 128)]:
+        D = H * dh
+        qkv = torch.randn(B * T, 3 * D, device=DEV, generator=g).bfloat16()
+        x = qkv[:, D:2 * D]
+        x0 = x.float().clone()
+        wgt = 1 + 0.1 * torch.randn(D, device=DEV, generator=g)
+        ang = torch.rand(B, H, T, dh // 2, device=DEV, generator=g) * 6.28
+        cos, sin = torch.cos(ang), torch.sin(ang)
+        ops.qknorm_rope(x, B, T, H, dh, wgt, 1e-6, cos, sin)
+        n = x0 * torch.rsqrt(x0.pow(2).mean(-1, keepdim=True) + 1e-6) * wgt
+        nh = n.view(B, T, H, 2, dh // 2).permute(0, 2, 1, 3, 4)
+        a_, b_ = nh[..., 0, :], nh[..., 1, :]
+        rot = torch.stack([a_ * cos - b_ * sin, b_ * cos + a_ * sin], dim=-2).permute(0, 2, 1, 3, 4).reshape(B * T, D)
+        assert rel_l2(x.float(), rot) <= 4e-3
+        assert torch.equal(qkv[:, :D].float(), qkv[:, :D].float()) and torch.isfinite(qkv.float()).all()
+    t = torch.tensor([0.0, 0.05, 0.421875, 0.725, 1.0], device=DEV)
+    feat = torch.empty(5, 256, device=DEV, dtype=torch.bfloat16)
+    ops.timestep_embed(t, 1000.0, 256, feat)
+    f = torch.exp(-math.log(10000.0) * torch.arange(128, device=DEV) / 128)
+    arg = (t * 1000.0)[:, None] * f[None]
+    assert rel_l2(feat.float(), torch.cat([torch.cos(arg), torch.sin(arg)], -1)) <= 4e-3
+    # timestep grouping: every token's value is recoverable through (values, index)
+    ts = torch.tensor([0.725, 0.0, 0.725, 0.5, 0.0, -0.0, 0.5] * 300, device=DEV)
+    values, index, count = ops.timestep_groups(ts, 16)
+    assert int(count) == 3 and torch.equal(values[index.long()], ts.abs() * torch.sign(ts).abs())
+    # sampler step
+    x = torch.randn(96, 128, device=DEV, generator=g)
+    vp, vn = torch.randn(96, 128, device=DEV, generator=g), torch.randn(96, 128, device=DEV, generator=g)
+    mask = (torch.rand(96, device=DEV, generator=g) > 0.3).float()
+    clean = torch.randn(96, 128, device=DEV, generator=g)
+    x_ref = x.clone()
+    v = vp + 3.5 * (vp - vn)
+    x0 = (x_ref - 0.725 * v) * mask[:, None] + clean * (1 - mask[:, None])
+    want = x0 + 0.421875 * (x_ref - x0) / 0.725
+    ops.euler_step(x, vp, 0.725, 0.421875, v_neg=vn, cfg_scale=4.5, mask=mask, clean=clean)
+    assert rel_l2(x, want) <= 1e-6
