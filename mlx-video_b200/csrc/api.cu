@@ -1,6 +1,7 @@
 // Library-level plumbing of the C ABI: last-error string, device check, TMA tensor-map encoding.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -51,6 +52,11 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
                      static_cast<int>(r), rank, static_cast<unsigned long long>(dims[0]),
                      static_cast<unsigned long long>(rank > 1 ? dims[1] : 1), box[0], rank > 1 ? box[1] : 1);
   return LTXB_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("LTXB_PDL"); return e == nullptr || atoi(e) != 0; }();
+  return on;
 }
 
 int num_sms() {

@@ -95,6 +95,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&hdr->tmem_base);
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -320,8 +322,7 @@ static int launch_attention(const void* Q, long long ldq, const void* K, long lo
   if ((rc = enc(&tk, K, ldk, p.Tk))) return rc;
   if ((rc = enc(&tv, V, ldv, p.Tk))) return rc;
   dim3 grid((p.Tq + kTileQ - 1) / kTileQ, p.H, p.B);
-  kernel<<<grid, kAttnThreads, smem, stream>>>(tq, tk, tv, p);
-  LTXB_CUDA(cudaGetLastError());
+  LTXB_CUDA(launch_kernel(kernel, grid, dim3(kAttnThreads), smem, stream, 1, tq, tk, tv, p));
   return LTXB_OK;
 }
 

@@ -70,6 +70,8 @@ norm_modulate_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* 
                      int D, float eps, const float* __restrict__ mod_scale, const float* __restrict__ mod_shift,
                      long long ld_mod, const float* __restrict__ table_scale, const float* __restrict__ table_shift,
                      int row_div, const int* __restrict__ row_index) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32];
   const long long row = blockIdx.x;
   const float* xr = x + row * ldx;
@@ -149,8 +151,8 @@ static int launch_norm_modulate(const float* x, long long ldx, void* out, long l
   const int chunks = (D / 8 + kRowThreads - 1) / kRowThreads;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
 #define LTXB_LAUNCH_NM(C)                                                                                        \
-  norm_modulate_kernel<C, kLayerNorm><<<R, kRowThreads, 0, s>>>(x, ldx, o, ldo, D, eps, mod_scale, mod_shift, ld_mod, \
-                                                                 table_scale, table_shift, row_div, row_index)
+  LTXB_CUDA(launch_kernel(norm_modulate_kernel<C, kLayerNorm>, dim3(R), dim3(kRowThreads), 0, s, 1, x, ldx, o, ldo, D, eps, mod_scale, mod_shift, ld_mod, \
+                                                                 table_scale, table_shift, row_div, row_index))
   if (chunks <= 1) LTXB_LAUNCH_NM(1);
   else if (chunks <= 2) LTXB_LAUNCH_NM(2);
   else if (chunks <= 4) LTXB_LAUNCH_NM(4);
@@ -167,6 +169,8 @@ __global__ void __launch_bounds__(256)
 gate_residual_kernel(float* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ y, long long ldy,
                      long long R, int D, const float* __restrict__ gate, long long gate_ld,
                      const float* __restrict__ gate_table, int row_div, const int* __restrict__ row_index) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cpr = D / 8;
   const long long total = R * cpr;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
@@ -202,6 +206,8 @@ gate_residual_kernel(float* __restrict__ x, long long ldx, const __nv_bfloat16* 
 __global__ void __launch_bounds__(1024)
 qknorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int T, int H, int dh, const float* __restrict__ weight,
                    float eps, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, int B_pe) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32];
   const long long row = blockIdx.x;
   const int half = dh / 2;
@@ -251,6 +257,8 @@ qknorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int T, int H, i
 // ------------------------------------------------------------------------------------------------
 __global__ void timestep_embed_kernel(const float* __restrict__ t, int n, float scale, int dim,
                                       __nv_bfloat16* __restrict__ out, long long ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half = dim / 2;
   const long long total = static_cast<long long>(n) * half;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -275,6 +283,8 @@ struct RopeAxes {
 __global__ void rope_table_kernel(const float* __restrict__ pos, int n_axes, int T, RopeAxes ax,
                                   const float* __restrict__ freq, int nfreq, int dim, int H, int use_middle,
                                   float* __restrict__ cos_out, float* __restrict__ sin_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half = dim / 2;
   const int hd2 = half / H;
   const int pad = half - nfreq * n_axes;
@@ -309,6 +319,8 @@ __global__ void rope_table_kernel(const float* __restrict__ pos, int n_axes, int
 // ------------------------------------------------------------------------------------------------
 __global__ void silu_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n8,
                                  long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<long long>(blockDim.x) * gridDim.x) {
     float v[8];
@@ -326,6 +338,8 @@ __global__ void silu_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
 }
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n8,
                                      long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<long long>(blockDim.x) * gridDim.x) {
     float v[8];
@@ -337,6 +351,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
 }
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long n8,
                                      long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<long long>(blockDim.x) * gridDim.x) {
     float v[8];
@@ -353,6 +369,8 @@ __global__ void euler_step_kernel(float* __restrict__ x, const float* __restrict
                                   const float* __restrict__ sigma_tok, float sigma, float sigma_next,
                                   const float* __restrict__ mask, const float* __restrict__ clean, long long n_tok,
                                   int C, float* __restrict__ x0_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = n_tok * C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(blockDim.x) * gridDim.x) {
@@ -382,6 +400,8 @@ constexpr unsigned kEmptySlot = 0xFFFFFFFFu;  // a NaN pattern no real timestep 
 __global__ void __launch_bounds__(1024)
 timestep_groups_kernel(const float* __restrict__ t, int n, int cap, float* __restrict__ values,
                        int* __restrict__ index, int* __restrict__ count) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ unsigned slots[];
   __shared__ int overflow;
   for (int i = threadIdx.x; i < cap; i += blockDim.x) slots[i] = kEmptySlot;
@@ -481,10 +501,9 @@ extern "C" int ltxb_gate_residual(float* x, int64_t ldx, const void* y, int64_t 
     LTXB_CHECK_ARG(row_index || row_div >= 1, "ltxb_gate_residual: row_div must be >= 1");
   }
   const long long work = static_cast<long long>(R) * (D / 8);
-  gate_residual_kernel<<<grid_for(work, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  LTXB_CUDA(launch_kernel(gate_residual_kernel, dim3(grid_for(work, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, 
       x, ldx, reinterpret_cast<const __nv_bfloat16*>(y), ldy, R, D, gate ? gate + gate_off : nullptr, gate_ld,
-      gate_table, row_div > 0 ? row_div : 1, row_index);
-  LTXB_CUDA(cudaGetLastError());
+      gate_table, row_div > 0 ? row_div : 1, row_index));
   return LTXB_OK;
 }
 
@@ -500,9 +519,8 @@ extern "C" int ltxb_qknorm_rope(void* x, int64_t ldx, int32_t B, int32_t T, int3
   LTXB_CHECK_ARG((cos_tab == nullptr) == (sin_tab == nullptr), "ltxb_qknorm_rope: cos/sin come in pairs");
   if (cos_tab) LTXB_CHECK_ARG(aligned16(cos_tab) && aligned16(sin_tab) && (B_pe == 1 || B_pe == B), "ltxb_qknorm_rope: bad rope table");
   const int nthr = ((H * (dh / 16) + 31) / 32) * 32;
-  qknorm_rope_kernel<<<B * T, nthr, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<__nv_bfloat16*>(x), ldx, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe);
-  LTXB_CUDA(cudaGetLastError());
+  LTXB_CUDA(launch_kernel(qknorm_rope_kernel, dim3(B * T), dim3(nthr), 0, reinterpret_cast<cudaStream_t>(stream), 1, 
+      reinterpret_cast<__nv_bfloat16*>(x), ldx, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe));
   return LTXB_OK;
 }
 
@@ -512,9 +530,8 @@ extern "C" int ltxb_timestep_embed(const float* t, int32_t n, float scale, int32
   if (n == 0) return LTXB_OK;
   LTXB_CHECK_ARG(n > 0 && dim > 0 && dim % 2 == 0 && ldo >= dim, "ltxb_timestep_embed: bad shape n=%d dim=%d", n, dim);
   const long long work = static_cast<long long>(n) * (dim / 2);
-  timestep_embed_kernel<<<grid_for(work, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      t, n, scale, dim, reinterpret_cast<__nv_bfloat16*>(out), ldo);
-  LTXB_CUDA(cudaGetLastError());
+  LTXB_CUDA(launch_kernel(timestep_embed_kernel, dim3(grid_for(work, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, 
+      t, n, scale, dim, reinterpret_cast<__nv_bfloat16*>(out), ldo));
   return LTXB_OK;
 }
 
@@ -529,9 +546,8 @@ extern "C" int ltxb_rope_table(const float* positions, int32_t B, int32_t n_axes
   LTXB_CHECK_ARG(nfreq >= 1 && nfreq * n_axes <= dim / 2, "ltxb_rope_table: nfreq=%d x %d axes exceeds dim/2=%d", nfreq, n_axes, dim / 2);
   RopeAxes ax{};
   for (int i = 0; i < n_axes; ++i) ax.max_pos[i] = max_pos_host[i];
-  rope_table_kernel<<<B * T, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(positions, n_axes, T, ax, freq, nfreq, dim,
-                                                                                 H, use_middle, cos_out, sin_out);
-  LTXB_CUDA(cudaGetLastError());
+  LTXB_CUDA(launch_kernel(rope_table_kernel, dim3(B * T), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, positions, n_axes, T, ax, freq, nfreq, dim,
+                                                                                 H, use_middle, cos_out, sin_out));
   return LTXB_OK;
 }
 
@@ -539,9 +555,8 @@ extern "C" int ltxb_silu_bf16(const void* x, void* out, int64_t n, void* stream)
   LTXB_CHECK_ARG(x && out && n >= 0, "ltxb_silu_bf16: bad argument");
   if (n == 0) return LTXB_OK;
   LTXB_CHECK_ARG(aligned16(x) && aligned16(out), "ltxb_silu_bf16: misaligned");
-  silu_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), n / 8, n);
-  LTXB_CUDA(cudaGetLastError());
+  LTXB_CUDA(launch_kernel(silu_bf16_kernel, dim3(grid_for(n / 8 + 1, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, 
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), n / 8, n));
   return LTXB_OK;
 }
 
@@ -549,9 +564,8 @@ extern "C" int ltxb_cast_f32_to_bf16(const float* x, void* out, int64_t n, void*
   LTXB_CHECK_ARG(x && out && n >= 0, "ltxb_cast_f32_to_bf16: bad argument");
   if (n == 0) return LTXB_OK;
   LTXB_CHECK_ARG(aligned16(x) && aligned16(out), "ltxb_cast_f32_to_bf16: misaligned");
-  cast_f32_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, reinterpret_cast<__nv_bfloat16*>(out), n / 8, n);
-  LTXB_CUDA(cudaGetLastError());
+  LTXB_CUDA(launch_kernel(cast_f32_bf16_kernel, dim3(grid_for(n / 8 + 1, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, 
+      x, reinterpret_cast<__nv_bfloat16*>(out), n / 8, n));
   return LTXB_OK;
 }
 
@@ -559,9 +573,8 @@ extern "C" int ltxb_cast_bf16_to_f32(const void* x, float* out, int64_t n, void*
   LTXB_CHECK_ARG(x && out && n >= 0, "ltxb_cast_bf16_to_f32: bad argument");
   if (n == 0) return LTXB_OK;
   LTXB_CHECK_ARG(aligned16(x) && aligned16(out), "ltxb_cast_bf16_to_f32: misaligned");
-  cast_bf16_f32_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), out, n / 8, n);
-  LTXB_CUDA(cudaGetLastError());
+  LTXB_CUDA(launch_kernel(cast_bf16_f32_kernel, dim3(grid_for(n / 8 + 1, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, 
+      reinterpret_cast<const __nv_bfloat16*>(x), out, n / 8, n));
   return LTXB_OK;
 }
 
@@ -572,9 +585,8 @@ extern "C" int ltxb_euler_step(float* x, const float* v_pos, const float* v_neg,
   LTXB_CHECK_ARG(sigma != 0.0f, "ltxb_euler_step: sigma must be non-zero (generate.py:1293-1301 divides by it)");
   LTXB_CHECK_ARG((mask == nullptr) || (clean != nullptr), "ltxb_euler_step: mask needs clean latents");
   if (n_tok == 0) return LTXB_OK;
-  euler_step_kernel<<<grid_for(n_tok * C, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, v_pos, v_neg, cfg_scale, sigma_tok, sigma, sigma_next, mask, clean, n_tok, C, x0_out);
-  LTXB_CUDA(cudaGetLastError());
+  LTXB_CUDA(launch_kernel(euler_step_kernel, dim3(grid_for(n_tok * C, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, 
+      x, v_pos, v_neg, cfg_scale, sigma_tok, sigma, sigma_next, mask, clean, n_tok, C, x0_out));
   return LTXB_OK;
 }
 
@@ -582,8 +594,7 @@ extern "C" int ltxb_timestep_groups(const float* t, int32_t n, int32_t cap, floa
                                     int32_t* count, void* stream) {
   LTXB_CHECK_ARG(t && values && index && count, "ltxb_timestep_groups: null pointer");
   LTXB_CHECK_ARG(n >= 0 && cap >= 1 && cap <= 4096, "ltxb_timestep_groups: bad n=%d / cap=%d (1..4096)", n, cap);
-  timestep_groups_kernel<<<1, 1024, cap * sizeof(unsigned), reinterpret_cast<cudaStream_t>(stream)>>>(t, n, cap, values,
-                                                                                                    index, count);
-  LTXB_CUDA(cudaGetLastError());
+  LTXB_CUDA(launch_kernel(timestep_groups_kernel, dim3(1), dim3(1024), cap * sizeof(unsigned), reinterpret_cast<cudaStream_t>(stream), 1, t, n, cap, values,
+                                                                                                    index, count));
   return LTXB_OK;
 }

@@ -75,25 +75,28 @@ __device__ __forceinline__ int sk_cluster_of(int total_units, int slots, int uni
   return c;
 }
 struct WorkIter {
-  int sk, num_kb, num_tiles, stride, tile, u, u_end;
+  int num_kb, num_tiles, stride, tile, u, u_end;
+  // Hybrid schedule: the first `sk_tiles` tiles (total_units = sk_tiles * num_kb) are stream-K'd — cut into equal
+  // contiguous k-block ranges, one per cluster — then the remaining tiles (a whole number of waves) are dealt
+  // round-robin.  Stream-K goes FIRST so that finishing a cut tile overlaps the next tile's main loop.
   __device__ WorkIter(const GemmParams& p, int cluster_id, int num_clusters, int num_kb_)
-      : sk(p.sk), num_kb(num_kb_), num_tiles(p.num_m_tiles * p.num_n_tiles), stride(num_clusters), tile(cluster_id) {
-    u = sk ? sk_unit_begin(p.total_units, num_clusters, cluster_id) : 0;
-    u_end = sk ? sk_unit_begin(p.total_units, num_clusters, cluster_id + 1) : 0;
+      : num_kb(num_kb_), num_tiles(p.num_m_tiles * p.num_n_tiles), stride(num_clusters) {
+    u = p.sk ? sk_unit_begin(p.total_units, num_clusters, cluster_id) : 0;
+    u_end = p.sk ? sk_unit_begin(p.total_units, num_clusters, cluster_id + 1) : 0;
+    tile = (p.sk ? p.total_units / num_kb_ : 0) + cluster_id;
   }
   __device__ __forceinline__ bool next(WorkItem& w) {
-    if (!sk) {
-      if (tile >= num_tiles) return false;
-      w.tile = tile, w.kb0 = 0, w.kb1 = num_kb;
-      tile += stride;
+    if (u < u_end) {
+      w.tile = u / num_kb;
+      w.kb0 = u - w.tile * num_kb;
+      const int len = min(num_kb - w.kb0, u_end - u);
+      w.kb1 = w.kb0 + len;
+      u += len;
       return true;
     }
-    if (u >= u_end) return false;
-    w.tile = u / num_kb;
-    w.kb0 = u - w.tile * num_kb;
-    const int len = min(num_kb - w.kb0, u_end - u);
-    w.kb1 = w.kb0 + len;
-    u += len;
+    if (tile >= num_tiles) return false;
+    w.tile = tile, w.kb0 = 0, w.kb1 = num_kb;
+    tile += stride;
     return true;
   }
 };
@@ -227,6 +230,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if constexpr (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&hdr->tmem_base);
+  pdl_launch_dependents();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -348,34 +353,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       } else {
         // ---- stream-K: this cluster holds only k-blocks [kb0, kb1) of the tile.
-        // 1. park the fp32 partial in this cluster's slot ([32-col chunk][row][32] so a thread's 128 B are contiguous)
+        // 1. park the fp32 partial in this cluster's slot ([32-col chunk][row][32] so a thread's 128 B are
+        //    contiguous); the accumulator stays in TMEM until we know whether we finish the tile
         const size_t slot_elems = static_cast<size_t>(kBlockM) * bn;
         auto slot_of = [&](int cluster, bool head) {
           return p.sk_partials + (static_cast<size_t>(cluster * 2 + (head ? 0 : 1)) * kCtas + cta_rank) * slot_elems;
         };
+        // slot layout [32-col chunk][float4 index 0..7][row 0..127]: for a fixed float4 index the 32 lanes of a
+        // warp touch 512 contiguous bytes, so both the dump and the reload are fully coalesced
+        constexpr int kF4Stride = kBlockM;  // float4s between consecutive float4 indices of one row
+        auto chunk_of = [&](float* slot, int c) {
+          return reinterpret_cast<float4*>(slot + static_cast<size_t>(c / 32) * (kBlockM * 32)) + row_in_cta;
+        };
         float* mine = slot_of(cluster_id, w.kb0 > 0);
         for (int c = 0; c < bn; c += 32) {
-          const bool last = (c + 32 >= bn);
-          float4* dst = reinterpret_cast<float4*>(mine + static_cast<size_t>(c / 32) * (kBlockM * 32) + row_in_cta * 32);
+          float4* dst = chunk_of(mine, c);
           if (c + 32 <= bn) {
             uint32_t r[32];
             tmem_ld_x32(t_row + c, r);
             tmem_wait_ld();
-            if (last) release_acc();
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              __stcg(dst + i, make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+              __stcg(dst + i * kF4Stride, make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
           } else {
             uint32_t r[16];
             tmem_ld_x16(t_row + c, r);
             tmem_wait_ld();
-            release_acc();
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              __stcg(dst + i, make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+              __stcg(dst + i * kF4Stride, make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
           }
         }
-        // 2. announce it; the LAST contributor to arrive owns the tile's epilogue
+        // 2. announce it; the LAST contributor to arrive finishes the tile (nobody ever waits)
         __threadfence();
         epilogue_bar_sync();
         int* counter = p.sk_counters + w.tile * kCtas + static_cast<int>(cta_rank);
@@ -384,33 +393,77 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int tile_u0 = w.tile * num_kb;
         const int first_c = sk_cluster_of(p.total_units, num_clusters, tile_u0);
         const int last_c = sk_cluster_of(p.total_units, num_clusters, tile_u0 + num_kb - 1);
-        if (*reinterpret_cast<volatile int*>(&hdr->sk_arrival) == last_c - first_c) {
+        const bool finisher = *reinterpret_cast<volatile int*>(&hdr->sk_arrival) == last_c - first_c;
+        if (!finisher) {
+          release_acc();
+        } else {
           __threadfence();
-          // 3. sum every contributor's partial in k order (fixed order: bit-reproducible) and finish the tile
-          for (int c = 0; c < bn; c += 32) {
-            const int width = (c + 32 <= bn) ? 32 : 16;
-            float accv[32];
+          auto finish_chunk = [&](const float* v, int c, int width) {
+            const int col = n0 + c;
+            if (!row_ok) return;
+            const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+            if (width == 32 && col + 32 <= p.N) {
+              epilogue_store<kEpi, 32>(p, r, row, col, grow);
+            } else if (col + 16 <= p.N) {
+              epilogue_store<kEpi, 16>(p, r, row, col, grow);
+            }
+          };
+          if (last_c - first_c == 1 && (bn & 31) == 0) {
+            // two contributors (the common cut): own partial still sits in TMEM, the other's comes from L2.
+            // Loads for four 32-column chunks are in flight together (32 x 16 B per thread) — the fix-up is
+            // a latency-bound L2 read, so memory-level parallelism is what makes it cheap.  a + b == b + a
+            // in fp32, so the result does not depend on which of the two finishes.
+            const int other_c = (cluster_id == first_c) ? last_c : first_c;
+            float* other = slot_of(other_c, sk_unit_begin(p.total_units, num_clusters, other_c) > tile_u0);
+            for (int g = 0; g < bn; g += 128) {
+              float4 ld[4][8];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) accv[i] = 0.f;
-            for (int cc = first_c; cc <= last_c; ++cc) {
-              const bool head = sk_unit_begin(p.total_units, num_clusters, cc) > tile_u0;
-              const float4* src = reinterpret_cast<const float4*>(slot_of(cc, head) + static_cast<size_t>(c / 32) * (kBlockM * 32) + row_in_cta * 32);
+              for (int j = 0; j < 4; ++j) {
+                if (g + 32 * j < bn) {
+                  const float4* src = chunk_of(other, g + 32 * j);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (i * 4 < width) {
-                  const float4 v = __ldcg(src + i);
-                  accv[4 * i] += v.x, accv[4 * i + 1] += v.y, accv[4 * i + 2] += v.z, accv[4 * i + 3] += v.w;
+                  for (int i = 0; i < 8; ++i) ld[j][i] = __ldcg(src + i * kF4Stride);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int c = g + 32 * j;
+                if (c < bn) {
+                  uint32_t r[32];
+                  tmem_ld_x32(t_row + c, r);
+                  tmem_wait_ld();
+                  if (c + 32 >= bn) release_acc();
+                  float v[32];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + ld[j][i].x;
+                    v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + ld[j][i].y;
+                    v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + ld[j][i].z;
+                    v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + ld[j][i].w;
+                  }
+                  finish_chunk(v, c, 32);
                 }
               }
             }
-            const int col = n0 + c;
-            if (row_ok) {
-              const uint32_t* r = reinterpret_cast<const uint32_t*>(accv);
-              if (width == 32 && col + 32 <= p.N) {
-                epilogue_store<kEpi, 32>(p, r, row, col, grow);
-              } else if (col + 16 <= p.N) {
-                epilogue_store<kEpi, 16>(p, r, row, col, grow);
+          } else {
+            // general cut: sum every contributor's parked partial in k order (fixed order: bit-reproducible)
+            release_acc();
+            for (int c = 0; c < bn; c += 32) {
+              const int width = (c + 32 <= bn) ? 32 : 16;
+              float accv[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) accv[i] = 0.f;
+              for (int cc = first_c; cc <= last_c; ++cc) {
+                const float4* src = chunk_of(slot_of(cc, sk_unit_begin(p.total_units, num_clusters, cc) > tile_u0), c);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  if (i * 4 < width) {
+                    const float4 v = __ldcg(src + i * kF4Stride);
+                    accv[4 * i] += v.x, accv[4 * i + 1] += v.y, accv[4 * i + 2] += v.z, accv[4 * i + 3] += v.w;
+                  }
+                }
               }
+              finish_chunk(accv, c, width);
             }
           }
           if (row_in_cta == 0) *counter = 0;  // ready for the next launch
@@ -476,12 +529,13 @@ static SkWorkspace g_sk_ws[kMaxDevices];
 
 struct SkChoice {
   bool use;
-  int block_n, ctas;
+  int block_n, ctas, sk_tiles;
 };
-// Stream-K pays when data-parallel tiling leaves a ragged last wave.  Costs in k-block units per cluster; a cut
-// tile costs its finisher one L2 round trip per contributor (~2 k-blocks each).
+// Stream-K pays when data-parallel tiling leaves a ragged last wave.  The stream-K region is the ragged
+// remainder plus one full wave, so every cluster's share is at least one tile's worth of k-blocks and a cut
+// tile has exactly two contributors (the cheap fix-up).  Costs are in k-block units per cluster.
 static SkChoice choose_stream_k(int M, int N, int K, int sms, int want_bn, int want_pair, const TileChoice& dp) {
-  SkChoice none{false, 0, 0};
+  SkChoice none{false, 0, 0, 0};
   if (want_bn > 0) return none;  // an explicit tile request means "run exactly this" (tests, sweeps)
   const int ctas = (want_pair == 0 || (want_pair < 0 && M <= kBlockM)) ? 1 : 2;
   const int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
@@ -490,18 +544,24 @@ static SkChoice choose_stream_k(int M, int N, int K, int sms, int want_bn, int w
   const int num_kb = K / kBlockK;
   const long long tiles = 1ll * ((M + kBlockM * ctas - 1) / (kBlockM * ctas)) * ((N + bn - 1) / bn);
   if (tiles * ctas > kSkCounterInts || tiles * num_kb > (1ll << 30)) return none;
-  const long long units = tiles * num_kb;
-  const long long per = (units + slots - 1) / slots;
-  if (per < 8) return none;  // slivers: the fix-up traffic would dominate
+  const long long waves = tiles / slots, rem = tiles % slots;
+  if (rem == 0) return none;
+  const long long sk_tiles = rem + (waves >= 1 ? slots : 0);
+  const long long per = (sk_tiles * num_kb + slots - 1) / slots;  // k-blocks per cluster inside the region
+  if (per < 16) return none;  // slivers: the fix-up traffic would dominate
   const long long contributors = (num_kb + per - 1) / per + 1;
-  const double t_sk = static_cast<double>(per) + 4.0 + 2.0 * static_cast<double>(contributors);
+  // measured on B200 (scripts/gemm_sweep.py): parking + finishing a cut tile costs about as much as 60 k-blocks
+  // of main loop when it ends the kernel, ~40 when later tiles follow — so stream-K only pays for long-K problems
+  // (the FFN down-projection, K = 16384: +25 %)
+  const double fixup = (waves >= 2 ? 40.0 : 60.0) + 20.0 * static_cast<double>(contributors - 2);
+  const double t_sk = static_cast<double>(per) + static_cast<double>(waves >= 1 ? waves - 1 : 0) * num_kb + fixup;
   // the data-parallel alternative, in the same units (per-tile time is ~independent of BN below 256: the
   // SS-mode A-operand read paces the MMA)
   const int dp_slots = sms / dp.ctas;
   const long long dp_tiles = 1ll * ((M + kBlockM * dp.ctas - 1) / (kBlockM * dp.ctas)) * ((N + dp.block_n - 1) / dp.block_n);
   const double t_dp = static_cast<double>((dp_tiles + dp_slots - 1) / dp_slots) * num_kb;
-  if (t_sk * 1.02 >= t_dp) return none;
-  return SkChoice{true, bn, ctas};
+  if (t_sk * 1.03 >= t_dp) return none;
+  return SkChoice{true, bn, ctas, static_cast<int>(sk_tiles)};
 }
 
 template <int kCtas, int kEpi>
@@ -513,19 +573,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmP
     LTXB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     configured = true;
   }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCtas;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  LTXB_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tw, p));
+  LTXB_CUDA(launch_kernel(kernel, dim3(grid), dim3(kGemmThreads), smem, stream, kCtas, ta, tw, p));
   return LTXB_OK;
 }
 
@@ -584,7 +632,7 @@ extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   int dev = 0;
   cudaGetDevice(&dev);
   const SkWorkspace ws = (dev >= 0 && dev < kMaxDevices) ? g_sk_ws[dev] : SkWorkspace{};
-  SkChoice sk{false, 0, 0};
+  SkChoice sk{false, 0, 0, 0};
   if (env_sk && ws.partials != nullptr) sk = choose_stream_k(M, N, K, sms, block_n, cta_pair, tc);
   const int ctas = sk.use ? sk.ctas : tc.ctas;
   const int bn = sk.use ? sk.block_n : tc.block_n;
@@ -630,7 +678,7 @@ extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   if (sk.use) {
     clusters = sms / ctas;
     p.sk = 1;
-    p.total_units = num_tiles * (K / kBlockK);
+    p.total_units = sk.sk_tiles * (K / kBlockK);
     p.sk_partials = ws.partials;
     p.sk_counters = ws.counters;
   }

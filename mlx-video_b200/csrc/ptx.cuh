@@ -28,6 +28,12 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// Programmatic dependent launch: every kernel lets its successor start launching at once (the successor's
+// prologue — barrier init, TMEM alloc, descriptor prefetch — then overlaps this kernel's tail) and blocks
+// before its first global-memory access until the predecessor grid has completed and flushed.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Device-side watchdog: a barrier that never flips is a protocol bug; trap instead of hanging
 // the GPU (a hung box costs a strike, a trapped kernel is just a failed launch).
 #ifndef LTXB_WATCHDOG_CYCLES

@@ -77,7 +77,7 @@ def test_gemm_stream_k_matches_data_parallel_and_is_reproducible():
         sk2 = gemm_case(M, N, K, _lib.EPI_BIAS_F32)
         dp = gemm_case(M, N, K, _lib.EPI_BIAS_F32, pair=1, bn=256)
         assert torch.equal(sk1, sk2), "stream-K result differs between two runs"
-        assert rel_l2(sk1, dp) < 2e-6
+        assert rel_l2(sk1, dp) < 2e-5
     # many back-to-back launches reuse the same scratch + counters
     outs = [gemm_case(1280, 4096, 4096, _lib.EPI_GELU_BF16, seed=3) for _ in range(5)]
     assert all(torch.equal(outs[0], o) for o in outs[1:])
