@@ -79,6 +79,12 @@ typedef struct ltxb_epilogue {
   int64_t gate_ld;
   const int32_t* gate_row_index; /* optional [M]                                     */
   const float* gate_table;       /* [N] added to gate, or NULL                       */
+  /* A-operand layout (0 = plain row-major [M, K]).  a_group_cols = g > 0: A is stored head-group-major,
+   * [K / g][M][g] with rows lda apart and groups a_group_stride elements apart — what the Ulysses gather
+   * all-to-all delivers — and is read in place through a 3-D TMA map (no transposing copy). */
+  int32_t a_group_cols;
+  int32_t reserved_;
+  int64_t a_group_stride;
 } ltxb_epilogue;
 
 int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int32_t M,
@@ -126,6 +132,16 @@ int ltxb_gate_residual(float* x, int64_t ldx, const void* y, int64_t ldy, int32_
  *   cos/sin f32 [B_pe, H, T, dh/2] (B_pe == 1 broadcasts) or NULL for no rotation (attn2). */
 int ltxb_qknorm_rope(void* x, int64_t ldx, int32_t B, int32_t T, int32_t H, int32_t dh, const float* weight,
                      float eps, const float* cos_tab, const float* sin_tab, int32_t B_pe, void* stream);
+
+/* Same operation writing to a SEPARATE, head-grouped destination — the send buffer of the Ulysses
+ * head-scatter all-to-all (new: the reference is single-device).  Head h of row r goes to
+ *   out + (h / heads_per_group) * group_stride + r * ldo + (h % heads_per_group) * dh
+ * so each destination rank's heads are one contiguous [rows, *] block.  weight == NULL copies without
+ * norm / rotation (the V operand).  The norm statistic still spans all H heads of the row (attention.py:96-97),
+ * which is why it must run BEFORE the heads are scattered. */
+int ltxb_qknorm_rope_scatter(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t heads_per_group,
+                             int64_t group_stride, int32_t B, int32_t T, int32_t H, int32_t dh, const float* weight,
+                             float eps, const float* cos_tab, const float* sin_tab, int32_t B_pe, void* stream);
 
 /* a5  sinusoidal timestep features  (utils.py:486-526 with adaln.py:66: dim 256, flip_sin_to_cos,
  *     shift 0):  out bf16 [n, dim] = [cos(t*scale*f_i) | sin(t*scale*f_i)], f_i = exp(-ln(1e4) i/(dim/2)). */

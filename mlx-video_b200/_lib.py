@@ -32,6 +32,9 @@ class Epilogue(C.Structure):
         ("gate_ld", _i64),
         ("gate_row_index", _vp),
         ("gate_table", _vp),
+        ("a_group_cols", _i32),
+        ("reserved_", _i32),
+        ("a_group_stride", _i64),
     ]
 
 
@@ -49,6 +52,7 @@ SIGNATURES = {
     "ltxb_layernorm_modulate": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp, _i64, _vp, _vp, _i32, _vp, _vp]),
     "ltxb_gate_residual": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _i32, _vp, _i32, _vp, _vp]),
     "ltxb_qknorm_rope": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _i32, _vp]),
+    "ltxb_qknorm_rope_scatter": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _i32, _vp]),
     "ltxb_timestep_embed": (C.c_int, [_vp, _i32, _f32, _i32, _vp, _i64, _vp]),
     "ltxb_timestep_groups": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "ltxb_rope_table": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(_f32), _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),

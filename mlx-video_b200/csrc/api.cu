@@ -75,7 +75,7 @@ int num_sms() {
 
 extern "C" const char* ltxb_last_error(void) { return ltxb::g_err; }
 
-extern "C" int ltxb_abi_version(void) { return 1; }
+extern "C" int ltxb_abi_version(void) { return 2; }
 
 extern "C" int ltxb_device_check(void) {
   int dev = 0;

@@ -204,7 +204,8 @@ gate_residual_kernel(float* __restrict__ x, long long ldx, const __nv_bfloat16* 
 // thread j owns elements [8j', 8j'+8) of the first half and the matching 8 of the second half of a head.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-qknorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int T, int H, int dh, const float* __restrict__ weight,
+qknorm_rope_kernel(const __nv_bfloat16* x, long long ldx, __nv_bfloat16* out, long long ldo,  // may alias (in place)
+                   int heads_per_group, long long group_stride, int T, int H, int dh, const float* __restrict__ weight,
                    float eps, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, int B_pe) {
   pdl_launch_dependents();
   pdl_wait();
@@ -216,40 +217,45 @@ qknorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int T, int H, i
   const bool active = threadIdx.x < nthr;
   const int h = active ? threadIdx.x / tph : 0;
   const int off = active ? (threadIdx.x % tph) * 8 : 0;
-  __nv_bfloat16* p1 = x + row * ldx + h * dh + off;
-  __nv_bfloat16* p2 = p1 + half;
+  const __nv_bfloat16* p1 = x + row * ldx + h * dh + off;
   float a[8], b[8];
   float s = 0.f;
   if (active) {
     load8_bf16(p1, a);
-    load8_bf16(p2, b);
+    load8_bf16(p1 + half, b);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += a[i] * a[i] + b[i] * b[i];
   }
-  s = block_sum(s, red);
-  if (!active) return;
-  const float rstd = rsqrtf(s / static_cast<float>(H * dh) + eps);
-  float w1[8], w2[8];
-  load8_ldg(weight + h * dh + off, w1);
-  load8_ldg(weight + h * dh + half + off, w2);
+  if (weight != nullptr) {  // weight == nullptr: plain (re-)layout copy, e.g. V on its way to the all-to-all
+    s = block_sum(s, red);
+    if (!active) return;
+    const float rstd = rsqrtf(s / static_cast<float>(H * dh) + eps);
+    float w1[8], w2[8];
+    load8_ldg(weight + h * dh + off, w1);
+    load8_ldg(weight + h * dh + half + off, w2);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) a[i] *= rstd * w1[i], b[i] *= rstd * w2[i];
-  if (cos_tab != nullptr) {
-    const long long bb = (B_pe == 1) ? 0 : row / T;
-    const long long t = row % T;
-    const long long tab = ((bb * H + h) * T + t) * half + off;
-    float c[8], sn[8];
-    load8_ldg(cos_tab + tab, c);
-    load8_ldg(sin_tab + tab, sn);
+    for (int i = 0; i < 8; ++i) a[i] *= rstd * w1[i], b[i] *= rstd * w2[i];
+    if (cos_tab != nullptr) {
+      const long long bb = (B_pe == 1) ? 0 : row / T;
+      const long long t = row % T;
+      const long long tab = ((bb * H + h) * T + t) * half + off;
+      float c[8], sn[8];
+      load8_ldg(cos_tab + tab, c);
+      load8_ldg(sin_tab + tab, sn);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float f = a[i] * c[i] - sn[i] * b[i];
-      const float g = b[i] * c[i] + sn[i] * a[i];
-      a[i] = f, b[i] = g;
+      for (int i = 0; i < 8; ++i) {
+        const float f = a[i] * c[i] - sn[i] * b[i];
+        const float g = b[i] * c[i] + sn[i] * a[i];
+        a[i] = f, b[i] = g;
+      }
     }
+  } else if (!active) {
+    return;
   }
-  store8_bf16(p1, a);
-  store8_bf16(p2, b);
+  // head h lands in group h / heads_per_group (one group per destination rank of the Ulysses all-to-all)
+  __nv_bfloat16* o1 = out + (h / heads_per_group) * group_stride + row * ldo + (h % heads_per_group) * dh + off;
+  store8_bf16(o1, a);
+  store8_bf16(o1 + half, b);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -507,21 +513,34 @@ extern "C" int ltxb_gate_residual(float* x, int64_t ldx, const void* y, int64_t 
   return LTXB_OK;
 }
 
-extern "C" int ltxb_qknorm_rope(void* x, int64_t ldx, int32_t B, int32_t T, int32_t H, int32_t dh,
-                                const float* weight, float eps, const float* cos_tab, const float* sin_tab,
-                                int32_t B_pe, void* stream) {
-  LTXB_CHECK_ARG(x && weight, "ltxb_qknorm_rope: null pointer");
+extern "C" int ltxb_qknorm_rope_scatter(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t heads_per_group,
+                                        int64_t group_stride, int32_t B, int32_t T, int32_t H, int32_t dh,
+                                        const float* weight, float eps, const float* cos_tab, const float* sin_tab,
+                                        int32_t B_pe, void* stream) {
+  LTXB_CHECK_ARG(x && out, "ltxb_qknorm_rope: null pointer");
   if (B == 0 || T == 0) return LTXB_OK;
   LTXB_CHECK_ARG(B > 0 && T > 0 && H > 0, "ltxb_qknorm_rope: bad shape B=%d T=%d H=%d", B, T, H);
   LTXB_CHECK_SUPPORTED(dh == 64 || dh == 128, "ltxb_qknorm_rope: head dim %d not in {64,128}", dh);
   LTXB_CHECK_SUPPORTED(H * (dh / 16) <= 1024, "ltxb_qknorm_rope: H*dh=%d too wide", H * dh);
-  LTXB_CHECK_ARG(aligned16(x) && ldx % 8 == 0 && aligned16(weight), "ltxb_qknorm_rope: misaligned x/weight");
+  LTXB_CHECK_ARG(aligned16(x) && ldx % 8 == 0 && aligned16(out) && ldo % 8 == 0 && group_stride % 8 == 0,
+                 "ltxb_qknorm_rope: misaligned x/out");
+  LTXB_CHECK_ARG(heads_per_group >= 1 && H % heads_per_group == 0, "ltxb_qknorm_rope: %d heads do not split into groups of %d", H, heads_per_group);
+  LTXB_CHECK_ARG(weight == nullptr || aligned16(weight), "ltxb_qknorm_rope: misaligned weight");
   LTXB_CHECK_ARG((cos_tab == nullptr) == (sin_tab == nullptr), "ltxb_qknorm_rope: cos/sin come in pairs");
+  LTXB_CHECK_ARG(cos_tab == nullptr || weight != nullptr, "ltxb_qknorm_rope: RoPE without the norm is not a path of the reference");
   if (cos_tab) LTXB_CHECK_ARG(aligned16(cos_tab) && aligned16(sin_tab) && (B_pe == 1 || B_pe == B), "ltxb_qknorm_rope: bad rope table");
   const int nthr = ((H * (dh / 16) + 31) / 32) * 32;
-  LTXB_CUDA(launch_kernel(qknorm_rope_kernel, dim3(B * T), dim3(nthr), 0, reinterpret_cast<cudaStream_t>(stream), 1, 
-      reinterpret_cast<__nv_bfloat16*>(x), ldx, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe));
+  LTXB_CUDA(launch_kernel(qknorm_rope_kernel, dim3(B * T), dim3(nthr), 0, reinterpret_cast<cudaStream_t>(stream), 1,
+                          reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(out), ldo,
+                          heads_per_group, group_stride, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe));
   return LTXB_OK;
+}
+
+extern "C" int ltxb_qknorm_rope(void* x, int64_t ldx, int32_t B, int32_t T, int32_t H, int32_t dh,
+                                const float* weight, float eps, const float* cos_tab, const float* sin_tab,
+                                int32_t B_pe, void* stream) {
+  LTXB_CHECK_ARG(weight, "ltxb_qknorm_rope: null weight");
+  return ltxb_qknorm_rope_scatter(x, ldx, x, ldx, H, 0, B, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe, stream);
 }
 
 extern "C" int ltxb_timestep_embed(const float* t, int32_t n, float scale, int32_t dim, void* out, int64_t ldo,

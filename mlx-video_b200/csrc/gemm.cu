@@ -50,6 +50,7 @@ struct GemmParams {
   int gate_row_div;
   const int* gate_row_index;
   const float* gate_table;
+  int a_group_cols;  // > 0: A is [groups][M][a_group_cols] (a 3-D tensor map), K index = group * a_group_cols + col
   // stream-K (sk == 0: data-parallel tile striding)
   int sk;
   int total_units;     // num_tiles * (K / kBlockK)
@@ -248,16 +249,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&hdr->empty[stage], phase ^ 1);
           uint8_t* sa = tiles + static_cast<size_t>(stage) * stage_bytes;
           uint8_t* sw = sa + a_bytes;
+          const int ka = kb * kBlockK;
           if constexpr (kCtas == 1) {
             mbar_arrive_expect_tx(&hdr->full[stage], stage_bytes);
-            tma_load_2d(sa, &tmap_a, &hdr->full[stage], kb * kBlockK, m0);
-            tma_load_2d(sw, &tmap_w, &hdr->full[stage], kb * kBlockK, n0);
+            if (p.a_group_cols > 0) tma_load_3d(sa, &tmap_a, &hdr->full[stage], ka % p.a_group_cols, m0, ka / p.a_group_cols);
+            else tma_load_2d(sa, &tmap_a, &hdr->full[stage], ka, m0);
+            tma_load_2d(sw, &tmap_w, &hdr->full[stage], ka, n0);
           } else {
             // both CTAs of the pair report their bytes on the LEADER's barrier
             if (is_leader) mbar_arrive_expect_tx(&hdr->full[stage], stage_bytes * 2);
             const uint32_t bar = mapa_u32(smem_u32(&hdr->full[stage]), 0);
-            tma_load_2d_pair(sa, &tmap_a, bar, kb * kBlockK, m0);
-            tma_load_2d_pair(sw, &tmap_w, bar, kb * kBlockK, n0);
+            if (p.a_group_cols > 0) tma_load_3d_pair(sa, &tmap_a, bar, ka % p.a_group_cols, m0, ka / p.a_group_cols);
+            else tma_load_2d_pair(sa, &tmap_a, bar, ka, m0);
+            tma_load_2d_pair(sw, &tmap_w, bar, ka, n0);
           }
           if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
         }
@@ -602,7 +606,7 @@ extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   LTXB_CHECK_ARG(aligned16(A) && aligned16(W) && aligned16(out), "ltxb_gemm_bf16: pointers must be 16-byte aligned");
   LTXB_CHECK_SUPPORTED(K % kBlockK == 0, "ltxb_gemm_bf16: K=%d must be a multiple of %d", K, kBlockK);
   LTXB_CHECK_SUPPORTED(N % 16 == 0, "ltxb_gemm_bf16: N=%d must be a multiple of 16", N);
-  LTXB_CHECK_SUPPORTED(lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0 && lda >= K && ldw >= K && ldo >= N,
+  LTXB_CHECK_SUPPORTED(lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0 && (lda >= K || epi->a_group_cols > 0) && ldw >= K && ldo >= N,
                        "ltxb_gemm_bf16: leading dimensions must be multiples of 8 and cover the row");
   LTXB_CHECK_ARG(epi->mode >= 0 && epi->mode < LTXB_EPI_COUNT, "ltxb_gemm_bf16: bad epilogue mode %d", epi->mode);
   LTXB_CHECK_ARG(block_n == 0 || (block_n >= 32 && block_n <= 256 && block_n % 16 == 0),
@@ -659,7 +663,17 @@ extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   p.gate_table = epi->gate_table;
 
   CUtensorMap ta, tw;
-  {
+  if (epi->a_group_cols > 0) {
+    // A arrives head-group-major from the Ulysses gather all-to-all: [K / gc][M][gc]; read it in place
+    LTXB_CHECK_SUPPORTED(epi->a_group_cols % kBlockK == 0 && K % epi->a_group_cols == 0 && epi->a_group_stride % 8 == 0,
+                         "ltxb_gemm_bf16: a_group_cols=%d must divide K=%d and be a multiple of %d", epi->a_group_cols, K, kBlockK);
+    p.a_group_cols = epi->a_group_cols;
+    const uint64_t dims[3] = {static_cast<uint64_t>(epi->a_group_cols), static_cast<uint64_t>(M), static_cast<uint64_t>(K / epi->a_group_cols)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(lda) * 2, static_cast<uint64_t>(epi->a_group_stride) * 2};
+    const uint32_t box[3] = {kBlockK, kBlockM, 1};
+    int rc = encode_tmap_bf16(&ta, A, 3, dims, strides, box);
+    if (rc) return rc;
+  } else {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
     const uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
     const uint32_t box[2] = {kBlockK, kBlockM};

@@ -100,10 +100,17 @@ def gemm(
     gate_row_index: Optional[torch.Tensor] = None,
     block_n: int = 0,
     cta_pair: int = -1,
+    a_group_cols: int = 0,
 ) -> torch.Tensor:
-    """out = epilogue(a @ w.T).  a: bf16 [..., K]; w: bf16 [N, K] (nn.Linear layout); see ltxb.h."""
+    """out = epilogue(a @ w.T).  a: bf16 [..., K]; w: bf16 [N, K] (nn.Linear layout); see ltxb.h.
+    a_group_cols = g > 0: ``a`` is a contiguous [K / g, M, g] tensor (head-group-major, as the Ulysses gather
+    all-to-all delivers it) standing for the [M, K] operand."""
     _prep(a)
-    M, K = _rows(a), a.shape[-1]
+    if a_group_cols > 0:
+        assert a.dim() == 3 and a.is_contiguous() and a.shape[2] == a_group_cols
+        M, K = a.shape[1], a.shape[0] * a.shape[2]
+    else:
+        M, K = _rows(a), a.shape[-1]
     N = w.shape[0]
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape[1] == K
     assert _rows(out) == M and out.shape[-1] == N
@@ -129,7 +136,10 @@ def gemm(
             if gate_table is not None:
                 assert gate_table.dtype == torch.float32 and gate_table.numel() == N
                 epi.gate_table = gate_table.data_ptr()
-    _call("ltxb_gemm_bf16", 2.0 * M * N * K, a.data_ptr(), _ld(a), w.data_ptr(), _ld(w), out.data_ptr(), _ld(out), M, N, K,
+    lda = _ld(a)
+    if a_group_cols > 0:
+        epi.a_group_cols, epi.a_group_stride, lda = a_group_cols, M * a_group_cols, a_group_cols
+    _call("ltxb_gemm_bf16", 2.0 * M * N * K, a.data_ptr(), lda, w.data_ptr(), _ld(w), out.data_ptr(), _ld(out), M, N, K,
                             C.byref(epi), block_n, cta_pair, _stream())
     return out
 
@@ -313,3 +323,22 @@ def timestep_groups(t: torch.Tensor, cap: int):
     count = torch.empty(1, dtype=torch.int32, device=t.device)
     _call("ltxb_timestep_groups", 0.0, t.data_ptr(), n, cap, values.data_ptr(), index.data_ptr(), count.data_ptr(), _stream())
     return values, index, count
+
+
+def qknorm_rope_scatter(x: torch.Tensor, out: torch.Tensor, slot: int, slots: int, groups: int, B: int, T: int, H: int,
+                        dh: int, weight: Optional[torch.Tensor], eps: float, cos: Optional[torch.Tensor] = None,
+                        sin: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q/k RMSNorm (+ split RoPE) of x bf16 [B*T, H*dh] written into slot ``slot`` of the head-grouped send
+    buffer ``out`` bf16 [groups, B*T, slots, (H/groups)*dh]; weight None = plain copy (V)."""
+    _prep(x)
+    hp = H // groups
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and out.is_contiguous()
+    assert tuple(out.shape) == (groups, B * T, slots, hp * dh), f"send buffer {tuple(out.shape)}"
+    b_pe = 1
+    if cos is not None:
+        assert cos.is_contiguous() and sin.is_contiguous() and cos.shape[1:] == (H, T, dh // 2)
+        b_pe = cos.shape[0]
+    base = out.data_ptr() + slot * hp * dh * 2
+    _call("ltxb_qknorm_rope_scatter", 0.0, x.data_ptr(), _ld(x), base, slots * hp * dh, hp, B * T * slots * hp * dh, B, T, H, dh,
+          _ptr(weight), eps, _ptr(cos), _ptr(sin), b_pe, _stream())
+    return out

@@ -1,0 +1,185 @@
+"""Multi-GPU partitioning of the denoise step on one NVLink/NVSwitch box: one process per GPU,
+``torch.distributed`` (NCCL) for the exchanges.
+
+The reference is single-device: no collective exists to mirror, so this is new design.
+
+* **Ulysses sequence parallelism** (``UlyssesGroup``).  Video tokens are sharded across P ranks; every
+  row-wise operator (AdaLN, norms, projections, FFN, residuals, output head) runs on T/P local rows with
+  replicated weights and needs no communication.  Only video self-attention mixes tokens:
+      local QKV GEMM -> q/k RMSNorm over the FULL hidden row + RoPE on local rows (the norm statistic spans
+      all heads, SURVEY F6, so it must precede the scatter) written straight into a head-grouped send buffer
+      -> ONE all-to-all (Q|K|V packed): [T/P, H, dh] -> [T, H/P, dh]
+      -> attention over all T tokens for H/P heads
+      -> ONE all-to-all back -> the to_out GEMM reads the head-group-major result in place (3-D TMA map).
+  Text cross-attention and audio->video attention have small replicated K/V: no communication.  The audio
+  stream (Ta ~ 68 tokens) is replicated; video->audio attention all-gathers the projected video K/V.
+* **CFG parallelism** (``CFGParallel``).  cond / uncond forwards of the dev pipeline are independent given the
+  latents (generate.py:1258-1283): two rank groups run one each and swap the (B, T, 128) velocity.
+"""
+from __future__ import annotations
+
+from dataclasses import replace
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .transformer import BF16, Modality, Workspace
+
+Tensor = torch.Tensor
+
+
+class CFGParallel:
+    """Ranks [0, world/2) run the conditional forward, ranks [world/2, world) the unconditional one."""
+
+    def __init__(self, world: int, rank: int) -> None:
+        if world % 2:
+            raise ValueError("CFG parallelism needs an even number of ranks")
+        half = world // 2
+        self.is_cond = rank < half
+        self.partner = rank + half if self.is_cond else rank - half
+        self.pair_group = None
+        for r in range(half):  # every rank creates every group, in the same order
+            g = dist.new_group([r, r + half])
+            if r == min(rank, self.partner):
+                self.pair_group = g
+
+    def exchange(self, mine: Tensor) -> Tuple[Tensor, Tensor]:
+        """-> (velocity_cond, velocity_uncond), both on every rank of the pair."""
+        mine = mine.contiguous()
+        both = [torch.empty_like(mine), torch.empty_like(mine)]
+        dist.all_gather(both, mine, group=self.pair_group)
+        return both[0], both[1]  # group ranks are ordered (cond, uncond)
+
+
+class UlyssesGroup:
+    """Head-scatter / sequence-gather all-to-all around video self-attention over ``ranks``."""
+
+    def __init__(self, ranks: List[int], rank: int, group=None) -> None:
+        self.ranks, self.size = list(ranks), len(ranks)
+        self.index = self.ranks.index(rank)
+        self.group = group
+        self._rope_cache: Dict[int, Tuple[Tensor, Tensor, Tuple[Tensor, Tensor]]] = {}
+
+    # ------------------------------------------------------------------ token sharding (pure torch + dist)
+    def local_slice(self, T: int) -> slice:
+        if T % self.size:
+            raise _lib.LtxbError(f"{T} video tokens do not split across {self.size} sequence-parallel ranks")
+        tl = T // self.size
+        return slice(self.index * tl, (self.index + 1) * tl)
+
+    def shard_modality(self, m: Modality) -> Modality:
+        T = m.latent.shape[1]
+        sl = self.local_slice(T)
+        ts = m.timesteps if m.timesteps.numel() == m.latent.shape[0] else m.timesteps[:, sl]
+        pe = m.positional_embeddings
+        if pe is not None:
+            key = pe[0].data_ptr()
+            hit = self._rope_cache.get(key)
+            if hit is None or hit[0] is not pe[0] or hit[1] is not pe[1]:
+                hit = (pe[0], pe[1], (pe[0][:, :, sl].contiguous(), pe[1][:, :, sl].contiguous()))
+                self._rope_cache = {key: hit}  # one live table at a time (constant across a denoise loop)
+            pe = hit[2]
+        return replace(m, latent=m.latent[:, sl].contiguous(), timesteps=ts.contiguous(), positions=m.positions[:, :, sl].contiguous(),
+                       positional_embeddings=pe)
+
+    def shard_inputs(self, video: Optional[Modality], audio: Optional[Modality]):
+        if video is not None and video.latent.shape[0] != 1:
+            raise _lib.LtxbError("sequence parallelism runs one video per group (use CFG parallelism or separate calls for B > 1)")
+        return (None if video is None else self.shard_modality(video)), audio  # the short audio stream is replicated
+
+    def gather_tokens(self, x: Tensor) -> Tensor:
+        """(B, T/P, C) on every rank -> (B, T, C)."""
+        x = x.contiguous()
+        parts = [torch.empty_like(x) for _ in range(self.size)]
+        dist.all_gather(parts, x, group=self.group)
+        return torch.cat(parts, dim=1)
+
+    def gather_outputs(self, vx: Optional[Tensor], ax: Optional[Tensor]):
+        return (None if vx is None else self.gather_tokens(vx)), ax
+
+    # ------------------------------------------------------------------ the exchanges
+    def all_to_all(self, send: Tensor, recv: Tensor) -> Tensor:
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv
+
+    def self_attention(self, attn, ws: Workspace, tag: str, xq: Tensor, B: int, Tl: int, pe) -> Tuple[Tensor, int]:
+        """Sequence-parallel attn1: xq bf16 [Tl, D] local rows -> (head-group-major attention output
+        bf16 [P, Tl, (H/P)*dh], group width) for the to_out GEMM."""
+        from . import ops
+
+        P, H, dh, inner, dev = self.size, attn.heads, attn.dim_head, attn.inner_dim, xq.device
+        if B != 1 or H % P:
+            raise _lib.LtxbError(f"sequence parallelism needs B == 1 and heads ({H}) divisible by ranks ({P})")
+        hp = H // P
+        qkv = ws.get(tag + ".qkv", (Tl, 3 * inner), BF16, dev)
+        ops.gemm(xq, attn.qkv_weight, attn.qkv_bias, qkv)
+        send = ws.get(tag + ".a2a_send", (P, Tl, 3, hp * dh), BF16, dev)
+        cos, sin = (None, None) if pe is None else pe
+        ops.qknorm_rope_scatter(qkv[:, :inner], send, 0, 3, P, 1, Tl, H, dh, attn.q_norm.weight, attn.q_norm.eps, cos, sin)
+        ops.qknorm_rope_scatter(qkv[:, inner:2 * inner], send, 1, 3, P, 1, Tl, H, dh, attn.k_norm.weight, attn.k_norm.eps, cos, sin)
+        ops.qknorm_rope_scatter(qkv[:, 2 * inner:], send, 2, 3, P, 1, Tl, H, dh, None, 0.0)
+        recv = self.all_to_all(send, ws.get(tag + ".a2a_recv", (P, Tl, 3, hp * dh), BF16, dev))
+        T = P * Tl
+        full = recv.view(T, 3 * hp * dh)  # chunk i came from rank i = tokens [i*Tl, (i+1)*Tl): already in token order
+        q, k, v = full[:, :hp * dh], full[:, hp * dh:2 * hp * dh], full[:, 2 * hp * dh:]
+        o = attn.sdpa(ws, tag + ".sp", q, k, v, 1, T, T, None, heads=hp)  # [T, hp*dh]
+        back = self.all_to_all(o.view(P, Tl, hp * dh), ws.get(tag + ".a2a_back", (P, Tl, hp * dh), BF16, dev))
+        return back, hp * dh
+
+    def video_to_audio(self, attn, ws: Workspace, a_in: Tensor, v_in: Tensor, Ba: int, Ta: int, Tl: int, ax: Tensor, a, v,
+                       gate: Tensor, gate_table: Tensor, row_div: int, row_index: Optional[Tensor]) -> None:
+        """v2a (transformer.py:326-339) with video rows sharded: project K/V on local rows, all-gather them,
+        attend redundantly on every rank (audio is replicated, so every rank computes the same update)."""
+        from . import ops
+
+        inner, dev = attn.inner_dim, a_in.device
+        q, k, vv = attn.project(ws, "av.v2a", a_in, Ba, Ta, v_in, Tl, a.cross_positional_embeddings, v.cross_positional_embeddings)
+        kv_local = ws.get("av.v2a.kv", (Ba * Tl, 2 * inner), BF16, dev)  # the buffer k / vv are views of
+        parts = ws.get("av.v2a.kv_all", (self.size, Ba * Tl, 2 * inner), BF16, dev)
+        dist.all_gather_into_tensor(parts, kv_local, group=self.group)
+        full = parts.view(self.size * Tl, 2 * inner)
+        o = attn.sdpa(ws, "av.v2a", q, full[:, :inner], full[:, inner:], Ba, Ta, self.size * Tl, None)
+        ops.gemm(o, attn.to_out.weight, attn.to_out.bias, ax, _lib.EPI_RESID_GATE_F32, resid=ax, gate=gate,
+                 gate_table=gate_table, gate_row_div=row_div, gate_row_index=row_index)
+
+
+class ParallelLayout:
+    """How ``world`` ranks are used: optional CFG split (2 groups) x Ulysses group inside each."""
+
+    def __init__(self, cfg: Optional[CFGParallel], ulysses: Optional[UlyssesGroup]) -> None:
+        self.cfg, self.ulysses = cfg, ulysses
+
+    def attach(self, model) -> None:
+        model.seq_parallel = self.ulysses
+
+    def describe(self) -> str:
+        parts = []
+        if self.cfg is not None:
+            parts.append("cfg2")
+        if self.ulysses is not None:
+            parts.append(f"ulysses{self.ulysses.size}")
+        return "x".join(parts) or "single"
+
+
+def plan(world: int, use_cfg: bool) -> Tuple[bool, int]:
+    """(split cond/uncond across two rank groups?, Ulysses degree)."""
+    if world < 1 or (world & (world - 1)):
+        raise ValueError("world size must be a power of two (1, 2, 4, 8 GPUs of one box)")
+    cfg = use_cfg and world >= 2
+    return cfg, (world // 2 if cfg else world)
+
+
+def make_layout(world: int, rank: int, use_cfg: bool) -> ParallelLayout:
+    cfg_split, sp = plan(world, use_cfg)
+    cfg = CFGParallel(world, rank) if cfg_split else None
+    uly = None
+    if sp > 1:
+        n_groups = world // sp
+        for gi in range(n_groups):  # all ranks create all groups in the same order
+            ranks = list(range(gi * sp, (gi + 1) * sp))
+            g = dist.new_group(ranks) if n_groups > 1 else None
+            if rank in ranks:
+                uly = UlyssesGroup(ranks, rank, g)
+    return ParallelLayout(cfg, uly)

@@ -203,14 +203,15 @@ class Attention:
               row_index: Optional[Tensor] = None, seq_parallel=None) -> None:
         """resid (f32 [B*Tq, query_dim]) += to_out(attention(...)) * gate, in place — the to_out GEMM's
         epilogue carries bias, gate and residual add (transformer.py:254,257-261)."""
-        q, k, v = self.project(ws, tag, xq, B, Tq, context, Tk, pe, k_pe)
-        Tk = Tq if context is None else Tk
-        if seq_parallel is not None and context is None:
-            o = seq_parallel.self_attention(self, ws, tag, q, k, v, B, Tq)
+        group_cols = 0
+        if seq_parallel is not None and context is None and self.is_self:
+            # rows are sharded across ranks: projections local, heads <-> sequence all-to-all around the attention
+            o, group_cols = seq_parallel.self_attention(self, ws, tag, xq, B, Tq, pe)
         else:
-            o = self.sdpa(ws, tag, q, k, v, B, Tq, Tk, kv_bias)
+            q, k, v = self.project(ws, tag, xq, B, Tq, context, Tk, pe, k_pe)
+            o = self.sdpa(ws, tag, q, k, v, B, Tq, Tq if context is None else Tk, kv_bias)
         ops.gemm(o, self.to_out.weight, self.to_out.bias, resid, _lib.EPI_RESID_GATE_F32, resid=resid, gate=gate,
-                 gate_table=gate_table, gate_row_div=row_div, gate_row_index=row_index)
+                 gate_table=gate_table, gate_row_div=row_div, gate_row_index=row_index, a_group_cols=group_cols)
 
     def __call__(self, x: Tensor, context: Optional[Tensor] = None, mask: Optional[Tensor] = None, pe=None,
                  k_pe=None) -> Tensor:
