@@ -82,3 +82,29 @@ def test_rope_base_frequencies_match_oracle():
     from mlx_video_b200.rope import rope_base_frequencies
     for n_axes, dim in [(3, 4096), (1, 2048), (3, 512), (1, 256)]:
         assert torch.equal(rope_base_frequencies(10000.0, n_axes, dim), O.rope_freq_indices(10000.0, n_axes, dim))
+
+
+def test_checkpoint_key_mapping_and_safetensors_roundtrip(tmp_path):
+    """ltx.py:508-533 key renames; header scan; transformer-only filtering."""
+    from safetensors.torch import save_file
+
+    from mlx_video_b200 import checkpoint as ck
+
+    P = "model.diffusion_model."
+    assert ck.sanitize_key(P + "transformer_blocks.3.attn1.to_out.0.weight") == "transformer_blocks.3.attn1.to_out.weight"
+    assert ck.sanitize_key(P + "transformer_blocks.0.ff.net.0.proj.bias") == "transformer_blocks.0.ff.proj_in.bias"
+    assert ck.sanitize_key(P + "transformer_blocks.0.audio_ff.net.2.weight") == "transformer_blocks.0.audio_ff.proj_out.weight"
+    assert ck.sanitize_key(P + "adaln_single.emb.timestep_embedder.linear_1.weight") == "adaln_single.emb.timestep_embedder.linear1.weight"
+    assert ck.sanitize_key(P + "caption_projection.linear_2.bias") == "caption_projection.linear2.bias"
+    assert ck.sanitize_key(P + "video_embeddings_connector.x.weight") is None and ck.sanitize_key("vae.decoder.conv.weight") is None
+    assert ck.sanitize_key("patchify_proj.weight") == "patchify_proj.weight"  # already sanitised
+    tensors = {P + "patchify_proj.weight": torch.randn(8, 4).bfloat16(), P + "transformer_blocks.0.attn1.to_out.0.bias": torch.randn(8),
+               "vae.decoder.w": torch.zeros(2), P + "audio_embeddings_connector.w": torch.zeros(2)}
+    save_file(tensors, str(tmp_path / "m.safetensors"))
+    assert sorted(ck.scan_keys([tmp_path / "m.safetensors"])) == sorted(tensors)
+    got = ck.load_transformer_weights(tmp_path)
+    assert sorted(got) == ["patchify_proj.weight", "transformer_blocks.0.attn1.to_out.bias"]
+    assert torch.equal(got["patchify_proj.weight"], tensors[P + "patchify_proj.weight"])
+    save_file({P + "x.weight": torch.zeros(2), P + "x.scales": torch.zeros(2)}, str(tmp_path / "q.safetensors"))
+    with pytest.raises(ValueError, match="quantised"):
+        ck.load_transformer_weights(tmp_path / "q.safetensors")
