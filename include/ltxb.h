@@ -91,12 +91,12 @@ int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void*
                    int32_t N, int32_t K, const ltxb_epilogue* epi, int32_t block_n, int32_t cta_pair,
                    void* stream);
 
-/* Stream-K scheduling scratch for ltxb_gemm_bf16.  The library never allocates: the host hands it one device
- * buffer of ltxb_gemm_workspace_bytes() per device (kept until replaced; NULL unregisters).  With a workspace
- * registered, problems whose tile count leaves a ragged last wave on the 148 SMs (M = 1280 tokens ...) are cut
- * into equal k-block ranges per SM; tiles cut across SMs are summed in k order by the last contributor to
- * arrive (bit-reproducible).  Without one, every GEMM runs data-parallel.  GEMMs sharing a workspace must be
- * issued on one stream. */
+/* Split-K scratch for ltxb_gemm_bf16.  The library never allocates: the host hands it one device buffer of
+ * ltxb_gemm_workspace_bytes() per device (kept until replaced; NULL unregisters).  With a workspace registered,
+ * a problem whose tile count leaves a ragged wave on the 148 SMs (M = 1280 tokens: 80 tiles for 74 SM pairs) runs
+ * the leftover tiles first, each cut into 2-4 k-ranges on different SM pairs; the pair holding a tile's first
+ * k-range adds the others' parked fp32 partials in k order (bit-reproducible) and applies the epilogue.  Without
+ * a workspace every GEMM runs data-parallel.  GEMMs sharing a workspace must be issued on one stream. */
 int64_t ltxb_gemm_workspace_bytes(void);
 int ltxb_gemm_set_workspace(void* workspace, int64_t bytes, void* stream);
 

@@ -51,48 +51,42 @@ struct GemmParams {
   const int* gate_row_index;
   const float* gate_table;
   int a_group_cols;  // > 0: A is [groups][M][a_group_cols] (a 3-D tensor map), K index = group * a_group_cols + col
-  // stream-K (sk == 0: data-parallel tile striding)
-  int sk;
-  int total_units;     // num_tiles * (K / kBlockK)
-  float* sk_partials;  // [clusters][2][ctas][kBlockM * block_n] fp32 partial accumulators
-  int* sk_counters;    // [num_tiles][ctas] arrivals per output tile; zero outside a launch
+  // split-K of the ragged wave (sk_splits <= 1: plain data-parallel tile striding)
+  int sk_rem;          // number of tiles in the ragged wave (tile indices [0, sk_rem))
+  int sk_splits;       // k-range pieces per such tile
+  float* sk_partials;  // [clusters][ctas][kBlockM * block_n] fp32 parked partial accumulators
+  int* sk_counters;    // [sk_rem][ctas] arrivals per cut tile; zero outside a launch
 };
 
-// One unit = one 64-wide k-block of one output tile.  Data-parallel mode hands whole tiles to clusters
-// round-robin; stream-K mode cuts the linear (tile, k-block) space into equal contiguous ranges, one per
-// cluster, so every SM works the same number of k-blocks whatever the tile count (M = 1280 gives 80 tiles
-// for 74 SM pairs: 2 waves data-parallel, 1.08 stream-K).  A tile cut across clusters is finished by
-// whichever contributor arrives last, summing the partials in k order (deterministic, no spinning).
+// Tiles are dealt to clusters round-robin, all clusters marching through K in lockstep (tiles that share an A
+// or W panel then hit it in L2 while it is hot).  When the tile count leaves a ragged wave — M = 1280 gives 80
+// tiles for 74 SM pairs — the `sk_rem` leftover tiles are run FIRST, each cut into `sk_splits` k-ranges on
+// different clusters (still in lockstep), so the wave costs 1/sk_splits of a tile instead of a whole one.  The
+// cluster holding a cut tile's first k-range owns its epilogue: the others park their fp32 partial in L2 and
+// signal; the owner adds them in k order (bit-reproducible) while its next tile's main loop is already running.
 struct WorkItem {
   int tile, kb0, kb1;
 };
-__device__ __forceinline__ int sk_unit_begin(int total_units, int slots, int c) {
-  return static_cast<int>((static_cast<long long>(total_units) * c) / slots);
-}
-__device__ __forceinline__ int sk_cluster_of(int total_units, int slots, int unit) {
-  int c = static_cast<int>((static_cast<long long>(unit) * slots) / total_units);
-  while (c + 1 < slots && sk_unit_begin(total_units, slots, c + 1) <= unit) ++c;
-  while (c > 0 && sk_unit_begin(total_units, slots, c) > unit) --c;
-  return c;
-}
 struct WorkIter {
-  int num_kb, num_tiles, stride, tile, u, u_end;
-  // Hybrid schedule: the first `sk_tiles` tiles (total_units = sk_tiles * num_kb) are stream-K'd — cut into equal
-  // contiguous k-block ranges, one per cluster — then the remaining tiles (a whole number of waves) are dealt
-  // round-robin.  Stream-K goes FIRST so that finishing a cut tile overlaps the next tile's main loop.
+  int num_kb, num_tiles, stride, tile, split_tile, split_kb0, split_kb1;
   __device__ WorkIter(const GemmParams& p, int cluster_id, int num_clusters, int num_kb_)
-      : num_kb(num_kb_), num_tiles(p.num_m_tiles * p.num_n_tiles), stride(num_clusters) {
-    u = p.sk ? sk_unit_begin(p.total_units, num_clusters, cluster_id) : 0;
-    u_end = p.sk ? sk_unit_begin(p.total_units, num_clusters, cluster_id + 1) : 0;
-    tile = (p.sk ? p.total_units / num_kb_ : 0) + cluster_id;
+      : num_kb(num_kb_), num_tiles(p.num_m_tiles * p.num_n_tiles), stride(num_clusters), split_tile(-1) {
+    int first = 0;
+    if (p.sk_splits > 1) {
+      first = p.sk_rem;
+      if (cluster_id < p.sk_rem * p.sk_splits) {
+        const int piece = cluster_id / p.sk_rem;  // consecutive clusters take consecutive tiles of the same k-range
+        split_tile = cluster_id % p.sk_rem;
+        split_kb0 = (num_kb_ * piece) / p.sk_splits;
+        split_kb1 = (num_kb_ * (piece + 1)) / p.sk_splits;
+      }
+    }
+    tile = first + cluster_id;
   }
   __device__ __forceinline__ bool next(WorkItem& w) {
-    if (u < u_end) {
-      w.tile = u / num_kb;
-      w.kb0 = u - w.tile * num_kb;
-      const int len = min(num_kb - w.kb0, u_end - u);
-      w.kb1 = w.kb0 + len;
-      u += len;
+    if (split_tile >= 0) {
+      w.tile = split_tile, w.kb0 = split_kb0, w.kb1 = split_kb1;
+      split_tile = -1;
       return true;
     }
     if (tile >= num_tiles) return false;
@@ -108,7 +102,6 @@ struct GemmSmemHeader {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
-  int sk_arrival;  // stream-K: this CTA's arrival number on the current tile
 };
 static_assert(sizeof(GemmSmemHeader) <= kSmemHeader, "header overflow");
 
@@ -328,9 +321,50 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           grow = p.gate_row_index != nullptr ? p.gate_row_index[row] : row / p.gate_row_div;
       }
       const bool partial = (w.kb0 > 0) || (w.kb1 < num_kb);
+      // ---- stream-K roles for a cut tile.  The cluster holding the tile's FIRST k-range (kb0 == 0) owns its
+      // epilogue and reaches it as the LAST item of its range; every other holder (kb0 > 0) reaches its piece as
+      // the FIRST item of its range, parks the fp32 partial in its slot and signals.  By the time the owner gets
+      // there the partials have been sitting in L2 for most of a tile, so its wait is a formality and it can pull
+      // them in underneath its own main loop.
+      const bool owner = partial && w.kb0 == 0;
+      const size_t slot_elems = static_cast<size_t>(kBlockM) * bn;
+      // slot layout [32-col chunk][float4 index 0..7][row 0..127]: for a fixed float4 index the 32 lanes of a warp
+      // touch 512 contiguous bytes, so both the dump and the reload are fully coalesced
+      constexpr int kF4Stride = kBlockM;
+      auto chunk_of = [&](int cluster, int c) {
+        float* slot = p.sk_partials + (static_cast<size_t>(cluster) * kCtas + cta_rank) * slot_elems;
+        return reinterpret_cast<float4*>(slot + static_cast<size_t>(c / 32) * (kBlockM * 32)) + row_in_cta;
+      };
+      int* counter = p.sk_counters + w.tile * kCtas + static_cast<int>(cta_rank);
+      int others = 0;  // owner: number of parked partials to add (clusters cluster_id+1 .. cluster_id+others)
+      if (owner) {
+        others = p.sk_splits - 1;
+        if (row_in_cta == 0) {
+          const long long t0 = clock64();
+          while (*reinterpret_cast<volatile int*>(counter) < others) {
+            if (clock64() - t0 > LTXB_WATCHDOG_CYCLES) {
+              printf("ltxb: split-K watchdog: tile %d waits for %d partials\n", w.tile, others);
+              __trap();
+            }
+          }
+          *counter = 0;  // every contributor has arrived; ready for the next launch
+        }
+        epilogue_bar_sync();
+        __threadfence();
+      }
       mbar_wait(&hdr->tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccStride;
+      auto finish_chunk = [&](const float* v, int c, int width) {
+        const int col = n0 + c;
+        if (!row_ok) return;
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+        if (width == 32 && col + 32 <= p.N) {
+          epilogue_store<kEpi, 32>(p, r, row, col, grow);
+        } else if (col + 16 <= p.N) {
+          epilogue_store<kEpi, 16>(p, r, row, col, grow);
+        }
+      };
       if (!partial) {
         for (int c = 0; c < bn; c += 32) {
           const bool last = (c + 32 >= bn);
@@ -355,23 +389,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (row_ok && col + 16 <= p.N) epilogue_store<kEpi, 16>(p, r, row, col, grow);
           }
         }
-      } else {
-        // ---- stream-K: this cluster holds only k-blocks [kb0, kb1) of the tile.
-        // 1. park the fp32 partial in this cluster's slot ([32-col chunk][row][32] so a thread's 128 B are
-        //    contiguous); the accumulator stays in TMEM until we know whether we finish the tile
-        const size_t slot_elems = static_cast<size_t>(kBlockM) * bn;
-        auto slot_of = [&](int cluster, bool head) {
-          return p.sk_partials + (static_cast<size_t>(cluster * 2 + (head ? 0 : 1)) * kCtas + cta_rank) * slot_elems;
-        };
-        // slot layout [32-col chunk][float4 index 0..7][row 0..127]: for a fixed float4 index the 32 lanes of a
-        // warp touch 512 contiguous bytes, so both the dump and the reload are fully coalesced
-        constexpr int kF4Stride = kBlockM;  // float4s between consecutive float4 indices of one row
-        auto chunk_of = [&](float* slot, int c) {
-          return reinterpret_cast<float4*>(slot + static_cast<size_t>(c / 32) * (kBlockM * 32)) + row_in_cta;
-        };
-        float* mine = slot_of(cluster_id, w.kb0 > 0);
+      } else if (!owner) {
+        // ---- contributor: park the partial, publish it, move on
         for (int c = 0; c < bn; c += 32) {
-          float4* dst = chunk_of(mine, c);
+          float4* dst = chunk_of(cluster_id, c);
           if (c + 32 <= bn) {
             uint32_t r[32];
             tmem_ld_x32(t_row + c, r);
@@ -388,89 +409,60 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               __stcg(dst + i * kF4Stride, make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
           }
         }
-        // 2. announce it; the LAST contributor to arrive finishes the tile (nobody ever waits)
+        release_acc();
         __threadfence();
         epilogue_bar_sync();
-        int* counter = p.sk_counters + w.tile * kCtas + static_cast<int>(cta_rank);
-        if (row_in_cta == 0) hdr->sk_arrival = atomicAdd(counter, 1);
-        epilogue_bar_sync();
-        const int tile_u0 = w.tile * num_kb;
-        const int first_c = sk_cluster_of(p.total_units, num_clusters, tile_u0);
-        const int last_c = sk_cluster_of(p.total_units, num_clusters, tile_u0 + num_kb - 1);
-        const bool finisher = *reinterpret_cast<volatile int*>(&hdr->sk_arrival) == last_c - first_c;
-        if (!finisher) {
-          release_acc();
-        } else {
-          __threadfence();
-          auto finish_chunk = [&](const float* v, int c, int width) {
-            const int col = n0 + c;
-            if (!row_ok) return;
-            const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
-            if (width == 32 && col + 32 <= p.N) {
-              epilogue_store<kEpi, 32>(p, r, row, col, grow);
-            } else if (col + 16 <= p.N) {
-              epilogue_store<kEpi, 16>(p, r, row, col, grow);
-            }
-          };
-          if (last_c - first_c == 1 && (bn & 31) == 0) {
-            // two contributors (the common cut): own partial still sits in TMEM, the other's comes from L2.
-            // Loads for four 32-column chunks are in flight together (32 x 16 B per thread) — the fix-up is
-            // a latency-bound L2 read, so memory-level parallelism is what makes it cheap.  a + b == b + a
-            // in fp32, so the result does not depend on which of the two finishes.
-            const int other_c = (cluster_id == first_c) ? last_c : first_c;
-            float* other = slot_of(other_c, sk_unit_begin(p.total_units, num_clusters, other_c) > tile_u0);
-            for (int g = 0; g < bn; g += 128) {
-              float4 ld[4][8];
+        if (row_in_cta == 0) atomicAdd(counter, 1);
+      } else {
+        // ---- owner: own accumulator (TMEM) + the parked partials of pieces 1.. in k order.  The loads of up to
+        // three partials for a 32-column chunk are issued together (the fix-up is a latency-bound L2 read).
+        for (int c = 0; c < bn; c += 32) {
+          const int width = (c + 32 <= bn) ? 32 : 16;
+          float4 ld[3][8];
+          const int batch = min(others, 3);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (g + 32 * j < bn) {
-                  const float4* src = chunk_of(other, g + 32 * j);
+          for (int o = 0; o < 3; ++o) {
+            if (o < batch) {
+              const float4* src = chunk_of(cluster_id + (o + 1) * p.sk_rem, c);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) ld[j][i] = __ldcg(src + i * kF4Stride);
-                }
-              }
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int c = g + 32 * j;
-                if (c < bn) {
-                  uint32_t r[32];
-                  tmem_ld_x32(t_row + c, r);
-                  tmem_wait_ld();
-                  if (c + 32 >= bn) release_acc();
-                  float v[32];
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + ld[j][i].x;
-                    v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + ld[j][i].y;
-                    v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + ld[j][i].z;
-                    v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + ld[j][i].w;
-                  }
-                  finish_chunk(v, c, 32);
-                }
-              }
-            }
-          } else {
-            // general cut: sum every contributor's parked partial in k order (fixed order: bit-reproducible)
-            release_acc();
-            for (int c = 0; c < bn; c += 32) {
-              const int width = (c + 32 <= bn) ? 32 : 16;
-              float accv[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) accv[i] = 0.f;
-              for (int cc = first_c; cc <= last_c; ++cc) {
-                const float4* src = chunk_of(slot_of(cc, sk_unit_begin(p.total_units, num_clusters, cc) > tile_u0), c);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  if (i * 4 < width) {
-                    const float4 v = __ldcg(src + i * kF4Stride);
-                    accv[4 * i] += v.x, accv[4 * i + 1] += v.y, accv[4 * i + 2] += v.z, accv[4 * i + 3] += v.w;
-                  }
-                }
-              }
-              finish_chunk(accv, c, width);
+              for (int i = 0; i < 8; ++i)
+                if (i * 4 < width) ld[o][i] = __ldcg(src + i * kF4Stride);
             }
           }
-          if (row_in_cta == 0) *counter = 0;  // ready for the next launch
+          float v[32];
+          if (width == 32) {
+            uint32_t r[32];
+            tmem_ld_x32(t_row + c, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          } else {
+            uint32_t r[16];
+            tmem_ld_x16(t_row + c, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]), v[16 + i] = 0.f;
+          }
+          if (c + 32 >= bn) release_acc();
+#pragma unroll
+          for (int o = 0; o < 3; ++o) {
+            if (o < batch) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (i * 4 < width) v[4 * i] += ld[o][i].x, v[4 * i + 1] += ld[o][i].y, v[4 * i + 2] += ld[o][i].z, v[4 * i + 3] += ld[o][i].w;
+            }
+          }
+          for (int o = 3; o < others; ++o) {
+            const float4* src = chunk_of(cluster_id + (o + 1) * p.sk_rem, c);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (i * 4 < width) {
+                const float4 t = __ldcg(src + i * kF4Stride);
+                v[4 * i] += t.x, v[4 * i + 1] += t.y, v[4 * i + 2] += t.z, v[4 * i + 3] += t.w;
+              }
+            }
+          }
+          finish_chunk(v, c, width);
         }
       }
       if (++acc == 2) acc = 0, acc_phase ^= 1;
@@ -513,7 +505,9 @@ static TileChoice choose_tile(int M, int N, int sms, int want_bn, int want_pair)
       const int n_tiles = (N + bn - 1) / bn;
       const long long tiles = 1ll * m_tiles * n_tiles;
       const long long waves = (tiles + slots - 1) / slots;
-      double cost = static_cast<double>(waves) * (bn + 12.0);
+      // measured (scripts/gemm_sweep.py, profiles/): a tile's main-loop time barely depends on BN between 128 and
+      // 256 — the SS-mode operand fetch paces the MMA — so a narrower tile only pays when it removes a whole wave
+      double cost = static_cast<double>(waves) * (std::max(bn, 224) + 12.0) - 0.01 * bn;
       if (ctas == 1) cost *= 1.03;  // pairs halve the W traffic per SM: prefer them on ties
       if (cost < best.cost) best = TileChoice{bn, ctas, cost};
     }
@@ -524,7 +518,7 @@ static TileChoice choose_tile(int M, int N, int sms, int want_bn, int want_pair)
 // ---- stream-K workspace: registered by the host framework (the library never allocates) -----------
 constexpr int kMaxDevices = 16;
 constexpr long long kSkCounterInts = 1 << 16;                                  // arrivals: [tiles][ctas]
-constexpr long long kSkPartialBytes = 148ll * 2 * kBlockM * 256 * sizeof(float);  // [<=148 CTAs][2 slots][128 x 256] fp32
+constexpr long long kSkPartialBytes = 148ll * kBlockM * 256 * sizeof(float);  // [<=148 CTAs][128 x 256] fp32 parked partials
 struct SkWorkspace {
   int* counters = nullptr;
   float* partials = nullptr;
@@ -533,13 +527,13 @@ static SkWorkspace g_sk_ws[kMaxDevices];
 
 struct SkChoice {
   bool use;
-  int block_n, ctas, sk_tiles;
+  int block_n, ctas, rem, splits;
 };
-// Stream-K pays when data-parallel tiling leaves a ragged last wave.  The stream-K region is the ragged
-// remainder plus one full wave, so every cluster's share is at least one tile's worth of k-blocks and a cut
-// tile has exactly two contributors (the cheap fix-up).  Costs are in k-block units per cluster.
-static SkChoice choose_stream_k(int M, int N, int K, int sms, int want_bn, int want_pair, const TileChoice& dp) {
-  SkChoice none{false, 0, 0, 0};
+// Split the ragged wave in K when that beats running it as a whole wave.  Costs in k-blocks of main loop per
+// cluster; parking + adding a partial costs the owner roughly `kFixup` k-blocks per contributor (hidden behind
+// its next tile when one follows).
+static SkChoice choose_split_k(int M, int N, int K, int sms, int want_bn, int want_pair, const TileChoice& dp) {
+  SkChoice none{false, 0, 0, 0, 0};
   if (want_bn > 0) return none;  // an explicit tile request means "run exactly this" (tests, sweeps)
   const int ctas = (want_pair == 0 || (want_pair < 0 && M <= kBlockM)) ? 1 : 2;
   const int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
@@ -547,25 +541,20 @@ static SkChoice choose_stream_k(int M, int N, int K, int sms, int want_bn, int w
   const int slots = sms / ctas;
   const int num_kb = K / kBlockK;
   const long long tiles = 1ll * ((M + kBlockM * ctas - 1) / (kBlockM * ctas)) * ((N + bn - 1) / bn);
-  if (tiles * ctas > kSkCounterInts || tiles * num_kb > (1ll << 30)) return none;
   const long long waves = tiles / slots, rem = tiles % slots;
-  if (rem == 0) return none;
-  const long long sk_tiles = rem + (waves >= 1 ? slots : 0);
-  const long long per = (sk_tiles * num_kb + slots - 1) / slots;  // k-blocks per cluster inside the region
-  if (per < 16) return none;  // slivers: the fix-up traffic would dominate
-  const long long contributors = (num_kb + per - 1) / per + 1;
-  // measured on B200 (scripts/gemm_sweep.py): parking + finishing a cut tile costs about as much as 60 k-blocks
-  // of main loop when it ends the kernel, ~40 when later tiles follow — so stream-K only pays for long-K problems
-  // (the FFN down-projection, K = 16384: +25 %)
-  const double fixup = (waves >= 2 ? 40.0 : 60.0) + 20.0 * static_cast<double>(contributors - 2);
-  const double t_sk = static_cast<double>(per) + static_cast<double>(waves >= 1 ? waves - 1 : 0) * num_kb + fixup;
-  // the data-parallel alternative, in the same units (per-tile time is ~independent of BN below 256: the
-  // SS-mode A-operand read paces the MMA)
+  if (rem == 0 || rem * ctas > kSkCounterInts) return none;
+  static const int env_max = [] { const char* e = getenv("LTXB_SK_MAX_SPLITS"); return e ? atoi(e) : 8; }();
+  static const double env_fixup = [] { const char* e = getenv("LTXB_SK_FIXUP"); return e ? atof(e) : 6.0; }();
+  int splits = static_cast<int>(std::min<long long>(slots / rem, env_max));
+  splits = std::min(splits, num_kb / 16);  // pieces of at least 16 k-blocks (measured: 8 is past the optimum)
+  if (splits < 2) return none;
+  const double fixup = env_fixup * (splits - 1) * (waves >= 1 ? 0.5 : 1.0);
+  const double t_sk = static_cast<double>(waves) * num_kb + static_cast<double>((num_kb + splits - 1) / splits) + fixup;
   const int dp_slots = sms / dp.ctas;
   const long long dp_tiles = 1ll * ((M + kBlockM * dp.ctas - 1) / (kBlockM * dp.ctas)) * ((N + dp.block_n - 1) / dp.block_n);
   const double t_dp = static_cast<double>((dp_tiles + dp_slots - 1) / dp_slots) * num_kb;
   if (t_sk * 1.03 >= t_dp) return none;
-  return SkChoice{true, bn, ctas, static_cast<int>(sk_tiles)};
+  return SkChoice{true, bn, ctas, static_cast<int>(rem), splits};
 }
 
 template <int kCtas, int kEpi>
@@ -636,8 +625,8 @@ extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   int dev = 0;
   cudaGetDevice(&dev);
   const SkWorkspace ws = (dev >= 0 && dev < kMaxDevices) ? g_sk_ws[dev] : SkWorkspace{};
-  SkChoice sk{false, 0, 0, 0};
-  if (env_sk && ws.partials != nullptr) sk = choose_stream_k(M, N, K, sms, block_n, cta_pair, tc);
+  SkChoice sk{false, 0, 0, 0, 0};
+  if (env_sk && ws.partials != nullptr) sk = choose_split_k(M, N, K, sms, block_n, cta_pair, tc);
   const int ctas = sk.use ? sk.ctas : tc.ctas;
   const int bn = sk.use ? sk.block_n : tc.block_n;
   if (ctas == 2) LTXB_CHECK_SUPPORTED(bn % 16 == 0 && (bn / 2) % 8 == 0, "pair mode needs block_n %% 16 == 0");
@@ -690,9 +679,9 @@ extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   int clusters = std::min(num_tiles, sms / ctas);
   if (sk.use) {
-    clusters = sms / ctas;
-    p.sk = 1;
-    p.total_units = sk.sk_tiles * (K / kBlockK);
+    clusters = std::min(sms / ctas, std::max(num_tiles, sk.rem * sk.splits));
+    p.sk_rem = sk.rem;
+    p.sk_splits = sk.splits;
     p.sk_partials = ws.partials;
     p.sk_counters = ws.counters;
   }

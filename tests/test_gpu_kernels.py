@@ -69,9 +69,9 @@ def test_gemm_explicit_tiles(pair, bn):
         gemm_case(M, N, K, _lib.EPI_BIAS_F32, pair=pair, bn=bn)
 
 
-def test_gemm_stream_k_matches_data_parallel_and_is_reproducible():
+def test_gemm_split_k_matches_data_parallel_and_is_reproducible():
     """An explicit block_n forces the data-parallel schedule; auto picks stream-K for this shape.  Both must
-    agree to fp32 summation order, and stream-K must be bit-reproducible run to run (fixed k-order fix-up)."""
+    agree to fp32 summation order, and split-K must be bit-reproducible run to run (fixed k-order fix-up)."""
     for M, N, K in [(1280, 4096, 4096), (1280, 4096, 16384), (1024, 8192, 4096)]:
         sk1 = gemm_case(M, N, K, _lib.EPI_BIAS_F32)
         sk2 = gemm_case(M, N, K, _lib.EPI_BIAS_F32)
