@@ -13,7 +13,7 @@ from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
 CSRC = _HERE / "csrc"
-LIB_PATH = CSRC / "libltxb.so"
+LIB_PATH = Path(os.environ["LTXB_LIB"]) if os.environ.get("LTXB_LIB") else CSRC / "libltxb.so"  # LTXB_LIB: A/B a build
 
 # (name, restype, argtypes) — must list EVERY symbol declared in include/ltxb.h (tests check this).
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p

@@ -28,7 +28,8 @@ constexpr int kBlockM = 128;  // rows of the output tile owned by ONE CTA (TMEM 
 constexpr int kBlockK = 64;   // 64 bf16 = 128 B = one swizzle span
 constexpr int kUmmaK = 16;
 constexpr int kMaxStages = 8;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kEpiThreads = 256;
 constexpr int kSmemHeader = 1024;  // barriers + tmem pointer live in front of the tile ring
 constexpr int kTmemCols = 512;
 constexpr uint32_t kAccStride = 256;  // TMEM column stride between the two accumulators
@@ -105,7 +106,7 @@ struct GemmSmemHeader {
 };
 static_assert(sizeof(GemmSmemHeader) <= kSmemHeader, "header overflow");
 
-__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // Apply the fused epilogue to `n` (16 or 32) consecutive accumulator columns of one output row.
 template <int kEpi, int kCols>
@@ -213,7 +214,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&hdr->tmem_full[a], 1);
-        mbar_init(&hdr->tmem_empty[a], 4 * kCtas);
+        mbar_init(&hdr->tmem_empty[a], 8 * kCtas);
       }
       fence_mbar_init();
     }
@@ -298,6 +299,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else {
     // ===================== epilogue warps =====================
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
+    // two warps share each lane quarter and split the tile's 32-column chunks between them: the epilogue is a
+    // chain of dependent memory round trips per chunk, so doubling the warps halves its (exposed) latency
+    const int col_half = (warp - 2) >> 2;
+    const int n_chunks = (bn + 31) / 32;
+    const int c_begin = (col_half == 0 ? 0 : (n_chunks + 1) / 2) * 32;
+    const int c_end = min(bn, (col_half == 0 ? (n_chunks + 1) / 2 : n_chunks) * 32);
+    const bool epi_leader = (warp == 2 && lane == 0);
     const int row_in_cta = quarter * 32 + lane;
     uint32_t acc = 0, acc_phase = 0;
     auto release_acc = [&]() {  // all of this warp's TMEM reads of the accumulator have completed
@@ -339,7 +347,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int others = 0;  // owner: number of parked partials to add (clusters cluster_id+1 .. cluster_id+others)
       if (owner) {
         others = p.sk_splits - 1;
-        if (row_in_cta == 0) {
+        if (epi_leader) {
           const long long t0 = clock64();
           while (*reinterpret_cast<volatile int*>(counter) < others) {
             if (clock64() - t0 > LTXB_WATCHDOG_CYCLES) {
@@ -365,9 +373,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           epilogue_store<kEpi, 16>(p, r, row, col, grow);
         }
       };
+      if (c_begin >= c_end && !(partial && !owner)) release_acc();  // nothing to read for this warp (narrow tile)
       if (!partial) {
-        for (int c = 0; c < bn; c += 32) {
-          const bool last = (c + 32 >= bn);
+        for (int c = c_begin; c < c_end; c += 32) {
+          const bool last = (c + 32 >= c_end);
           const int col = n0 + c;
           if (c + 32 <= bn) {
             uint32_t r[32];
@@ -391,7 +400,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       } else if (!owner) {
         // ---- contributor: park the partial, publish it, move on
-        for (int c = 0; c < bn; c += 32) {
+        for (int c = c_begin; c < c_end; c += 32) {
           float4* dst = chunk_of(cluster_id, c);
           if (c + 32 <= bn) {
             uint32_t r[32];
@@ -412,16 +421,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         release_acc();
         __threadfence();
         epilogue_bar_sync();
-        if (row_in_cta == 0) atomicAdd(counter, 1);
+        if (epi_leader) atomicAdd(counter, 1);
       } else {
         // ---- owner: own accumulator (TMEM) + the parked partials of pieces 1.. in k order.  The loads of up to
         // three partials for a 32-column chunk are issued together (the fix-up is a latency-bound L2 read).
-        for (int c = 0; c < bn; c += 32) {
+        for (int c = c_begin; c < c_end; c += 32) {
           const int width = (c + 32 <= bn) ? 32 : 16;
-          float4 ld[3][8];
-          const int batch = min(others, 3);
+          float4 ld[2][8];
+          const int batch = min(others, 2);
 #pragma unroll
-          for (int o = 0; o < 3; ++o) {
+          for (int o = 0; o < 2; ++o) {
             if (o < batch) {
               const float4* src = chunk_of(cluster_id + (o + 1) * p.sk_rem, c);
 #pragma unroll
@@ -443,16 +452,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]), v[16 + i] = 0.f;
           }
-          if (c + 32 >= bn) release_acc();
+          if (c + 32 >= c_end) release_acc();
 #pragma unroll
-          for (int o = 0; o < 3; ++o) {
+          for (int o = 0; o < 2; ++o) {
             if (o < batch) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 if (i * 4 < width) v[4 * i] += ld[o][i].x, v[4 * i + 1] += ld[o][i].y, v[4 * i + 2] += ld[o][i].z, v[4 * i + 3] += ld[o][i].w;
             }
           }
-          for (int o = 3; o < others; ++o) {
+          for (int o = 2; o < others; ++o) {
             const float4* src = chunk_of(cluster_id + (o + 1) * p.sk_rem, c);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
