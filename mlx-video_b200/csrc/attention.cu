@@ -9,9 +9,12 @@
 //   warp 0      TMA producer: Q once, then K and V tiles into 2-deep rings
 //   warp 1      MMA issuer:   S_j = Q K_j^T  (K-major x K-major)      -> TMEM S[j&1]   (128 fp32 cols)
 //                             O  += P_j V_j  (K-major x MN-major V)   -> TMEM O        (dh fp32 cols)
-//   warps 2..5  softmax: thread = query row (TMEM lane). S row -> registers, running max / sum in
-//               log2 domain, P_j -> smem as bf16 in the canonical 128B-swizzled K-major layout,
-//               O rescaled in TMEM only when a row maximum moved; final O / l -> global bf16.
+//   warps 2..9  softmax: TWO threads per query row (TMEM lane), one per half of the 128 score columns —
+//               two warps per SM sub-partition, so one warp's dependent ALU / MUFU latencies hide behind the
+//               other's (with a single warp per sub-partition the kernel was softmax-issue bound).  The halves
+//               exchange their row maxima through smem (one named barrier per KV tile), keep partial row sums,
+//               write their half of P_j to smem as bf16 in the canonical 128B-swizzled K-major layout and
+//               rescale / store their half of the O columns.  O is rescaled in TMEM only when a maximum moved.
 // S_{j+1} is issued before P_j V_j, so the tensor core computes the next scores while the softmax
 // warps work on the current ones.
 #include "common.cuh"
@@ -19,10 +22,11 @@
 
 namespace ltxb {
 
-constexpr int kAttnThreads = 192;
+constexpr int kSplit = 2;  // softmax threads per query row
+constexpr int kAttnThreads = 64 + 128 * kSplit;
 constexpr int kTileQ = 128;
 constexpr int kTileKV = 128;
-constexpr int kAttnHeader = 1024;
+constexpr int kAttnHeader = 4096;
 constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO = 256;
 
 struct AttnParams {
@@ -41,6 +45,7 @@ struct AttnSmemHeader {
   uint64_t p_full;
   uint64_t pv_done;
   uint32_t tmem_base;
+  float row_stat[2][kSplit][128];  // per-tile partial row maxima (double-buffered); partial row sums at the end
 };
 static_assert(sizeof(AttnSmemHeader) <= kAttnHeader, "header overflow");
 
@@ -82,9 +87,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         mbar_init(&hdr->v_full[i], 1);
         mbar_init(&hdr->v_empty[i], 1);
         mbar_init(&hdr->s_full[i], 1);
-        mbar_init(&hdr->s_empty[i], 128);
+        mbar_init(&hdr->s_empty[i], 128 * kSplit);
       }
-      mbar_init(&hdr->p_full, 128);
+      mbar_init(&hdr->p_full, 128 * kSplit);
       mbar_init(&hdr->pv_done, 1);
       fence_mbar_init();
     }
@@ -164,42 +169,46 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
     }
   } else {
-    // ===================== softmax / correction / epilogue (128 threads, thread = query row) =========
+    // ===================== softmax / correction / epilogue (kSplit threads per query row) =========
+    constexpr int kCols = 128 / kSplit;   // score columns per thread
+    constexpr int kOCols = kDh / kSplit;  // O columns per thread
+    static_assert(kCols % 32 == 0 && kOCols % 32 == 0, "column split must keep 32-column TMEM accesses");
     const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
+    const int part = (warp - 2) >> 2;    // which column slice of the row this thread owns
+    const int r = quarter * 32 + lane;   // row inside the tile == TMEM lane
+    const int c0 = part * kCols;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    auto softmax_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(128 * kSplit) : "memory"); };
     float m = -INFINITY, l = 0.f;
     constexpr float kLog2e = 1.4426950408889634f;
     for (int it = 0; it < n_kv; ++it) {
       const int st = it & 1;
       mbar_wait(&hdr->s_full[st], (it >> 1) & 1);
       tc_fence_after_sync();
-      uint32_t sr[128];
+      uint32_t sr[kCols];
       {
-        const uint32_t t_s = t_lane + (st ? kColS1 : kColS0);
-        tmem_ld_x32(t_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
-        tmem_ld_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
-        tmem_ld_x32(t_s + 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[64]));
-        tmem_ld_x32(t_s + 96, *reinterpret_cast<uint32_t(*)[32]>(&sr[96]));
+        const uint32_t t_s = t_lane + (st ? kColS1 : kColS0) + c0;
+#pragma unroll
+        for (int c = 0; c < kCols; c += 32) tmem_ld_x32(t_s + c, *reinterpret_cast<uint32_t(*)[32]>(&sr[c]));
         tmem_wait_ld();
       }
       tc_fence_before_sync();
       mbar_arrive(&hdr->s_empty[st]);
 
-      const int kv_valid = p.Tk - it * kTileKV;  // >= 1
+      const int kv_valid = p.Tk - it * kTileKV - c0;  // valid columns of this thread's slice (may be <= 0)
       float mt = -INFINITY;
       if (p.kv_bias != nullptr) {
-        const float* bias = p.kv_bias + static_cast<long long>(b) * p.Tk + it * kTileKV;
+        const float* bias = p.kv_bias + static_cast<long long>(b) * p.Tk + it * kTileKV + c0;
 #pragma unroll
-        for (int c = 0; c < 128; ++c) {
+        for (int c = 0; c < kCols; ++c) {
           float s = __uint_as_float(sr[c]) * p.scale_log2;
           if (c < kv_valid) s += __ldg(bias + c) * kLog2e; else s = -INFINITY;
           sr[c] = __float_as_uint(s);
           mt = fmaxf(mt, s);
         }
-      } else if (kv_valid < kTileKV) {
+      } else if (kv_valid < kCols) {
 #pragma unroll
-        for (int c = 0; c < 128; ++c) {
+        for (int c = 0; c < kCols; ++c) {
           float s = __uint_as_float(sr[c]) * p.scale_log2;
           if (c >= kv_valid) s = -INFINITY;
           sr[c] = __float_as_uint(s);
@@ -207,18 +216,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < 128; ++c) {
+        for (int c = 0; c < kCols; ++c) {
           const float s = __uint_as_float(sr[c]) * p.scale_log2;
           sr[c] = __float_as_uint(s);
           mt = fmaxf(mt, s);
         }
       }
+      // the row's maximum over all slices (double-buffered exchange: one barrier per tile is enough)
+      hdr->row_stat[st][part][r] = mt;
+      softmax_bar();
+#pragma unroll
+      for (int q = 0; q < kSplit; ++q) mt = fmaxf(mt, hdr->row_stat[st][q][r]);
       const float m_new = fmaxf(m, mt);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = fast_exp2(m - m_use);  // m = -inf -> 0
       float rs = 0.f;
 #pragma unroll
-      for (int c = 0; c < 128; ++c) {
+      for (int c = 0; c < kCols; ++c) {
         const float e = fast_exp2(__uint_as_float(sr[c]) - m_use);
         rs += e;
         sr[c] = __float_as_uint(e);
@@ -235,29 +249,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       {
         uint8_t* prow = sP + r * 128;
 #pragma unroll
-        for (int blk = 0; blk < 2; ++blk) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = blk * 64 + j * 8;
-            uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(sr[c + 0]), __uint_as_float(sr[c + 1]));
-            w.y = pack_bf16x2(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3]));
-            w.z = pack_bf16x2(__uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5]));
-            w.w = pack_bf16x2(__uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7]));
-            *reinterpret_cast<uint4*>(prow + blk * kBlockBytes + ((j ^ (r & 7)) << 4)) = w;
-          }
+        for (int j8 = 0; j8 < kCols / 8; ++j8) {
+          const int c = c0 + j8 * 8;         // first of 8 score columns
+          const int blk = c >> 6, j = (c & 63) >> 3;
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(sr[j8 * 8 + 0]), __uint_as_float(sr[j8 * 8 + 1]));
+          w.y = pack_bf16x2(__uint_as_float(sr[j8 * 8 + 2]), __uint_as_float(sr[j8 * 8 + 3]));
+          w.z = pack_bf16x2(__uint_as_float(sr[j8 * 8 + 4]), __uint_as_float(sr[j8 * 8 + 5]));
+          w.w = pack_bf16x2(__uint_as_float(sr[j8 * 8 + 6]), __uint_as_float(sr[j8 * 8 + 7]));
+          *reinterpret_cast<uint4*>(prow + blk * kBlockBytes + ((j ^ (r & 7)) << 4)) = w;
         }
       }
-      // rescale the running O (TMEM) when some row of this warp moved its maximum
+      // rescale this thread's slice of the running O (TMEM) when some row of this warp moved its maximum
       if (it > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll
-        for (int c = 0; c < kDh; c += 32) {
+        for (int c = 0; c < kOCols; c += 32) {
           uint32_t o[32];
-          tmem_ld_x32(t_lane + kColO + c, o);
+          tmem_ld_x32(t_lane + kColO + part * kOCols + c, o);
           tmem_wait_ld();
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_x32(t_lane + kColO + c, o);
+          tmem_st_x32(t_lane + kColO + part * kOCols + c, o);
         }
         tmem_wait_st();
       }
@@ -265,16 +277,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       tc_fence_before_sync();
       mbar_arrive(&hdr->p_full);
     }
-    // ---- epilogue: O / l -> global bf16 ----
+    // ---- row sum over all slices, then epilogue: O / l -> global bf16 ----
+    softmax_bar();  // every thread is done reading the last tile's maxima
+    hdr->row_stat[0][part][r] = l;
+    softmax_bar();
+    l = 0.f;
+#pragma unroll
+    for (int q = 0; q < kSplit; ++q) l += hdr->row_stat[0][q][r];
     mbar_wait(&hdr->pv_done, (n_kv - 1) & 1);
     tc_fence_after_sync();
     const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
     const int row = q0 + r;
-    __nv_bfloat16* orow = p.O + (static_cast<long long>(b) * p.Tq + row) * p.ldo + h * kDh;
+    __nv_bfloat16* orow = p.O + (static_cast<long long>(b) * p.Tq + row) * p.ldo + h * kDh + part * kOCols;
 #pragma unroll
-    for (int c = 0; c < kDh; c += 32) {
+    for (int c = 0; c < kOCols; c += 32) {
       uint32_t o[32];
-      tmem_ld_x32(t_lane + kColO + c, o);
+      tmem_ld_x32(t_lane + kColO + part * kOCols + c, o);
       tmem_wait_ld();
       if (row < p.Tq) {
 #pragma unroll

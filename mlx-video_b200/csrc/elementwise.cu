@@ -3,11 +3,12 @@
 // row statistic is needed (warp-shuffle + one smem hop), grid-stride otherwise.  HBM roofline kernels:
 // algorithmic bytes per element are stated next to each entry point in DESIGN.md.
 #include "common.cuh"
+#include <algorithm>
 #include "ptx.cuh"
 
 namespace ltxb {
 
-constexpr int kRowThreads = 256;
+constexpr int kRowThreads = 128;  // 16 rows resident per SM: 1280-token problems fit ONE wave of 148 x 16 CTAs
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -65,7 +66,7 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
 // mod_scale / mod_shift point at the first column of the scale / shift slice of the modulation row.
 // ------------------------------------------------------------------------------------------------
 template <int kChunks, bool kLayerNorm>
-__global__ void __launch_bounds__(kRowThreads)
+__global__ void __launch_bounds__(kRowThreads, kChunks <= 4 ? 9 : 1)  // <= 56 registers: 9 rows per SM, 1280 tokens in ONE wave
 norm_modulate_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out, long long ldo,
                      int D, float eps, const float* __restrict__ mod_scale, const float* __restrict__ mod_shift,
                      long long ld_mod, const float* __restrict__ table_scale, const float* __restrict__ table_shift,
@@ -75,13 +76,38 @@ norm_modulate_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* 
   __shared__ float red[32];
   const long long row = blockIdx.x;
   const float* xr = x + row * ldx;
+  // narrow rows keep the whole modulation in registers too, so its loads are in flight together with x's
+  // instead of after the reduction (the kernel is a chain of L2 round trips, not a bandwidth problem)
+  constexpr bool kPrefetch = kChunks <= 1;  // wider rows would push the register count past one-wave occupancy
+  const bool has_mod = (mod_scale != nullptr) || (table_scale != nullptr);
+  long long mrow = 0;
+  if (mod_scale != nullptr) mrow = row_index != nullptr ? row_index[row] : row / row_div;
+  auto load_mod = [&](int c, float (&sc)[8], float (&sh)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sc[i] = 0.f, sh[i] = 0.f;
+    if (table_scale != nullptr) {
+      load8_ldg(table_scale + c, sc);
+      load8_ldg(table_shift + c, sh);
+    }
+    if (mod_scale != nullptr) {
+      float a[8], b[8];
+      load8_ldg(mod_scale + mrow * ld_mod + c, a);
+      load8_ldg(mod_shift + mrow * ld_mod + c, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sc[i] += a[i], sh[i] += b[i];
+    }
+  };
   float v[kChunks][8];
+  float psc[kPrefetch ? kChunks : 1][8], psh[kPrefetch ? kChunks : 1][8];
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < kChunks; ++j) {
     const int c = (threadIdx.x + j * kRowThreads) * 8;
     if (c < D) {
       load8(xr + c, v[j]);
+      if constexpr (kPrefetch) {
+        if (has_mod) load_mod(c, psc[j], psh[j]);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) s += kLayerNorm ? v[j][i] : v[j][i] * v[j][i];
     } else {
@@ -110,9 +136,6 @@ norm_modulate_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* 
   } else {
     rstd = rsqrtf(s / static_cast<float>(D) + eps);
   }
-  const bool has_mod = (mod_scale != nullptr) || (table_scale != nullptr);
-  long long mrow = 0;
-  if (mod_scale != nullptr) mrow = row_index != nullptr ? row_index[row] : row / row_div;
   __nv_bfloat16* orow = out + row * ldo;
 #pragma unroll
   for (int j = 0; j < kChunks; ++j) {
@@ -122,22 +145,15 @@ norm_modulate_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* 
 #pragma unroll
     for (int i = 0; i < 8; ++i) y[i] = (v[j][i] - mean) * rstd;
     if (has_mod) {
-      float sc[8], sh[8];
+      if constexpr (kPrefetch) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sc[i] = 0.f, sh[i] = 0.f;
-      if (table_scale != nullptr) {
-        load8_ldg(table_scale + c, sc);
-        load8_ldg(table_shift + c, sh);
+        for (int i = 0; i < 8; ++i) y[i] = fmaf(y[i], 1.0f + psc[j][i], psh[j][i]);
+      } else {
+        float sc[8], sh[8];
+        load_mod(c, sc, sh);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = fmaf(y[i], 1.0f + sc[i], sh[i]);
       }
-      if (mod_scale != nullptr) {
-        float a[8], b[8];
-        load8_ldg(mod_scale + mrow * ld_mod + c, a);
-        load8_ldg(mod_shift + mrow * ld_mod + c, b);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sc[i] += a[i], sh[i] += b[i];
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = fmaf(y[i], 1.0f + sc[i], sh[i]);
     }
     store8_bf16(orow + c, y);
   }
@@ -156,7 +172,8 @@ static int launch_norm_modulate(const float* x, long long ldx, void* out, long l
   if (chunks <= 1) LTXB_LAUNCH_NM(1);
   else if (chunks <= 2) LTXB_LAUNCH_NM(2);
   else if (chunks <= 4) LTXB_LAUNCH_NM(4);
-  else LTXB_LAUNCH_NM(8);
+  else if (chunks <= 8) LTXB_LAUNCH_NM(8);
+  else LTXB_LAUNCH_NM(16);
 #undef LTXB_LAUNCH_NM
   LTXB_CUDA(cudaGetLastError());
   return LTXB_OK;
@@ -203,7 +220,8 @@ gate_residual_kernel(float* __restrict__ x, long long ldx, const __nv_bfloat16* 
 // full-width RMSNorm with weight, then split RoPE per head, in place on bf16.
 // thread j owns elements [8j', 8j'+8) of the first half and the matching 8 of the second half of a head.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+template <int kPer>
+__global__ void __launch_bounds__(128, kPer <= 2 ? 9 : 1)  // <= 56 registers: 9 rows per SM, 1280 tokens in ONE wave
 qknorm_rope_kernel(const __nv_bfloat16* x, long long ldx, __nv_bfloat16* out, long long ldo,  // may alias (in place)
                    int heads_per_group, long long group_stride, int T, int H, int dh, const float* __restrict__ weight,
                    float eps, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, int B_pe) {
@@ -212,50 +230,58 @@ qknorm_rope_kernel(const __nv_bfloat16* x, long long ldx, __nv_bfloat16* out, lo
   __shared__ float red[32];
   const long long row = blockIdx.x;
   const int half = dh / 2;
-  const int tph = half / 8;  // threads per head
-  const int nthr = H * tph;
-  const bool active = threadIdx.x < nthr;
-  const int h = active ? threadIdx.x / tph : 0;
-  const int off = active ? (threadIdx.x % tph) * 8 : 0;
-  const __nv_bfloat16* p1 = x + row * ldx + h * dh + off;
-  float a[8], b[8];
+  const int tph = half / 8;  // work items per head: one item = 8 elements of each half of a head
+  const int items = H * tph;
+  const long long bb = (B_pe == 1) ? 0 : row / T;
+  const long long t = row % T;
+  float a[kPer][8], b[kPer][8];
   float s = 0.f;
-  if (active) {
-    load8_bf16(p1, a);
-    load8_bf16(p1 + half, b);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += a[i] * a[i] + b[i] * b[i];
+  for (int j = 0; j < kPer; ++j) {
+    const int item = threadIdx.x + j * blockDim.x;
+    if (item < items) {
+      const int h = item / tph, off = (item % tph) * 8;
+      const __nv_bfloat16* p1 = x + row * ldx + h * dh + off;
+      load8_bf16(p1, a[j]);
+      load8_bf16(p1 + half, b[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += a[j][i] * a[j][i] + b[j][i] * b[j][i];
+    }
   }
+  float rstd = 1.f;
   if (weight != nullptr) {  // weight == nullptr: plain (re-)layout copy, e.g. V on its way to the all-to-all
     s = block_sum(s, red);
-    if (!active) return;
-    const float rstd = rsqrtf(s / static_cast<float>(H * dh) + eps);
-    float w1[8], w2[8];
-    load8_ldg(weight + h * dh + off, w1);
-    load8_ldg(weight + h * dh + half + off, w2);
+    rstd = rsqrtf(s / static_cast<float>(H * dh) + eps);
+  }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] *= rstd * w1[i], b[i] *= rstd * w2[i];
-    if (cos_tab != nullptr) {
-      const long long bb = (B_pe == 1) ? 0 : row / T;
-      const long long t = row % T;
-      const long long tab = ((bb * H + h) * T + t) * half + off;
-      float c[8], sn[8];
-      load8_ldg(cos_tab + tab, c);
-      load8_ldg(sin_tab + tab, sn);
+  for (int j = 0; j < kPer; ++j) {
+    const int item = threadIdx.x + j * blockDim.x;
+    if (item >= items) continue;
+    const int h = item / tph, off = (item % tph) * 8;
+    if (weight != nullptr) {
+      float w1[8], w2[8];
+      load8_ldg(weight + h * dh + off, w1);
+      load8_ldg(weight + h * dh + half + off, w2);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float f = a[i] * c[i] - sn[i] * b[i];
-        const float g = b[i] * c[i] + sn[i] * a[i];
-        a[i] = f, b[i] = g;
+      for (int i = 0; i < 8; ++i) a[j][i] *= rstd * w1[i], b[j][i] *= rstd * w2[i];
+      if (cos_tab != nullptr) {
+        const long long tab = ((bb * H + h) * T + t) * half + off;
+        float c[8], sn[8];
+        load8_ldg(cos_tab + tab, c);
+        load8_ldg(sin_tab + tab, sn);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float f = a[j][i] * c[i] - sn[i] * b[j][i];
+          const float g = b[j][i] * c[i] + sn[i] * a[j][i];
+          a[j][i] = f, b[j][i] = g;
+        }
       }
     }
-  } else if (!active) {
-    return;
+    // head h lands in group h / heads_per_group (one group per destination rank of the Ulysses all-to-all)
+    __nv_bfloat16* o1 = out + (h / heads_per_group) * group_stride + row * ldo + (h % heads_per_group) * dh + off;
+    store8_bf16(o1, a[j]);
+    store8_bf16(o1 + half, b[j]);
   }
-  // head h lands in group h / heads_per_group (one group per destination rank of the Ulysses all-to-all)
-  __nv_bfloat16* o1 = out + (h / heads_per_group) * group_stride + row * ldo + (h % heads_per_group) * dh + off;
-  store8_bf16(o1, a);
-  store8_bf16(o1 + half, b);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -463,7 +489,7 @@ extern "C" int ltxb_rmsnorm_modulate(const float* x, int64_t ldx, void* out, int
   LTXB_CHECK_ARG(x && out, "ltxb_rmsnorm_modulate: null pointer");
   if (R == 0) return LTXB_OK;
   LTXB_CHECK_ARG(R > 0 && D > 0, "ltxb_rmsnorm_modulate: bad shape R=%d D=%d", R, D);
-  LTXB_CHECK_SUPPORTED(D % 8 == 0 && D <= 8 * 8 * kRowThreads, "ltxb_rmsnorm_modulate: D=%d must be a multiple of 8, <= 16384", D);
+  LTXB_CHECK_SUPPORTED(D % 8 == 0 && D <= 16 * 8 * kRowThreads, "ltxb_rmsnorm_modulate: D=%d must be a multiple of 8, <= 16384", D);
   LTXB_CHECK_ARG(aligned16(x) && aligned16(out) && ldx % 4 == 0 && ldo % 8 == 0, "ltxb_rmsnorm_modulate: misaligned x/out");
   LTXB_CHECK_ARG((table_scale == nullptr) == (table_shift == nullptr), "ltxb_rmsnorm_modulate: tables come in pairs");
   if (mod) {
@@ -483,7 +509,7 @@ extern "C" int ltxb_layernorm_modulate(const float* x, int64_t ldx, void* out, i
   LTXB_CHECK_ARG(x && out, "ltxb_layernorm_modulate: null pointer");
   if (R == 0) return LTXB_OK;
   LTXB_CHECK_ARG(R > 0 && D > 0, "ltxb_layernorm_modulate: bad shape R=%d D=%d", R, D);
-  LTXB_CHECK_SUPPORTED(D % 8 == 0 && D <= 8 * 8 * kRowThreads, "ltxb_layernorm_modulate: D=%d must be a multiple of 8, <= 16384", D);
+  LTXB_CHECK_SUPPORTED(D % 8 == 0 && D <= 16 * 8 * kRowThreads, "ltxb_layernorm_modulate: D=%d must be a multiple of 8, <= 16384", D);
   LTXB_CHECK_ARG(aligned16(x) && aligned16(out) && ldx % 4 == 0 && ldo % 8 == 0, "ltxb_layernorm_modulate: misaligned x/out");
   LTXB_CHECK_ARG((table_scale == nullptr) == (table_shift == nullptr), "ltxb_layernorm_modulate: tables come in pairs");
   if (emb) {
@@ -521,7 +547,7 @@ extern "C" int ltxb_qknorm_rope_scatter(const void* x, int64_t ldx, void* out, i
   if (B == 0 || T == 0) return LTXB_OK;
   LTXB_CHECK_ARG(B > 0 && T > 0 && H > 0, "ltxb_qknorm_rope: bad shape B=%d T=%d H=%d", B, T, H);
   LTXB_CHECK_SUPPORTED(dh == 64 || dh == 128, "ltxb_qknorm_rope: head dim %d not in {64,128}", dh);
-  LTXB_CHECK_SUPPORTED(H * (dh / 16) <= 1024, "ltxb_qknorm_rope: H*dh=%d too wide", H * dh);
+  LTXB_CHECK_SUPPORTED(H * (dh / 16) <= 2048, "ltxb_qknorm_rope: H*dh=%d too wide", H * dh);
   LTXB_CHECK_ARG(aligned16(x) && ldx % 8 == 0 && aligned16(out) && ldo % 8 == 0 && group_stride % 8 == 0,
                  "ltxb_qknorm_rope: misaligned x/out");
   LTXB_CHECK_ARG(heads_per_group >= 1 && H % heads_per_group == 0, "ltxb_qknorm_rope: %d heads do not split into groups of %d", H, heads_per_group);
@@ -529,10 +555,22 @@ extern "C" int ltxb_qknorm_rope_scatter(const void* x, int64_t ldx, void* out, i
   LTXB_CHECK_ARG((cos_tab == nullptr) == (sin_tab == nullptr), "ltxb_qknorm_rope: cos/sin come in pairs");
   LTXB_CHECK_ARG(cos_tab == nullptr || weight != nullptr, "ltxb_qknorm_rope: RoPE without the norm is not a path of the reference");
   if (cos_tab) LTXB_CHECK_ARG(aligned16(cos_tab) && aligned16(sin_tab) && (B_pe == 1 || B_pe == B), "ltxb_qknorm_rope: bad rope table");
-  const int nthr = ((H * (dh / 16) + 31) / 32) * 32;
-  LTXB_CUDA(launch_kernel(qknorm_rope_kernel, dim3(B * T), dim3(nthr), 0, reinterpret_cast<cudaStream_t>(stream), 1,
-                          reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(out), ldo,
-                          heads_per_group, group_stride, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe));
+  // 128 threads per row for the LTX widths (16 rows resident per SM: 1280 tokens are one wave)
+  const int items = H * (dh / 16);
+  const int per = items <= 128 ? 1 : (items <= 256 ? 2 : (items <= 512 ? 4 : (items <= 1024 ? 8 : 16)));
+  const int nthr = std::min(128, (((items + per - 1) / per + 31) / 32) * 32);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* oi = reinterpret_cast<__nv_bfloat16*>(out);
+#define LTXB_LAUNCH_QK(P)                                                                                             \
+  LTXB_CUDA(launch_kernel(qknorm_rope_kernel<P>, dim3(B * T), dim3(nthr), 0, st, 1, xi, ldx, oi, ldo, heads_per_group, \
+                          group_stride, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe))
+  if (per == 1) LTXB_LAUNCH_QK(1);
+  else if (per == 2) LTXB_LAUNCH_QK(2);
+  else if (per == 4) LTXB_LAUNCH_QK(4);
+  else if (per == 8) LTXB_LAUNCH_QK(8);
+  else LTXB_LAUNCH_QK(16);
+#undef LTXB_LAUNCH_QK
   return LTXB_OK;
 }
 
