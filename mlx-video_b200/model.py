@@ -22,7 +22,8 @@ from . import _lib, ops
 from ._lib import LtxbError
 from .config import LTXModelConfig, LTXModelType, LTXRopeType
 from .rope import precompute_freqs_cis
-from .transformer import (BF16, F32, BasicAVTransformerBlock, Linear, Modality, TransformerArgs, Workspace, _kv_bias)
+from .transformer import (BF16, F32, BasicAVTransformerBlock, ContextCache, Linear, Modality, TransformerArgs, Workspace,
+                          _kv_bias)
 
 Tensor = torch.Tensor
 
@@ -110,7 +111,8 @@ class LTXModel:
     the reference's one-row-per-token evaluation literally."""
 
     def __init__(self, config: LTXModelConfig, device: Union[str, torch.device, None] = None,
-                 dedupe_timesteps: bool = True, timestep_capacity: int = 128) -> None:
+                 dedupe_timesteps: bool = True, timestep_capacity: int = 128, cache_context: bool = False,
+                 cuda_graphs: bool = False) -> None:
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
         if device is None or torch.device(device).type != "cuda":
@@ -123,6 +125,12 @@ class LTXModel:
         self.timestep_scale_multiplier = config.timestep_scale_multiplier
         self.positional_embedding_theta = config.positional_embedding_theta
         self.dedupe_timesteps, self.timestep_capacity = dedupe_timesteps, timestep_capacity
+        # cache_context: keep the caption projection and every block's text K/V while the SAME context tensor keeps
+        # coming in (constant across a denoise loop; the reference recomputes them every step — off by default so
+        # the default forward executes the reference's work).  cuda_graphs: replay one captured graph per input
+        # signature instead of ~800 launches per forward.
+        self.cache_context, self._context_caches, self._context_keys = cache_context, {}, {}
+        self._graphs = {} if cuda_graphs else None
         self.workspace = Workspace()
         self.seq_parallel = None  # set by parallel.UlyssesGroup.attach()
         self._group_counts: List[Tensor] = []
@@ -271,7 +279,14 @@ class LTXModel:
         values, index, (rb, rt) = self._timestep_rows(m.timesteps, B, T)
         scale = float(self.timestep_scale_multiplier)
         mod, emb = getattr(self, pre + "adaln_single")(values, scale)
-        ctx = getattr(self, pre + "caption_projection")(_as_bf16(m.context)).view(B, -1, inner)
+        cache = self._context_cache_for(pre, m.context) if self.cache_context else None
+        proj = getattr(self, pre + "caption_projection")
+        if cache is None:
+            ctx = proj(_as_bf16(m.context)).view(m.context.shape[0], -1, inner)
+        else:
+            ctx = cache.context_buffer((m.context.shape[0], m.context.shape[1], inner), self.device)
+            if not cache.valid:
+                proj.linear2(proj.linear1(_as_bf16(m.context), mode=_lib.EPI_GELU_BF16), out=ctx)
         mask = _kv_bias(m.context_mask, B, ctx.shape[1])
         pe = m.positional_embeddings
         if pe is None:
@@ -279,7 +294,7 @@ class LTXModel:
                                       self.use_middle_indices_grid, heads, self.rope_type, c.double_precision_rope)
         args = TransformerArgs(x=x, context=ctx, context_mask=mask, timesteps=mod.view(rb, rt, -1),
                                embedded_timestep=emb.view(rb, rt, -1), positional_embeddings=pe, enabled=m.enabled,
-                               timestep_index=index)
+                               timestep_index=index, context_cache=cache)
         if self._av:  # ltx.py:201-247
             cross_pe = precompute_freqs_cis(m.positions[:, 0:1].to(self.device), self.audio_cross_attention_dim,
                                             self.positional_embedding_theta, [self.cross_pe_max_pos], True, heads,
@@ -323,7 +338,86 @@ class LTXModel:
                                  seq_parallel=self.seq_parallel)
         return video, audio
 
+    # ------------------------------------------------------------------ context cache / CUDA graphs (row N1)
+    @staticmethod
+    def _tensor_key(t: Tensor):
+        return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, t._version)
+
+    def _context_cache_for(self, pre: str, context: Tensor) -> ContextCache:
+        cache = self._context_caches.get(pre)
+        if cache is None:
+            cache = self._context_caches[pre] = ContextCache()
+        # under graph replay the forward sees a static copy of the context; the caller's tensor names the cache
+        cache.retarget(self._context_keys.get(pre) or self._tensor_key(context))
+        return cache
+
+    def clear_caches(self) -> None:
+        self._context_caches.clear()
+        if self._graphs is not None:
+            self._graphs.clear()
+
     def __call__(self, video: Optional[Modality] = None, audio: Optional[Modality] = None):
+        if self._graphs is not None and not torch.cuda.is_current_stream_capturing():
+            return self._graphed_call(video, audio)
+        return self._forward(video, audio)
+
+    def _graphed_call(self, video: Optional[Modality], audio: Optional[Modality]):
+        """One captured CUDA graph per input signature (and per context-cache state); the inputs are copied
+        into the graph's static tensors, the outputs cloned out of them."""
+        def fields(m):
+            if m is None:
+                return []
+            pe = m.positional_embeddings
+            return [m.latent, m.timesteps, m.positions, m.context, m.context_mask] + ([None, None] if pe is None else [pe[0], pe[1]])
+
+        def sig(t):
+            return None if t is None else (tuple(t.shape), t.dtype)
+
+        flat = fields(video) + fields(audio)
+        for t in flat:
+            if t is not None and not t.is_cuda:
+                raise LtxbError("LTXModel inputs must be CUDA tensors; there is no CPU fallback on this path")
+        hits = []
+        for pre, m in (("", video), ("audio_", audio)):
+            hit = False
+            if self.cache_context and m is not None:
+                self._context_keys[pre] = self._tensor_key(m.context)
+                c = self._context_caches.get(pre)
+                hit = c is not None and c.valid and c.key == self._context_keys[pre]
+            hits.append(hit)
+        key = (video is None, audio is None, tuple(sig(t) for t in flat), tuple(hits), self.seq_parallel is not None)
+        try:
+            entry = self._graphs.get(key)
+            if entry is None:
+                def static(m):
+                    if m is None:
+                        return None
+                    c = lambda t: None if t is None else t.clone()  # noqa: E731
+                    pe = m.positional_embeddings
+                    return Modality(c(m.latent), c(m.timesteps), c(m.positions), c(m.context), m.enabled, c(m.context_mask),
+                                    None if pe is None else (c(pe[0]), c(pe[1])))
+                sv, sa = static(video), static(audio)
+                valid_before = {pre: c.valid for pre, c in self._context_caches.items()}
+                self._forward(sv, sa)  # eager warm-up: sizes the workspaces, configures the kernels
+                torch.cuda.synchronize()
+                for pre, c in self._context_caches.items():  # capture the same variant (fill vs reuse) as this key
+                    c.valid = valid_before.get(pre, False) and c.valid
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = self._forward(sv, sa)
+                entry = self._graphs[key] = (graph, sv, sa, out)
+            graph, sv, sa, out = entry
+            for dst, src in zip(fields(sv) + fields(sa), flat):
+                if dst is not None:
+                    dst.copy_(src)
+            graph.replay()
+            for c in self._context_caches.values():
+                c.valid = c.context is not None
+        finally:
+            self._context_keys.clear()
+        return tuple(None if o is None else o.clone() for o in out)
+
+    def _forward(self, video: Optional[Modality] = None, audio: Optional[Modality] = None):
         sp = self.seq_parallel
         if sp is not None:
             video, audio = sp.shard_inputs(video, audio)
@@ -335,6 +429,8 @@ class LTXModel:
         ax = self._process_output(self.audio_scale_shift_table, self.audio_proj_out, aa, adt) if aa is not None else None
         if sp is not None:
             vx, ax = sp.gather_outputs(vx, ax)
+        for c in self._context_caches.values():  # every block has now filled its K/V entry
+            c.valid = c.context is not None
         return vx, ax
 
     # ------------------------------------------------------------------ accounting

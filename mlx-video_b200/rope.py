@@ -56,5 +56,11 @@ def precompute_freqs_cis(
     n_axes = grid.shape[1]
     assert n_axes == len(max_pos), "Number of position dimensions must match max_pos length"  # rope.py:228
     grid = grid.to(torch.float32).contiguous()
-    freq = rope_base_frequencies(theta, n_axes, dim).to(grid.device)
+    key = (float(theta), n_axes, dim, str(grid.device))
+    freq = _freq_cache.get(key)
+    if freq is None:  # host-built once per geometry, then resident (no H2D copy in the steady state / under graph capture)
+        freq = _freq_cache[key] = rope_base_frequencies(theta, n_axes, dim).to(grid.device)
     return ops.rope_table(grid, max_pos, freq, dim, num_attention_heads, use_middle_indices_grid)
+
+
+_freq_cache: dict = {}

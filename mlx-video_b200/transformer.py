@@ -64,6 +64,36 @@ class TransformerArgs:
     cross_gate_timestep: Optional[Tensor] = None
     enabled: bool = True
     timestep_index: Optional[Tensor] = None
+    context_cache: Optional["ContextCache"] = None  # opt-in reuse of the text K/V across denoise steps
+
+
+class ContextCache:
+    """Projected caption and per-block text-cross-attention K/V (after k-norm) of ONE context tensor.  The
+    context, hence these projections, are constant across all steps of a denoise loop (SURVEY.md F9, §8f N1);
+    the reference recomputes them every step.  Buffers keep their addresses when the context changes (only
+    ``valid`` drops), so captured CUDA graphs that fill or read them stay correct."""
+
+    def __init__(self) -> None:
+        self.key = None
+        self.context: Optional[Tensor] = None  # projected caption, bf16 (B, Tc, D)
+        self.kv: Dict[int, Tensor] = {}
+        self.valid = False
+
+    def retarget(self, key) -> None:
+        if key != self.key:
+            self.key, self.valid = key, False
+
+    def context_buffer(self, shape, device) -> Tensor:
+        if self.context is None or tuple(self.context.shape) != tuple(shape):
+            self.context, self.valid = torch.empty(shape, dtype=BF16, device=device), False
+        return self.context
+
+    def entry(self, block_idx: int, shape, device) -> Tensor:
+        t = self.kv.get(block_idx)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = self.kv[block_idx] = torch.empty(shape, dtype=BF16, device=device)
+            self.valid = False
+        return t
 
 
 class Workspace:
@@ -156,7 +186,7 @@ class Attention:
 
     # -- the pieces, exposed separately so the sequence-parallel path can put its all-to-all between them
     def project(self, ws: Workspace, tag: str, xq: Tensor, B: int, Tq: int, context: Optional[Tensor], Tk: int,
-                pe, k_pe) -> Tuple[Tensor, Tensor, Tensor]:
+                pe, k_pe, kv_out: Optional[Tensor] = None, kv_ready: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
         """Q/K/V projections + full-width q/k RMSNorm + split RoPE (attention.py:123-136).
         xq: bf16 [B*Tq, query_dim]; context: bf16 [B*Tk, context_dim] or None (self)."""
         inner, dev = self.inner_dim, xq.device
@@ -172,21 +202,23 @@ class Attention:
         else:
             q = ws.get(tag + ".q", (B * Tq, inner), BF16, dev)
             ops.gemm(xq, self.to_q.weight, self.to_q.bias, q)
-            if self.is_self:  # self-attention weights applied to an explicit context (attention.py:124-126)
-                kv = ws.get(tag + ".kv", (B * Tk, 2 * inner), BF16, dev)
-                ops.gemm(context, self.qkv_weight[inner:], self.qkv_bias[inner:], kv)
-            else:
-                kv = ws.get(tag + ".kv", (B * Tk, 2 * inner), BF16, dev)
-                ops.gemm(context, self.kv_weight, self.kv_bias, kv)
+            kv = ws.get(tag + ".kv", (B * Tk, 2 * inner), BF16, dev) if kv_out is None else kv_out
+            if not kv_ready:
+                if self.is_self:  # self-attention weights applied to an explicit context (attention.py:124-126)
+                    ops.gemm(context, self.qkv_weight[inner:], self.qkv_bias[inner:], kv)
+                else:
+                    ops.gemm(context, self.kv_weight, self.kv_bias, kv)
             k, v = kv[:, :inner], kv[:, inner:]
         H, dh = self.heads, self.dim_head
         if pe is not None:
             kp = pe if k_pe is None else k_pe
             ops.qknorm_rope(q, B, Tq, H, dh, self.q_norm.weight, self.q_norm.eps, pe[0], pe[1])
-            ops.qknorm_rope(k, B, Tk, H, dh, self.k_norm.weight, self.k_norm.eps, kp[0], kp[1])
+            if not kv_ready:
+                ops.qknorm_rope(k, B, Tk, H, dh, self.k_norm.weight, self.k_norm.eps, kp[0], kp[1])
         else:
             ops.qknorm_rope(q, B, Tq, H, dh, self.q_norm.weight, self.q_norm.eps)
-            ops.qknorm_rope(k, B, Tk, H, dh, self.k_norm.weight, self.k_norm.eps)
+            if not kv_ready:
+                ops.qknorm_rope(k, B, Tk, H, dh, self.k_norm.weight, self.k_norm.eps)
         return q, k, v
 
     def sdpa(self, ws: Workspace, tag: str, q: Tensor, k: Tensor, v: Tensor, B: int, Tq: int, Tk: int,
@@ -200,7 +232,8 @@ class Attention:
     def fused(self, ws: Workspace, tag: str, xq: Tensor, B: int, Tq: int, resid: Tensor, *,
               context: Optional[Tensor] = None, Tk: int = 0, pe=None, k_pe=None, kv_bias: Optional[Tensor] = None,
               gate: Optional[Tensor] = None, gate_table: Optional[Tensor] = None, row_div: int = 1,
-              row_index: Optional[Tensor] = None, seq_parallel=None) -> None:
+              row_index: Optional[Tensor] = None, seq_parallel=None, kv_out: Optional[Tensor] = None,
+              kv_ready: bool = False) -> None:
         """resid (f32 [B*Tq, query_dim]) += to_out(attention(...)) * gate, in place — the to_out GEMM's
         epilogue carries bias, gate and residual add (transformer.py:254,257-261)."""
         group_cols = 0
@@ -208,7 +241,7 @@ class Attention:
             # rows are sharded across ranks: projections local, heads <-> sequence all-to-all around the attention
             o, group_cols = seq_parallel.self_attention(self, ws, tag, xq, B, Tq, pe)
         else:
-            q, k, v = self.project(ws, tag, xq, B, Tq, context, Tk, pe, k_pe)
+            q, k, v = self.project(ws, tag, xq, B, Tq, context, Tk, pe, k_pe, kv_out, kv_ready)
             o = self.sdpa(ws, tag, q, k, v, B, Tq, Tq if context is None else Tk, kv_bias)
         ops.gemm(o, self.to_out.weight, self.to_out.bias, resid, _lib.EPI_RESID_GATE_F32, resid=resid, gate=gate,
                  gate_table=gate_table, gate_row_div=row_div, gate_row_index=row_index, a_group_cols=group_cols)
@@ -319,7 +352,10 @@ class BasicAVTransformerBlock:
                     gate_table=table[2], row_div=div, row_index=idx, seq_parallel=seq_parallel)
         ops.rmsnorm_modulate(x2, nx, self.norm_eps)
         Tc = a.context.shape[1]
-        attn2.fused(ws, tag + ".attn2", nx, B, T, x2, context=a.context.reshape(B * Tc, -1), Tk=Tc, kv_bias=a.context_mask)
+        cache = a.context_cache
+        kv_out = None if cache is None else cache.entry(self.idx, (a.context.shape[0] * Tc, 2 * attn2.inner_dim), x2.device)
+        attn2.fused(ws, tag + ".attn2", nx, B, T, x2, context=a.context.reshape(-1, a.context.shape[-1]), Tk=Tc,
+                    kv_bias=a.context_mask, kv_out=kv_out, kv_ready=cache is not None and cache.valid)
 
     def _ff(self, ws, tag, a: TransformerArgs, ff: FeedForward, table: Tensor) -> None:
         """x += ff(rms(x)(1+scale)+shift) * gate   (transformer.py:342-355)"""

@@ -296,3 +296,44 @@ def test_reference_attention_and_ff_signatures():
     got = blk.attn2(x.to(DEV), context=ctx.to(DEV), mask=fmask.to(DEV))
     assert_close(got, want, "attn2 masked")
     assert_close(blk.ff(x.to(DEV)), O.feed_forward(p.sub("ff"), x.float()), "ff")
+
+
+def test_cuda_graph_and_context_cache_are_exact():
+    """Row N1: graph replay and the cross-step text K/V cache must reproduce the plain forward bit for bit, and the
+    cache must drop when a different context comes in."""
+    cfg = O.small_config(O.LTXModelType.AudioVideo, num_layers=2)
+    tensors = O.init_params(cfg, seed=31)
+    g = torch.Generator().manual_seed(32)
+    T, Ta, Tc = 96, 21, 24
+    pos = torch.from_numpy(O.create_position_grid(1, 2, 6, 8)).to(DEV)
+    apos = torch.from_numpy(O.create_audio_position_grid(1, Ta)).to(DEV)
+
+    def inputs(seed, sigma):
+        gg = torch.Generator().manual_seed(seed)
+        v = M.Modality(torch.randn(1, T, 128, generator=gg).to(DEV), torch.full((1, T), sigma, device=DEV), pos, ctx_v)
+        a = M.Modality(torch.randn(1, Ta, 128, generator=gg).to(DEV), torch.full((1, Ta), sigma, device=DEV), apos, ctx_a)
+        return v, a
+
+    ctx_v, ctx_a = torch.randn(1, Tc, 256, generator=g).to(DEV), torch.randn(1, Tc, 256, generator=g).to(DEV)
+    plain = build(cfg, tensors)
+    variants = {"graph": build(cfg, tensors, cuda_graphs=True), "cache": build(cfg, tensors, cache_context=True),
+                "graph+cache": build(cfg, tensors, cuda_graphs=True, cache_context=True)}
+    for step, sigma in enumerate([1.0, 0.725, 0.421875]):
+        v, a = inputs(100 + step, sigma)
+        want_v, want_a = plain(video=v, audio=a)
+        for name, model in variants.items():
+            got_v, got_a = model(video=v, audio=a)
+            assert torch.equal(got_v, want_v) and torch.equal(got_a, want_a), f"{name} differs at step {step}"
+    assert variants["cache"]._context_caches[""].valid and len(variants["graph+cache"]._graphs) == 2  # fill + reuse graphs
+    # a new prompt: same shapes, different tensor -> caches must be refilled
+    ctx_v, ctx_a = torch.randn(1, Tc, 256, generator=g).to(DEV), torch.randn(1, Tc, 256, generator=g).to(DEV)
+    v, a = inputs(200, 0.9)
+    want_v, want_a = plain(video=v, audio=a)
+    for name, model in variants.items():
+        got_v, got_a = model(video=v, audio=a)
+        assert torch.equal(got_v, want_v) and torch.equal(got_a, want_a), f"{name} served a stale context"
+    # in-place edit of the SAME tensor is also seen (tensor version counter)
+    ctx_v.mul_(0.5)
+    want_v, _ = plain(video=v, audio=a)
+    got_v, _ = variants["graph+cache"](video=v, audio=a)
+    assert torch.equal(got_v, want_v)
