@@ -219,8 +219,11 @@ def main() -> int:
         parallelism = par.describe()
 
     # ---------------- model + resident inputs (synthetic, seeded; random-init weights of the real architecture)
+    # graph replay is single-GPU only for now: capturing the NCCL exchanges of the sequence-parallel path hung on the
+    # first attempt (profiles/README.md), so multi-rank runs launch eagerly
+    use_graph = (not args.no_graph) and world == 1
     model = M.LTXModel(M.production_config(M.LTXModelType.VideoOnly, num_layers=args.layers), device=dev,
-                       cuda_graphs=not args.no_graph, cache_context=args.cache_context).init_random(seed=0)
+                       cuda_graphs=use_graph, cache_context=args.cache_context).init_random(seed=0)
     if par is not None:
         par.attach(model)
     g = torch.Generator().manual_seed(1234)
@@ -378,7 +381,7 @@ def main() -> int:
             "e2e": {"value": T * args.steps / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms / args.steps,
                     "wall_ms_per_step": e2e_wall_ms / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": gpu_launches if gpu_launches > 0 else launches_per_step * args.steps,
-            "launch_mode": "eager" if args.no_graph else f"cuda graph replay ({launches_per_step} kernels per step captured)",
+            "launch_mode": "eager" if not use_graph else f"cuda graph replay ({launches_per_step} kernels per step captured)",
             "context_cache": bool(args.cache_context),
             "roofline": {"kernel": "gemm_bf16_kernel (tcgen05/TMEM, TMA-fed)", "bound": "tensor", "achieved": gemm_tflops, "peak": pk["tflops"],
                          "unit": "TFLOP/s", "frac": gemm_tflops / pk["tflops"], "traffic": traffic, "peak_source": pk["source"] + " sustained",

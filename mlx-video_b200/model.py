@@ -357,7 +357,7 @@ class LTXModel:
             self._graphs.clear()
 
     def __call__(self, video: Optional[Modality] = None, audio: Optional[Modality] = None):
-        if self._graphs is not None and not torch.cuda.is_current_stream_capturing():
+        if self._graphs is not None and self.seq_parallel is None and not torch.cuda.is_current_stream_capturing():
             return self._graphed_call(video, audio)
         return self._forward(video, audio)
 
