@@ -11,6 +11,8 @@ A *step* is one denoising step of the sampler loop: build the Modality, run the 
              (strong scaling: the same video on N GPUs).
   dev        BASELINE configs[2]: 768x768x65 -> 24x24x9 = 5184 tokens, CFG 4.5 (cond + uncond forward per
              step).  N = 1: cfg_batch (B=2).  N >= 2: CFG-parallel x Ulysses-(N/2).
+  av         BASELINE configs[3]: the joint audio+video model (5184 video + 68 audio tokens).  N > 1: Ulysses-N.
+  long       BASELINE configs[4]: 1280x704x121 -> 14080 video tokens, distilled stage 2.  N > 1: Ulysses-N.
 One JSON line on stdout (rank 0).  `value` has inputs resident in HBM; `e2e` goes through the public
 API with pinned HOST buffers copied in and the velocity read back every step.
 The only place this file touches oracle/ is the CPU baseline (`cpu_baseline`, `--impl reference`).
@@ -34,6 +36,10 @@ WORKLOADS = {
     # name: (frames, height, width, text tokens, cfg_scale, sigmas)
     "distilled": dict(grid=(5, 16, 16), Tc=1024, cfg=1.0, desc="LTX-2 19B video-only DiT, 48 blocks, distilled stage-1, 512x512x33 (16x16x5=1280 tokens), 1024 text tokens"),
     "dev": dict(grid=(9, 24, 24), Tc=1024, cfg=4.5, desc="LTX-2 19B video-only DiT, 48 blocks, dev pipeline, 768x768x65 (24x24x9=5184 tokens), CFG 4.5, 1024 text tokens"),
+    # BASELINE configs[4]: distilled stage 2 of 1280x704x121 -> 40x22x16 = 14080 video tokens
+    "long": dict(grid=(16, 22, 40), Tc=1024, cfg=1.0, desc="LTX-2 19B video-only DiT, 48 blocks, distilled stage-2, 1280x704x121 (40x22x16=14080 tokens), 1024 text tokens"),
+    # BASELINE configs[3]: joint audio+video model, 768x768x65 + 68 audio latents (audio<->video cross-attention in every block)
+    "av": dict(grid=(9, 24, 24), Tc=1024, cfg=1.0, Ta=68, desc="LTX-2 19B audio+video DiT, 48 blocks, 768x768x65 (5184 video + 68 audio tokens), 1024 text tokens per modality"),
 }
 
 
@@ -111,7 +117,7 @@ class CpuSample:
         cfg = O.OracleConfig(num_layers=1)
         self.model = O.OracleLTXModel(cfg, O.init_params(cfg, seed=0))
         g = torch.Generator().manual_seed(1)
-        F_, H_, W_ = {1280: (5, 16, 16), 5184: (9, 24, 24)}.get(T, (1, 1, T))
+        F_, H_, W_ = {1280: (5, 16, 16), 5184: (9, 24, 24), 14080: (16, 22, 40)}.get(T, (1, 1, T))
         video = O.Modality(torch.randn(1, T, 128, generator=g), torch.full((1, T), 0.725),
                            torch.from_numpy(O.create_position_grid(1, F_, H_, W_)), torch.randn(1, Tc, 3840, generator=g))
         with torch.no_grad():
@@ -178,6 +184,7 @@ def main() -> int:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cache-context", action="store_true", help="headline run WITH the cross-step text K/V cache (row N1); default recomputes them like the reference")
+    ap.add_argument("--nccl-exchange", action="store_true", help="sequence parallelism through NCCL all_to_all instead of the NVLink-fused kernels")
     ap.add_argument("--kernel-table", action="store_true", help="print the per-kernel time table to stderr")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -215,14 +222,15 @@ def main() -> int:
     if world > 1:
         from mlx_video_b200 import parallel
 
-        par = parallel.make_layout(world, rank, use_cfg)
+        par = parallel.make_layout(world, rank, use_cfg, fused=False if args.nccl_exchange else None)
         parallelism = par.describe()
 
     # ---------------- model + resident inputs (synthetic, seeded; random-init weights of the real architecture)
     # graph replay is single-GPU only for now: capturing the NCCL exchanges of the sequence-parallel path hung on the
     # first attempt (profiles/README.md), so multi-rank runs launch eagerly
     use_graph = (not args.no_graph) and world == 1
-    model = M.LTXModel(M.production_config(M.LTXModelType.VideoOnly, num_layers=args.layers), device=dev,
+    Ta = wl.get("Ta", 0)
+    model = M.LTXModel(M.production_config(M.LTXModelType.AudioVideo if Ta else M.LTXModelType.VideoOnly, num_layers=args.layers), device=dev,
                        cuda_graphs=use_graph, cache_context=args.cache_context).init_random(seed=0)
     if par is not None:
         par.attach(model)
@@ -245,6 +253,13 @@ def main() -> int:
         ctx_cat = torch.cat([ctx_pos, ctx_neg], 0)
         pos_cat = torch.cat([pos, pos], 0)
     ts_buf = torch.empty(b, T, device=dev)
+    if Ta:  # audio stream: latents (1, Ta, 128), its own text context, positions in seconds
+        a0 = torch.randn(1, Ta, 128, generator=g).to(dev)
+        xa = a0.clone()
+        a_ctx = torch.randn(1, Tc, 3840, generator=g).to(torch.bfloat16).to(dev)
+        a_pos = torch.from_numpy(sampler.create_audio_position_grid(1, Ta)).to(dev)
+        a_rope = sampler._audio_rope(model, a_pos)
+        a_ones = torch.ones(1, Ta, device=dev)
 
     def forward(xin, sigma):
         """One denoise step's model work -> (v_pos, v_neg)."""
@@ -257,7 +272,10 @@ def main() -> int:
             ctx = ctx_pos if par.cfg.is_cond else ctx_neg
             mine, _ = model(video=M.Modality(xin, ts_buf, pos, ctx, True, None, rope), audio=None)
             return par.cfg.exchange(mine)
-        v, _ = model(video=M.Modality(xin, ts_buf, pos, ctx_pos, True, None, rope), audio=None)
+        am = M.Modality(xa, a_ones * sigma, a_pos, a_ctx, True, None, a_rope) if Ta else None
+        v, va = model(video=M.Modality(xin, ts_buf, pos, ctx_pos, True, None, rope), audio=am)
+        if Ta:
+            forward.audio_velocity = va
         return v, None
 
     def step(i):
@@ -266,6 +284,10 @@ def main() -> int:
             x.copy_(x0)
         v_pos, v_neg = forward(x, sig[k])
         sampler._advance(x, v_pos.contiguous(), sig[k], sig[k + 1], v_neg=None if v_neg is None else v_neg.contiguous(), cfg_scale=cfg_scale)
+        if Ta:
+            if k == 0:
+                xa.copy_(a0)
+            sampler._advance(xa, forward.audio_velocity.contiguous(), sig[k], sig[k + 1])
 
     def barrier():
         if world > 1:
@@ -314,7 +336,8 @@ def main() -> int:
             out_h.copy_(v, non_blocking=True)
         else:
             m = M.Modality(xin, ts_dev, p, cp, True, None, rope)
-            v, _ = model(video=m, audio=None)
+            am = M.Modality(a0, a_ones * sigma, a_pos, a_ctx, True, None, a_rope) if Ta else None
+            v, _ = model(video=m, audio=am)
             out_h.copy_(v, non_blocking=True)
         torch.cuda.synchronize()
 
@@ -358,7 +381,7 @@ def main() -> int:
     if rank == 0:
         ms_step = ms_total / args.steps
         forwards = 2 if use_cfg else 1
-        flops_step = model.forward_flops(T, Tc) * forwards
+        flops_step = model.forward_flops(T, Tc, Ta) * forwards
         tflops = flops_step / (ms_step * 1e-3) / 1e12
         gemm = table.get("ltxb_gemm_bf16", dict(launches=1, ms=1e-9, work=0.0))
         gemm_tflops = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12
@@ -370,7 +393,7 @@ def main() -> int:
             "metric": "video_tokens_per_s", "value": T * args.steps / (ms_total * 1e-3), "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "steps_per_s": 1e3 / ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": wl["desc"], "video_tokens": T, "text_tokens": Tc, "layers": args.layers, "batch": b,
+            "config": {"workload": wl["desc"], "video_tokens": T, "audio_tokens": Ta, "text_tokens": Tc, "layers": args.layers, "batch": b,
                        "forwards_per_step": forwards, "parallelism": parallelism,
                        "l2": "48 blocks x 537 MB of bf16 weights stream through the 126 MB L2 every step (inputs larger than L2)",
                        "weights": "random-init, seeded, bf16; fp32 residual stream",
@@ -391,7 +414,7 @@ def main() -> int:
         att = table.get("ltxb_attention_fwd")
         if att:
             line["attention_tflops"] = att["work"] / (att["ms"] * 1e-3) / 1e12
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not Ta:
             s = cpu_block_sample(T, Tc)
             cpu_value = T / (s["t_forward"] * forwards)
             line["cpu_baseline"] = {"value": cpu_value, "unit": "tokens/s", "cores": s["cores"], "kind": "port", "sample": s["sample"]}

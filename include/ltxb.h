@@ -143,6 +143,19 @@ int ltxb_qknorm_rope_scatter(const void* x, int64_t ldx, void* out, int64_t ldo,
                              int64_t group_stride, int32_t B, int32_t T, int32_t H, int32_t dh, const float* weight,
                              float eps, const float* cos_tab, const float* sin_tab, int32_t B_pe, void* stream);
 
+/* The same, fused with the head-scatter all-to-all: group g's heads are stored to group_bases[g] (host array of
+ * n_groups device pointers — NVLink-mapped receive buffers of the destination ranks, each already offset to this
+ * rank's chunk), rows ldo apart.  No send buffer and no collective call: the exchange is this kernel's stores. */
+int ltxb_qknorm_rope_scatter_peers(const void* x, int64_t ldx, void* const* group_bases, int32_t n_groups, int64_t ldo,
+                                   int32_t B, int32_t T, int32_t H, int32_t dh, const float* weight, float eps,
+                                   const float* cos_tab, const float* sin_tab, int32_t B_pe, void* stream);
+
+/* Cross-GPU barrier on NVLink peer memory (new).  flag_ptrs: host array, flag_ptrs[i] = rank i's
+ * int32[n_peers] flag array mapped into this process (zero-initialised once).  Stream-ordered: raises this rank's
+ * flag on every peer to `epoch` (release, system scope) once all earlier work of the stream has completed, then
+ * waits until every peer's flag here is >= epoch.  `epoch` must increase by one per call on every rank. */
+int ltxb_peer_barrier(int32_t* const* flag_ptrs, int32_t n_peers, int32_t my_rank, int32_t epoch, void* stream);
+
 /* a5  sinusoidal timestep features  (utils.py:486-526 with adaln.py:66: dim 256, flip_sin_to_cos,
  *     shift 0):  out bf16 [n, dim] = [cos(t*scale*f_i) | sin(t*scale*f_i)], f_i = exp(-ln(1e4) i/(dim/2)). */
 int ltxb_timestep_embed(const float* t, int32_t n, float scale, int32_t dim, void* out, int64_t ldo, void* stream);
@@ -178,6 +191,13 @@ int ltxb_cast_bf16_to_f32(const void* x, float* out, int64_t n, void* stream);
 int ltxb_attention_fwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
                        int64_t ldo, int32_t B, int32_t Tq, int32_t Tk, int32_t H, int32_t dh, float scale,
                        const float* kv_bias, void* stream);
+
+/* The same with the Ulysses sequence-gather all-to-all fused into the epilogue (B = 1): output row r is stored to
+ * o_peers[r / rows_per_peer] + (r % rows_per_peer) * ldo — rank i's NVLink-mapped receive buffer, already offset
+ * to this rank's head-group chunk — instead of a local O followed by a collective. */
+int ltxb_attention_fwd_peers(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
+                             void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, int64_t ldo, int32_t Tq,
+                             int32_t Tk, int32_t H, int32_t dh, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a21/a22 sampler-side elementwise (utils.py:404-440; generate.py:1255,1283,1288-1301)

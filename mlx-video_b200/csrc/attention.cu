@@ -35,6 +35,10 @@ struct AttnParams {
   __nv_bfloat16* O;
   long long ldo;
   const float* kv_bias;  // [B, Tk] additive (natural-log domain) or null
+  // Ulysses gather fused into the epilogue: query rows [i*rows_per_peer, (i+1)*rows_per_peer) are stored straight
+  // into rank i's receive buffer over NVLink (rows_per_peer == 0: plain local output)
+  int rows_per_peer;
+  __nv_bfloat16* o_peer[8];
 };
 
 struct AttnSmemHeader {
@@ -288,7 +292,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     tc_fence_after_sync();
     const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
     const int row = q0 + r;
-    __nv_bfloat16* orow = p.O + (static_cast<long long>(b) * p.Tq + row) * p.ldo + h * kDh + part * kOCols;
+    __nv_bfloat16* orow;
+    if (p.rows_per_peer > 0) {
+      const int dst = min(row / p.rows_per_peer, 7);
+      orow = p.o_peer[dst] + static_cast<long long>(row - dst * p.rows_per_peer) * p.ldo + h * kDh + part * kOCols;
+    } else {
+      orow = p.O + (static_cast<long long>(b) * p.Tq + row) * p.ldo + h * kDh + part * kOCols;
+    }
 #pragma unroll
     for (int c = 0; c < kOCols; c += 32) {
       uint32_t o[32];
@@ -348,9 +358,27 @@ static int launch_attention(const void* Q, long long ldq, const void* K, long lo
 
 using namespace ltxb;
 
+static int attention_impl(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                          int64_t ldo, int32_t B, int32_t Tq, int32_t Tk, int32_t H, int32_t dh, float scale,
+                          const float* kv_bias, void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, void* stream);
+
 extern "C" int ltxb_attention_fwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
                                   void* O, int64_t ldo, int32_t B, int32_t Tq, int32_t Tk, int32_t H, int32_t dh,
                                   float scale, const float* kv_bias, void* stream) {
+  return attention_impl(Q, ldq, K, ldk, V, ldv, O, ldo, B, Tq, Tk, H, dh, scale, kv_bias, nullptr, 0, 0, stream);
+}
+
+extern "C" int ltxb_attention_fwd_peers(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
+                                        void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, int64_t ldo,
+                                        int32_t Tq, int32_t Tk, int32_t H, int32_t dh, float scale, void* stream) {
+  LTXB_CHECK_ARG(o_peers && n_peers >= 1 && n_peers <= 8 && rows_per_peer > 0 && n_peers * rows_per_peer >= Tq,
+                 "ltxb_attention_fwd_peers: %d peers x %d rows do not cover Tq=%d", n_peers, rows_per_peer, Tq);
+  return attention_impl(Q, ldq, K, ldk, V, ldv, o_peers[0], ldo, 1, Tq, Tk, H, dh, scale, nullptr, o_peers, n_peers, rows_per_peer, stream);
+}
+
+static int attention_impl(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                          int64_t ldo, int32_t B, int32_t Tq, int32_t Tk, int32_t H, int32_t dh, float scale,
+                          const float* kv_bias, void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, void* stream) {
   LTXB_CHECK_ARG(Q && K && V && O, "ltxb_attention_fwd: null pointer");
   if (B == 0 || Tq == 0) return LTXB_OK;
   LTXB_CHECK_ARG(B > 0 && Tq > 0 && Tk > 0 && H > 0, "ltxb_attention_fwd: bad shape B=%d Tq=%d Tk=%d H=%d", B, Tq, Tk, H);
@@ -365,6 +393,12 @@ extern "C" int ltxb_attention_fwd(const void* Q, int64_t ldq, const void* K, int
   p.O = reinterpret_cast<__nv_bfloat16*>(O);
   p.ldo = ldo;
   p.kv_bias = kv_bias;
+  p.rows_per_peer = rows_per_peer;
+  for (int i = 0; i < 8; ++i) {
+    void* base = (i < n_peers) ? o_peers[i] : (n_peers > 0 ? o_peers[n_peers - 1] : nullptr);
+    if (i < n_peers) LTXB_CHECK_ARG(base && aligned16(base), "ltxb_attention_fwd_peers: null / misaligned peer base %d", i);
+    p.o_peer[i] = reinterpret_cast<__nv_bfloat16*>(base);
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (dh == 128) return launch_attention<128>(Q, ldq, K, ldk, V, ldv, p, s);
   return launch_attention<64>(Q, ldq, K, ldk, V, ldv, p, s);

@@ -220,10 +220,15 @@ gate_residual_kernel(float* __restrict__ x, long long ldx, const __nv_bfloat16* 
 // full-width RMSNorm with weight, then split RoPE per head, in place on bf16.
 // thread j owns elements [8j', 8j'+8) of the first half and the matching 8 of the second half of a head.
 // ------------------------------------------------------------------------------------------------
+struct PeerBases {
+  void* p[8];
+};
+
 template <int kPer>
 __global__ void __launch_bounds__(128, kPer <= 2 ? 9 : 1)  // <= 56 registers: 9 rows per SM, 1280 tokens in ONE wave
 qknorm_rope_kernel(const __nv_bfloat16* x, long long ldx, __nv_bfloat16* out, long long ldo,  // may alias (in place)
-                   int heads_per_group, long long group_stride, int T, int H, int dh, const float* __restrict__ weight,
+                   int heads_per_group, long long group_stride, const PeerBases peers, int T, int H, int dh,
+                   const float* __restrict__ weight,
                    float eps, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, int B_pe) {
   pdl_launch_dependents();
   pdl_wait();
@@ -278,7 +283,11 @@ qknorm_rope_kernel(const __nv_bfloat16* x, long long ldx, __nv_bfloat16* out, lo
       }
     }
     // head h lands in group h / heads_per_group (one group per destination rank of the Ulysses all-to-all)
-    __nv_bfloat16* o1 = out + (h / heads_per_group) * group_stride + row * ldo + (h % heads_per_group) * dh + off;
+    // ... and with peer bases the group IS the destination GPU: the store goes straight over NVLink into that
+    // rank's receive buffer (no send buffer, no separate all-to-all)
+    const int grp = h / heads_per_group;
+    __nv_bfloat16* gbase = (out == nullptr) ? reinterpret_cast<__nv_bfloat16*>(peers.p[grp]) : out + grp * group_stride;
+    __nv_bfloat16* o1 = gbase + row * ldo + (h % heads_per_group) * dh + off;
     store8_bf16(o1, a[j]);
     store8_bf16(o1 + half, b[j]);
   }
@@ -470,6 +479,35 @@ timestep_groups_kernel(const float* __restrict__ t, int n, int cap, float* __res
   if (threadIdx.x == 0) *count = overflow ? cap + 1 : total;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cross-GPU barrier over NVLink peer memory: every rank raises its flag on every peer to `epoch`, then waits
+// until all peers have raised theirs here.  Runs stream-ordered between the kernel that WROTE peer memory and the
+// kernel that READS what the peers wrote, so the exchange needs no host round trip and no collective library.
+// ------------------------------------------------------------------------------------------------
+struct PeerFlags {
+  int* p[8];  // p[i] = rank i's flag array (n_peers ints), mapped into this process
+};
+__global__ void peer_barrier_kernel(const PeerFlags flags, int n_peers, int my_rank, int epoch) {
+  pdl_launch_dependents();
+  pdl_wait();  // everything this rank wrote to its peers before the barrier has completed
+  const int i = threadIdx.x;
+  if (i < n_peers) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flags.p[i] + my_rank), "r"(epoch) : "memory");
+    const int* mine = flags.p[my_rank] + i;
+    const long long t0 = clock64();
+    int seen;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+      if (seen - epoch < 0 && clock64() - t0 > LTXB_WATCHDOG_CYCLES) {
+        printf("ltxb: peer barrier watchdog: rank %d waits for rank %d (epoch %d, seen %d)\n", my_rank, i, epoch, seen);
+        __trap();
+      }
+    } while (seen - epoch < 0);
+    __threadfence_system();
+  }
+}
+
 static int grid_for(long long work_items, int threads) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = 148ll * 16;
@@ -539,17 +577,44 @@ extern "C" int ltxb_gate_residual(float* x, int64_t ldx, const void* y, int64_t 
   return LTXB_OK;
 }
 
+static int qknorm_rope_launch(const void* x, int64_t ldx, void* out, const PeerBases& peers, int64_t ldo,
+                              int32_t heads_per_group, int64_t group_stride, int32_t B, int32_t T, int32_t H, int32_t dh,
+                              const float* weight, float eps, const float* cos_tab, const float* sin_tab, int32_t B_pe,
+                              void* stream);
+
 extern "C" int ltxb_qknorm_rope_scatter(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t heads_per_group,
                                         int64_t group_stride, int32_t B, int32_t T, int32_t H, int32_t dh,
                                         const float* weight, float eps, const float* cos_tab, const float* sin_tab,
                                         int32_t B_pe, void* stream) {
-  LTXB_CHECK_ARG(x && out, "ltxb_qknorm_rope: null pointer");
+  LTXB_CHECK_ARG(out && aligned16(out) && group_stride % 8 == 0, "ltxb_qknorm_rope: null / misaligned out");
+  return qknorm_rope_launch(x, ldx, out, PeerBases{}, ldo, heads_per_group, group_stride, B, T, H, dh, weight, eps, cos_tab,
+                            sin_tab, B_pe, stream);
+}
+
+extern "C" int ltxb_qknorm_rope_scatter_peers(const void* x, int64_t ldx, void* const* group_bases, int32_t n_groups,
+                                              int64_t ldo, int32_t B, int32_t T, int32_t H, int32_t dh,
+                                              const float* weight, float eps, const float* cos_tab,
+                                              const float* sin_tab, int32_t B_pe, void* stream) {
+  LTXB_CHECK_ARG(group_bases && n_groups >= 1 && n_groups <= 8 && H % n_groups == 0,
+                 "ltxb_qknorm_rope_scatter_peers: 1..8 groups dividing H=%d", H);
+  PeerBases peers{};
+  for (int i = 0; i < n_groups; ++i) {
+    LTXB_CHECK_ARG(group_bases[i] && aligned16(group_bases[i]), "ltxb_qknorm_rope_scatter_peers: null / misaligned base %d", i);
+    peers.p[i] = group_bases[i];
+  }
+  return qknorm_rope_launch(x, ldx, nullptr, peers, ldo, H / n_groups, 0, B, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe, stream);
+}
+
+static int qknorm_rope_launch(const void* x, int64_t ldx, void* out, const PeerBases& peers, int64_t ldo,
+                              int32_t heads_per_group, int64_t group_stride, int32_t B, int32_t T, int32_t H, int32_t dh,
+                              const float* weight, float eps, const float* cos_tab, const float* sin_tab, int32_t B_pe,
+                              void* stream) {
+  LTXB_CHECK_ARG(x, "ltxb_qknorm_rope: null pointer");
   if (B == 0 || T == 0) return LTXB_OK;
   LTXB_CHECK_ARG(B > 0 && T > 0 && H > 0, "ltxb_qknorm_rope: bad shape B=%d T=%d H=%d", B, T, H);
   LTXB_CHECK_SUPPORTED(dh == 64 || dh == 128, "ltxb_qknorm_rope: head dim %d not in {64,128}", dh);
   LTXB_CHECK_SUPPORTED(H * (dh / 16) <= 2048, "ltxb_qknorm_rope: H*dh=%d too wide", H * dh);
-  LTXB_CHECK_ARG(aligned16(x) && ldx % 8 == 0 && aligned16(out) && ldo % 8 == 0 && group_stride % 8 == 0,
-                 "ltxb_qknorm_rope: misaligned x/out");
+  LTXB_CHECK_ARG(aligned16(x) && ldx % 8 == 0 && ldo % 8 == 0, "ltxb_qknorm_rope: misaligned x/out");
   LTXB_CHECK_ARG(heads_per_group >= 1 && H % heads_per_group == 0, "ltxb_qknorm_rope: %d heads do not split into groups of %d", H, heads_per_group);
   LTXB_CHECK_ARG(weight == nullptr || aligned16(weight), "ltxb_qknorm_rope: misaligned weight");
   LTXB_CHECK_ARG((cos_tab == nullptr) == (sin_tab == nullptr), "ltxb_qknorm_rope: cos/sin come in pairs");
@@ -564,7 +629,7 @@ extern "C" int ltxb_qknorm_rope_scatter(const void* x, int64_t ldx, void* out, i
   __nv_bfloat16* oi = reinterpret_cast<__nv_bfloat16*>(out);
 #define LTXB_LAUNCH_QK(P)                                                                                             \
   LTXB_CUDA(launch_kernel(qknorm_rope_kernel<P>, dim3(B * T), dim3(nthr), 0, st, 1, xi, ldx, oi, ldo, heads_per_group, \
-                          group_stride, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe))
+                          group_stride, peers, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe))
   if (per == 1) LTXB_LAUNCH_QK(1);
   else if (per == 2) LTXB_LAUNCH_QK(2);
   else if (per == 4) LTXB_LAUNCH_QK(4);
@@ -653,5 +718,18 @@ extern "C" int ltxb_timestep_groups(const float* t, int32_t n, int32_t cap, floa
   LTXB_CHECK_ARG(n >= 0 && cap >= 1 && cap <= 4096, "ltxb_timestep_groups: bad n=%d / cap=%d (1..4096)", n, cap);
   LTXB_CUDA(launch_kernel(timestep_groups_kernel, dim3(1), dim3(1024), cap * sizeof(unsigned), reinterpret_cast<cudaStream_t>(stream), 1, t, n, cap, values,
                                                                                                     index, count));
+  return LTXB_OK;
+}
+
+extern "C" int ltxb_peer_barrier(int32_t* const* flag_ptrs, int32_t n_peers, int32_t my_rank, int32_t epoch, void* stream) {
+  LTXB_CHECK_ARG(flag_ptrs && n_peers >= 1 && n_peers <= 8 && my_rank >= 0 && my_rank < n_peers,
+                 "ltxb_peer_barrier: bad group (n_peers=%d, my_rank=%d)", n_peers, my_rank);
+  PeerFlags f{};
+  for (int i = 0; i < n_peers; ++i) {
+    LTXB_CHECK_ARG(flag_ptrs[i] != nullptr, "ltxb_peer_barrier: null flag pointer %d", i);
+    f.p[i] = flag_ptrs[i];
+  }
+  LTXB_CUDA(launch_kernel(peer_barrier_kernel, dim3(1), dim3(32), 0, reinterpret_cast<cudaStream_t>(stream), 1, f, n_peers,
+                          my_rank, epoch));
   return LTXB_OK;
 }

@@ -342,3 +342,36 @@ def qknorm_rope_scatter(x: torch.Tensor, out: torch.Tensor, slot: int, slots: in
     _call("ltxb_qknorm_rope_scatter", 0.0, x.data_ptr(), _ld(x), base, slots * hp * dh, hp, B * T * slots * hp * dh, B, T, H, dh,
           _ptr(weight), eps, _ptr(cos), _ptr(sin), b_pe, _stream())
     return out
+
+
+def _ptr_array(ptrs):
+    return (C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def qknorm_rope_scatter_peers(x: torch.Tensor, group_bases, B: int, T: int, H: int, dh: int, ldo: int,
+                              weight: Optional[torch.Tensor], eps: float, cos: Optional[torch.Tensor] = None,
+                              sin: Optional[torch.Tensor] = None) -> None:
+    """q/k RMSNorm (+ RoPE) of x bf16 [B*T, H*dh]; head group g is stored to the raw device address
+    ``group_bases[g]`` (a peer GPU's receive buffer, rows ``ldo`` elements apart).  weight None = copy (V)."""
+    _prep(x)
+    assert x.dtype == torch.bfloat16
+    b_pe = 1
+    if cos is not None:
+        assert cos.is_contiguous() and sin.is_contiguous() and cos.shape[1:] == (H, T, dh // 2)
+        b_pe = cos.shape[0]
+    _call("ltxb_qknorm_rope_scatter_peers", 0.0, x.data_ptr(), _ld(x), _ptr_array(group_bases), len(group_bases), ldo, B, T, H, dh,
+          _ptr(weight), eps, _ptr(cos), _ptr(sin), b_pe, _stream())
+
+
+def attention_peers(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o_bases, rows_per_peer: int, ldo: int, Tq: int, Tk: int,
+                    H: int, dh: int, scale: float) -> None:
+    """Attention (B = 1) whose output rows [i*rows_per_peer, (i+1)*rows_per_peer) go to ``o_bases[i]``."""
+    _prep(q)
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16
+    _call("ltxb_attention_fwd_peers", 4.0 * H * Tq * Tk * dh, q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v),
+          _ptr_array(o_bases), len(o_bases), rows_per_peer, ldo, Tq, Tk, H, dh, scale, _stream())
+
+
+def peer_barrier(flag_ptrs, my_rank: int, epoch: int) -> None:
+    """Stream-ordered cross-GPU barrier on NVLink-mapped flag arrays (see ltxb.h)."""
+    _call("ltxb_peer_barrier", 0.0, _ptr_array(flag_ptrs), len(flag_ptrs), my_rank, epoch, _stream())

@@ -53,14 +53,59 @@ class CFGParallel:
         return both[0], both[1]  # group ranks are ordered (cond, uncond)
 
 
-class UlyssesGroup:
-    """Head-scatter / sequence-gather all-to-all around video self-attention over ``ranks``."""
+class PeerMemory:
+    """NVLink peer-mapped buffers of one rank group (torch symmetric memory supplies the allocation and the
+    address exchange; every load / store / flag on them is issued by libltxb kernels)."""
 
-    def __init__(self, ranks: List[int], rank: int, group=None) -> None:
+    def __init__(self, group, size: int, index: int) -> None:
+        import torch.distributed._symmetric_memory as symm
+
+        self._symm, self.group, self.size, self.index = symm, group, size, index
+        self._bufs: Dict[tuple, tuple] = {}
+        self.epoch = 0
+        flags = symm.empty(64, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+        flags.zero_()
+        torch.cuda.synchronize()
+        handle = symm.rendezvous(flags, group)
+        self._flags, self._flags_handle = flags, handle
+        self.flag_ptrs = [int(p) for p in handle.buffer_ptrs]
+        dist.barrier(group=group)  # every rank has zeroed its flags before anyone raises one
+
+    def buffer(self, tag: str, shape, dtype):
+        """-> (local tensor, [base address of that buffer on every rank of the group]).  Collective on first use."""
+        key = (tag, tuple(shape), dtype)
+        hit = self._bufs.get(key)
+        if hit is None:
+            t = self._symm.empty(*shape, dtype=dtype, device=torch.device("cuda", torch.cuda.current_device()))
+            handle = self._symm.rendezvous(t, self.group)
+            hit = self._bufs[key] = (t, [int(p) for p in handle.buffer_ptrs], handle)
+        return hit[0], hit[1]
+
+    def barrier(self) -> None:
+        from . import ops
+
+        self.epoch += 1
+        ops.peer_barrier(self.flag_ptrs, self.index, self.epoch)
+
+
+class UlyssesGroup:
+    """Head-scatter / sequence-gather all-to-all around video self-attention over ``ranks``.
+
+    ``fused=True`` (default on GPUs): the two all-to-alls of a block are not collective calls at all — the
+    norm+RoPE kernel stores each head group straight into the destination rank's receive buffer, the attention
+    kernel stores each output row straight into its owner's buffer, and a one-warp flag barrier on peer memory
+    orders producers and consumers.  ``fused=False``: NCCL ``all_to_all_single`` between the same kernels."""
+
+    def __init__(self, ranks: List[int], rank: int, group=None, fused: Optional[bool] = None) -> None:
         self.ranks, self.size = list(ranks), len(ranks)
         self.index = self.ranks.index(rank)
         self.group = group
         self._rope_cache: Dict[int, Tuple[Tensor, Tensor, Tuple[Tensor, Tensor]]] = {}
+        self.peers: Optional[PeerMemory] = None
+        if fused is None:
+            fused = torch.cuda.is_available() and dist.get_backend(group) == "nccl"
+        if fused:
+            self.peers = PeerMemory(dist.group.WORLD if group is None else group, self.size, self.index)
 
     # ------------------------------------------------------------------ token sharding (pure torch + dist)
     def local_slice(self, T: int) -> slice:
@@ -115,6 +160,8 @@ class UlyssesGroup:
         hp = H // P
         qkv = ws.get(tag + ".qkv", (Tl, 3 * inner), BF16, dev)
         ops.gemm(xq, attn.qkv_weight, attn.qkv_bias, qkv)
+        if self.peers is not None:
+            return self._self_attention_fused(attn, qkv, Tl, pe), hp * dh
         send = ws.get(tag + ".a2a_send", (P, Tl, 3, hp * dh), BF16, dev)
         cos, sin = (None, None) if pe is None else pe
         ops.qknorm_rope_scatter(qkv[:, :inner], send, 0, 3, P, 1, Tl, H, dh, attn.q_norm.weight, attn.q_norm.eps, cos, sin)
@@ -127,6 +174,31 @@ class UlyssesGroup:
         o = attn.sdpa(ws, tag + ".sp", q, k, v, 1, T, T, None, heads=hp)  # [T, hp*dh]
         back = self.all_to_all(o.view(P, Tl, hp * dh), ws.get(tag + ".a2a_back", (P, Tl, hp * dh), BF16, dev))
         return back, hp * dh
+
+    def _self_attention_fused(self, attn, qkv: Tensor, Tl: int, pe) -> Tensor:
+        """The exchange as NVLink stores of the producing kernels (see class docstring).  Receive buffers are
+        single: the two barriers of a block already order block b+1's remote writes after block b's reads."""
+        import math
+
+        from . import ops
+
+        P, H, dh, inner, me = self.size, attn.heads, attn.dim_head, attn.inner_dim, self.index
+        hp, w = H // P, (H // P) * dh
+        T = P * Tl
+        recv, recv_ptrs = self.peers.buffer("qkv", (P, Tl, 3, w), BF16)   # chunk i: rank i's tokens, my heads
+        back, back_ptrs = self.peers.buffer("o", (P, Tl, w), BF16)         # chunk j: head group j, my tokens
+        cos, sin = (None, None) if pe is None else pe
+        chunk = Tl * 3 * w * 2  # bytes of one rank's chunk in a qkv receive buffer
+        for slot, (lo, norm) in enumerate(((0, attn.q_norm), (inner, attn.k_norm), (2 * inner, None))):
+            bases = [recv_ptrs[j] + me * chunk + slot * w * 2 for j in range(P)]
+            ops.qknorm_rope_scatter_peers(qkv[:, lo:lo + inner], bases, 1, Tl, H, dh, 3 * w, None if norm is None else norm.weight,
+                                          0.0 if norm is None else norm.eps, None if norm is None else cos, None if norm is None else sin)
+        self.peers.barrier()  # every rank's q/k/v have landed here
+        full = recv.view(T, 3 * w)
+        o_bases = [back_ptrs[i] + me * Tl * w * 2 for i in range(P)]
+        ops.attention_peers(full[:, :w], full[:, w:2 * w], full[:, 2 * w:], o_bases, Tl, w, T, T, hp, dh, 1.0 / math.sqrt(dh))
+        self.peers.barrier()  # every rank's attention rows for my tokens have landed here
+        return back
 
     def video_to_audio(self, attn, ws: Workspace, a_in: Tensor, v_in: Tensor, Ba: int, Ta: int, Tl: int, ax: Tensor, a, v,
                        gate: Tensor, gate_table: Tensor, row_div: int, row_index: Optional[Tensor]) -> None:
@@ -159,7 +231,7 @@ class ParallelLayout:
         if self.cfg is not None:
             parts.append("cfg2")
         if self.ulysses is not None:
-            parts.append(f"ulysses{self.ulysses.size}")
+            parts.append(f"ulysses{self.ulysses.size}" + ("(nvlink-fused)" if self.ulysses.peers is not None else "(nccl)"))
         return "x".join(parts) or "single"
 
 
@@ -171,7 +243,7 @@ def plan(world: int, use_cfg: bool) -> Tuple[bool, int]:
     return cfg, (world // 2 if cfg else world)
 
 
-def make_layout(world: int, rank: int, use_cfg: bool) -> ParallelLayout:
+def make_layout(world: int, rank: int, use_cfg: bool, fused: Optional[bool] = None) -> ParallelLayout:
     cfg_split, sp = plan(world, use_cfg)
     cfg = CFGParallel(world, rank) if cfg_split else None
     uly = None
@@ -181,5 +253,5 @@ def make_layout(world: int, rank: int, use_cfg: bool) -> ParallelLayout:
             ranks = list(range(gi * sp, (gi + 1) * sp))
             g = dist.new_group(ranks) if n_groups > 1 else None
             if rank in ranks:
-                uly = UlyssesGroup(ranks, rank, g)
+                uly = UlyssesGroup(ranks, rank, g, fused)
     return ParallelLayout(cfg, uly)

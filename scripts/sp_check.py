@@ -60,15 +60,18 @@ for mt, name in [(O.LTXModelType.VideoOnly, "video"), (O.LTXModelType.AudioVideo
     model = M.LTXModel(product_config(cfg), device=dev)
     model.load_weights(tensors)
     sv, sa = model(video=to_dev(video), audio=to_dev(audio))  # single GPU
-    layout = parallel.make_layout(world, rank, use_cfg=False)
-    layout.attach(model)
-    pv, pa = model(video=to_dev(video), audio=to_dev(audio))  # sequence parallel over all ranks
-    model.seq_parallel = None
-    report(f"{name}: ulysses{world} vs oracle (video)", rel(pv, wv), 1e-2)
-    report(f"{name}: ulysses{world} vs single GPU (video)", rel(pv, sv), 5e-3)
-    if audio is not None:
-        report(f"{name}: ulysses{world} vs oracle (audio)", rel(pa, wa), 1e-2)
-        report(f"{name}: ulysses{world} vs single GPU (audio)", rel(pa, sa), 5e-3)
+    for fused in (False, True):
+        layout = parallel.make_layout(world, rank, use_cfg=False, fused=fused)
+        layout.attach(model)
+        for rep in range(2):  # twice: the second pass reuses the peer buffers / flag epochs
+            pv, pa = model(video=to_dev(video), audio=to_dev(audio))  # sequence parallel over all ranks
+        model.seq_parallel = None
+        tag = f"{name}: {layout.describe()}"
+        report(f"{tag} vs oracle (video)", rel(pv, wv), 1e-2)
+        report(f"{tag} vs single GPU (video)", rel(pv, sv), 5e-3)
+        if audio is not None:
+            report(f"{tag} vs oracle (audio)", rel(pa, wa), 1e-2)
+            report(f"{tag} vs single GPU (audio)", rel(pa, sa), 5e-3)
 
 # CFG-parallel (x Ulysses when world > 2) dev sampler vs the single-GPU cfg_batch sampler
 if world % 2 == 0:

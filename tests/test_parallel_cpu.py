@@ -76,7 +76,7 @@ def _worker(rank: int, world: int, port: int):
         ops.gemm, ops.qknorm_rope_scatter, ops.attention = fake_gemm, fake_scatter, fake_attention
         g = torch.Generator().manual_seed(0)  # identical on both ranks
         # ---------------- token sharding + gather
-        uly = parallel.UlyssesGroup(list(range(world)), rank)
+        uly = parallel.UlyssesGroup(list(range(world)), rank, fused=False)
         T, Tc = 24, 6
         cos, sin = torch.randn(1, 4, T, 64, generator=g), torch.randn(1, 4, T, 64, generator=g)
         m = M.Modality(latent=torch.randn(1, T, 128, generator=g), timesteps=torch.rand(1, T, generator=g),
