@@ -228,7 +228,7 @@ def main() -> int:
     # ---------------- model + resident inputs (synthetic, seeded; random-init weights of the real architecture)
     # graph replay is single-GPU only for now: capturing the NCCL exchanges of the sequence-parallel path hung on the
     # first attempt (profiles/README.md), so multi-rank runs launch eagerly
-    use_graph = (not args.no_graph) and world == 1
+    use_graph = (not args.no_graph) and (world == 1 or not args.nccl_exchange)
     Ta = wl.get("Ta", 0)
     model = M.LTXModel(M.production_config(M.LTXModelType.AudioVideo if Ta else M.LTXModelType.VideoOnly, num_layers=args.layers), device=dev,
                        cuda_graphs=use_graph, cache_context=args.cache_context).init_random(seed=0)

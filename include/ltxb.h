@@ -151,10 +151,16 @@ int ltxb_qknorm_rope_scatter_peers(const void* x, int64_t ldx, void* const* grou
                                    const float* cos_tab, const float* sin_tab, int32_t B_pe, void* stream);
 
 /* Cross-GPU barrier on NVLink peer memory (new).  flag_ptrs: host array, flag_ptrs[i] = rank i's
- * int32[n_peers] flag array mapped into this process (zero-initialised once).  Stream-ordered: raises this rank's
- * flag on every peer to `epoch` (release, system scope) once all earlier work of the stream has completed, then
- * waits until every peer's flag here is >= epoch.  `epoch` must increase by one per call on every rank. */
-int ltxb_peer_barrier(int32_t* const* flag_ptrs, int32_t n_peers, int32_t my_rank, int32_t epoch, void* stream);
+ * int32[n_peers] flag array mapped into this process (zero-initialised once); epoch_counter: one int32 in LOCAL
+ * device memory, zero-initialised once, advanced by the kernel (so a captured CUDA graph can replay the barrier).
+ * Stream-ordered: once all earlier work of the stream has completed, raises this rank's flag on every peer to the
+ * next epoch (release, system scope), then waits until every peer's flag here has reached it.  Every rank must
+ * call it the same number of times. */
+int ltxb_peer_barrier(int32_t* const* flag_ptrs, int32_t n_peers, int32_t my_rank, int32_t* epoch_counter, void* stream);
+
+/* Store `bytes` (multiple of 16) from src to dst_ptrs[0..n_peers) — this rank's block of an all-gather, written
+ * straight into every peer's (and its own) gather buffer over NVLink. */
+int ltxb_peer_broadcast(const void* src, int64_t bytes, void* const* dst_ptrs, int32_t n_peers, void* stream);
 
 /* a5  sinusoidal timestep features  (utils.py:486-526 with adaln.py:66: dim 256, flip_sin_to_cos,
  *     shift 0):  out bf16 [n, dim] = [cos(t*scale*f_i) | sin(t*scale*f_i)], f_i = exp(-ln(1e4) i/(dim/2)). */

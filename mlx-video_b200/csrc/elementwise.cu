@@ -487,9 +487,17 @@ timestep_groups_kernel(const float* __restrict__ t, int n, int cap, float* __res
 struct PeerFlags {
   int* p[8];  // p[i] = rank i's flag array (n_peers ints), mapped into this process
 };
-__global__ void peer_barrier_kernel(const PeerFlags flags, int n_peers, int my_rank, int epoch) {
+__global__ void peer_barrier_kernel(const PeerFlags flags, int n_peers, int my_rank, int* epoch_counter) {
   pdl_launch_dependents();
   pdl_wait();  // everything this rank wrote to its peers before the barrier has completed
+  // the epoch lives in device memory and advances by one per barrier, identically on every rank — so a captured
+  // CUDA graph can replay the barrier (a host-supplied epoch would be frozen into the graph)
+  int epoch = 0;
+  if (threadIdx.x == 0) {
+    epoch = *epoch_counter + 1;
+    *epoch_counter = epoch;
+  }
+  epoch = __shfl_sync(0xffffffffu, epoch, 0);
   const int i = threadIdx.x;
   if (i < n_peers) {
     __threadfence_system();
@@ -505,6 +513,19 @@ __global__ void peer_barrier_kernel(const PeerFlags flags, int n_peers, int my_r
       }
     } while (seen - epoch < 0);
     __threadfence_system();
+  }
+}
+
+// one source block stored to the same offset of every peer's buffer (the all-gather of a sequence-parallel result)
+struct PeerDsts {
+  uint4* p[8];
+};
+__global__ void __launch_bounds__(256) peer_broadcast_kernel(const uint4* __restrict__ src, long long n16, const PeerDsts dst, int n_peers) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n16; i += 256ll * gridDim.x) {
+    const uint4 v = src[i];
+    for (int r = 0; r < n_peers; ++r) dst.p[r][i] = v;
   }
 }
 
@@ -721,8 +742,9 @@ extern "C" int ltxb_timestep_groups(const float* t, int32_t n, int32_t cap, floa
   return LTXB_OK;
 }
 
-extern "C" int ltxb_peer_barrier(int32_t* const* flag_ptrs, int32_t n_peers, int32_t my_rank, int32_t epoch, void* stream) {
-  LTXB_CHECK_ARG(flag_ptrs && n_peers >= 1 && n_peers <= 8 && my_rank >= 0 && my_rank < n_peers,
+extern "C" int ltxb_peer_barrier(int32_t* const* flag_ptrs, int32_t n_peers, int32_t my_rank, int32_t* epoch_counter,
+                                 void* stream) {
+  LTXB_CHECK_ARG(flag_ptrs && epoch_counter && n_peers >= 1 && n_peers <= 8 && my_rank >= 0 && my_rank < n_peers,
                  "ltxb_peer_barrier: bad group (n_peers=%d, my_rank=%d)", n_peers, my_rank);
   PeerFlags f{};
   for (int i = 0; i < n_peers; ++i) {
@@ -730,6 +752,20 @@ extern "C" int ltxb_peer_barrier(int32_t* const* flag_ptrs, int32_t n_peers, int
     f.p[i] = flag_ptrs[i];
   }
   LTXB_CUDA(launch_kernel(peer_barrier_kernel, dim3(1), dim3(32), 0, reinterpret_cast<cudaStream_t>(stream), 1, f, n_peers,
-                          my_rank, epoch));
+                          my_rank, epoch_counter));
+  return LTXB_OK;
+}
+
+extern "C" int ltxb_peer_broadcast(const void* src, int64_t bytes, void* const* dst_ptrs, int32_t n_peers, void* stream) {
+  LTXB_CHECK_ARG(src && dst_ptrs && bytes >= 0 && bytes % 16 == 0 && aligned16(src) && n_peers >= 1 && n_peers <= 8,
+                 "ltxb_peer_broadcast: need a 16-byte aligned source, a multiple of 16 bytes and 1..8 destinations");
+  if (bytes == 0) return LTXB_OK;
+  PeerDsts d{};
+  for (int i = 0; i < n_peers; ++i) {
+    LTXB_CHECK_ARG(dst_ptrs[i] && aligned16(dst_ptrs[i]), "ltxb_peer_broadcast: null / misaligned destination %d", i);
+    d.p[i] = reinterpret_cast<uint4*>(dst_ptrs[i]);
+  }
+  LTXB_CUDA(launch_kernel(peer_broadcast_kernel, dim3(grid_for(bytes / 16, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                          1, reinterpret_cast<const uint4*>(src), static_cast<long long>(bytes / 16), d, n_peers));
   return LTXB_OK;
 }

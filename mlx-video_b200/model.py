@@ -357,7 +357,10 @@ class LTXModel:
             self._graphs.clear()
 
     def __call__(self, video: Optional[Modality] = None, audio: Optional[Modality] = None):
-        if self._graphs is not None and self.seq_parallel is None and not torch.cuda.is_current_stream_capturing():
+        # sequence-parallel forwards are captured only when every exchange is a libltxb kernel on NVLink peer memory
+        # (capturing NCCL collectives hung, profiles/README.md)
+        sp_ok = self.seq_parallel is None or getattr(self.seq_parallel, "peers", None) is not None
+        if self._graphs is not None and sp_ok and not torch.cuda.is_current_stream_capturing():
             return self._graphed_call(video, audio)
         return self._forward(video, audio)
 

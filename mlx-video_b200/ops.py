@@ -372,6 +372,15 @@ def attention_peers(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o_bases, 
           _ptr_array(o_bases), len(o_bases), rows_per_peer, ldo, Tq, Tk, H, dh, scale, _stream())
 
 
-def peer_barrier(flag_ptrs, my_rank: int, epoch: int) -> None:
+def peer_barrier(flag_ptrs, my_rank: int, epoch_counter: torch.Tensor) -> None:
     """Stream-ordered cross-GPU barrier on NVLink-mapped flag arrays (see ltxb.h)."""
-    _call("ltxb_peer_barrier", 0.0, _ptr_array(flag_ptrs), len(flag_ptrs), my_rank, epoch, _stream())
+    _prep(epoch_counter)
+    assert epoch_counter.dtype == torch.int32
+    _call("ltxb_peer_barrier", 0.0, _ptr_array(flag_ptrs), len(flag_ptrs), my_rank, epoch_counter.data_ptr(), _stream())
+
+
+def peer_broadcast(src: torch.Tensor, dst_ptrs) -> None:
+    """This rank's contiguous block -> the raw device addresses ``dst_ptrs`` (one per peer)."""
+    _prep(src)
+    assert src.is_contiguous()
+    _call("ltxb_peer_broadcast", 0.0, src.data_ptr(), src.numel() * src.element_size(), _ptr_array(dst_ptrs), len(dst_ptrs), _stream())

@@ -62,7 +62,7 @@ class PeerMemory:
 
         self._symm, self.group, self.size, self.index = symm, group, size, index
         self._bufs: Dict[tuple, tuple] = {}
-        self.epoch = 0
+        self.epoch_counter = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
         flags = symm.empty(64, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
         flags.zero_()
         torch.cuda.synchronize()
@@ -84,8 +84,20 @@ class PeerMemory:
     def barrier(self) -> None:
         from . import ops
 
-        self.epoch += 1
-        ops.peer_barrier(self.flag_ptrs, self.index, self.epoch)
+        ops.peer_barrier(self.flag_ptrs, self.index, self.epoch_counter)
+
+    def all_gather(self, tag: str, block: Tensor) -> Tensor:
+        """Every rank's ``block`` -> (P, *block.shape) on every rank, as NVLink stores + one flag barrier.  The
+        barrier BEFORE the stores keeps a fast rank from overwriting a buffer a slow rank is still reading."""
+        from . import ops
+
+        block = block.contiguous()
+        out, ptrs = self.buffer(tag, (self.size, *block.shape), block.dtype)
+        nbytes = block.numel() * block.element_size()
+        self.barrier()
+        ops.peer_broadcast(block, [p + self.index * nbytes for p in ptrs])
+        self.barrier()
+        return out
 
 
 class UlyssesGroup:
@@ -137,6 +149,8 @@ class UlyssesGroup:
     def gather_tokens(self, x: Tensor) -> Tensor:
         """(B, T/P, C) on every rank -> (B, T, C)."""
         x = x.contiguous()
+        if self.peers is not None and x.shape[0] == 1 and (x.numel() * x.element_size()) % 16 == 0:
+            return self.peers.all_gather("tokens", x[0]).reshape(1, self.size * x.shape[1], x.shape[2]).clone()
         parts = [torch.empty_like(x) for _ in range(self.size)]
         dist.all_gather(parts, x, group=self.group)
         return torch.cat(parts, dim=1)
@@ -209,8 +223,11 @@ class UlyssesGroup:
         inner, dev = attn.inner_dim, a_in.device
         q, k, vv = attn.project(ws, "av.v2a", a_in, Ba, Ta, v_in, Tl, a.cross_positional_embeddings, v.cross_positional_embeddings)
         kv_local = ws.get("av.v2a.kv", (Ba * Tl, 2 * inner), BF16, dev)  # the buffer k / vv are views of
-        parts = ws.get("av.v2a.kv_all", (self.size, Ba * Tl, 2 * inner), BF16, dev)
-        dist.all_gather_into_tensor(parts, kv_local, group=self.group)
+        if self.peers is not None:
+            parts = self.peers.all_gather("av.v2a.kv_all", kv_local)
+        else:
+            parts = ws.get("av.v2a.kv_all", (self.size, Ba * Tl, 2 * inner), BF16, dev)
+            dist.all_gather_into_tensor(parts, kv_local, group=self.group)
         full = parts.view(self.size * Tl, 2 * inner)
         o = attn.sdpa(ws, "av.v2a", q, full[:, :inner], full[:, inner:], Ba, Ta, self.size * Tl, None)
         ops.gemm(o, attn.to_out.weight, attn.to_out.bias, ax, _lib.EPI_RESID_GATE_F32, resid=ax, gate=gate,
