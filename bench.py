@@ -310,7 +310,7 @@ def main() -> int:
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    gpu_launches = ops.launches - launches0  # 0 when a CUDA graph replays them; recounted from an eager step below
+    gpu_launches = ops.launches - launches0  # host-side launches only: kernels replayed from a CUDA graph are recounted from an eager step below
     clk = clocks.stop()
     assert torch.isfinite(x).all(), "latents went non-finite"
 
@@ -403,7 +403,7 @@ def main() -> int:
             "clocks": clk,
             "e2e": {"value": T * args.steps / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms / args.steps,
                     "wall_ms_per_step": e2e_wall_ms / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": gpu_launches if gpu_launches > 0 else launches_per_step * args.steps,
+            "gpu_launches": gpu_launches if not use_graph else launches_per_step * args.steps,
             "launch_mode": "eager" if not use_graph else f"cuda graph replay ({launches_per_step} kernels per step captured)",
             "context_cache": bool(args.cache_context),
             "roofline": {"kernel": "gemm_bf16_kernel (tcgen05/TMEM, TMA-fed)", "bound": "tensor", "achieved": gemm_tflops, "peak": pk["tflops"],

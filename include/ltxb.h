@@ -40,6 +40,10 @@ int ltxb_device_check(void);
  * Call once per thread before the first launch when the host framework uses a device other than 0. */
 int ltxb_set_device(int32_t device);
 
+/* Kernels launched by this library since it was loaded (one C-ABI call may launch more than one: the attention
+ * key-split adds a merge kernel).  bench.py reports the delta over its timed region as `gpu_launches`. */
+int64_t ltxb_kernel_launches(void);
+
 /* ------------------------------------------------------------------------------------------------
  * K1  nn.Linear  (attention.py:91-93,100,123-126,142; feed_forward.py:31,33; ltx.py:130,292,301;
  *                 adaln.py:27,130-132; text_projection.py:18,20)
@@ -193,10 +197,21 @@ int ltxb_cast_bf16_to_f32(const void* x, float* out, int64_t n, void* stream);
  *   O bf16 [B*Tq, H*dh] (ldo).  Non-causal.  kv_bias f32 [B, Tk] additive or NULL
  *   (ltx.py:91-107 turns a 0/1 context mask into (m-1)*1e9).  dh in {64,128}.
  * FlashAttention-style online softmax; both contractions on tcgen05 with TMEM accumulators, TMA loads.
+ * Tq <= 128: one query tile per CTA, P staged in shared memory.  Tq > 128: two query tiles per CTA ping-pong on
+ * the tensor core, P kept in TMEM as the A operand of O += P V (attention_pair.cu).
  * ---------------------------------------------------------------------------------------------- */
 int ltxb_attention_fwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
                        int64_t ldo, int32_t B, int32_t Tq, int32_t Tk, int32_t H, int32_t dh, float scale,
                        const float* kv_bias, void* stream);
+
+/* Scratch for the key-split of the ragged last wave of attention CTAs (Tq > 128): when the (batch, head, 256-query)
+ * jobs do not divide the SM count, the jobs of the last partial wave are cut into key ranges whose partial
+ * (O, max, sum) are parked here and merged by a second small kernel.  The library never allocates: the host
+ * framework registers one buffer per device (bytes >= ltxb_attention_workspace_bytes()); without it (or with
+ * workspace == NULL) the last wave simply runs unsplit.  The buffer must stay valid while attention calls are in
+ * flight; its contents are scratch. */
+int64_t ltxb_attention_workspace_bytes(void);
+int ltxb_attention_set_workspace(void* workspace, int64_t bytes);
 
 /* The same with the Ulysses sequence-gather all-to-all fused into the epilogue (B = 1): output row r is stored to
  * o_peers[r / rows_per_peer] + (r % rows_per_peer) * ldo — rank i's NVLink-mapped receive buffer, already offset

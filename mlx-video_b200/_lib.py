@@ -45,6 +45,7 @@ SIGNATURES = {
     "ltxb_abi_version": (C.c_int, []),
     "ltxb_device_check": (C.c_int, []),
     "ltxb_set_device": (C.c_int, [_i32]),
+    "ltxb_kernel_launches": (C.c_int64, []),
     "ltxb_gemm_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, C.POINTER(Epilogue), _i32, _i32, _vp]),
     "ltxb_gemm_workspace_bytes": (C.c_int64, []),
     "ltxb_gemm_set_workspace": (C.c_int, [_vp, _i64, _vp]),
@@ -64,6 +65,8 @@ SIGNATURES = {
     "ltxb_cast_f32_to_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),
     "ltxb_cast_bf16_to_f32": (C.c_int, [_vp, _vp, _i64, _vp]),
     "ltxb_attention_fwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
+    "ltxb_attention_workspace_bytes": (C.c_int64, []),
+    "ltxb_attention_set_workspace": (C.c_int, [_vp, _i64]),
     "ltxb_euler_step": (C.c_int, [_vp, _vp, _vp, _f32, _vp, _f32, _f32, _vp, _vp, _i64, _i32, _vp, _vp]),
 }
 

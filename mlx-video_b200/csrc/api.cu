@@ -54,6 +54,8 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
   return LTXB_OK;
 }
 
+std::atomic<long long> g_kernel_launches{0};
+
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("LTXB_PDL"); return e == nullptr || atoi(e) != 0; }();
   return on;
@@ -75,7 +77,9 @@ int num_sms() {
 
 extern "C" const char* ltxb_last_error(void) { return ltxb::g_err; }
 
-extern "C" int ltxb_abi_version(void) { return 2; }
+extern "C" int ltxb_abi_version(void) { return 3; }
+
+extern "C" int64_t ltxb_kernel_launches(void) { return ltxb::g_kernel_launches.load(std::memory_order_relaxed); }
 
 extern "C" int ltxb_device_check(void) {
   int dev = 0;

@@ -17,7 +17,9 @@
 //               rescale / store their half of the O columns.  O is rescaled in TMEM only when a maximum moved.
 // S_{j+1} is issued before P_j V_j, so the tensor core computes the next scores while the softmax
 // warps work on the current ones.
-#include "common.cuh"
+#include <cstdlib>
+
+#include "attention.cuh"
 #include "ptx.cuh"
 
 namespace ltxb {
@@ -28,18 +30,6 @@ constexpr int kTileQ = 128;
 constexpr int kTileKV = 128;
 constexpr int kAttnHeader = 4096;
 constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO = 256;
-
-struct AttnParams {
-  int B, Tq, Tk, H;
-  float scale_log2;  // softmax scale * log2(e)
-  __nv_bfloat16* O;
-  long long ldo;
-  const float* kv_bias;  // [B, Tk] additive (natural-log domain) or null
-  // Ulysses gather fused into the epilogue: query rows [i*rows_per_peer, (i+1)*rows_per_peer) are stored straight
-  // into rank i's receive buffer over NVLink (rows_per_peer == 0: plain local output)
-  int rows_per_peer;
-  __nv_bfloat16* o_peer[8];
-};
 
 struct AttnSmemHeader {
   uint64_t q_full;
@@ -292,13 +282,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     tc_fence_after_sync();
     const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
     const int row = q0 + r;
-    __nv_bfloat16* orow;
-    if (p.rows_per_peer > 0) {
-      const int dst = min(row / p.rows_per_peer, 7);
-      orow = p.o_peer[dst] + static_cast<long long>(row - dst * p.rows_per_peer) * p.ldo + h * kDh + part * kOCols;
-    } else {
-      orow = p.O + (static_cast<long long>(b) * p.Tq + row) * p.ldo + h * kDh + part * kOCols;
-    }
+    __nv_bfloat16* orow = attn_out_row(p, b, row, h, kDh) + part * kOCols;
 #pragma unroll
     for (int c = 0; c < kOCols; c += 32) {
       uint32_t o[32];
@@ -400,6 +384,9 @@ static int attention_impl(const void* Q, int64_t ldq, const void* K, int64_t ldk
     p.o_peer[i] = reinterpret_cast<__nv_bfloat16*>(base);
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // more than one query tile: two tiles per CTA ping-pong on the tensor core (attention_pair.cu)
+  static const bool force_single = [] { const char* e = getenv("LTXB_ATTN_SINGLE"); return e != nullptr && atoi(e) != 0; }();
+  if (Tq > kTileQ && !force_single) return launch_attention_pair(Q, ldq, K, ldk, V, ldv, p, dh, s);
   if (dh == 128) return launch_attention<128>(Q, ldq, K, ldk, V, ldv, p, s);
   return launch_attention<64>(Q, ldq, K, ldk, V, ldv, p, s);
 }

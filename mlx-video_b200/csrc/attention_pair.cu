@@ -1,0 +1,538 @@
+// K2, more than one query tile: two 128-row query tiles per CTA share every K/V tile and take turns on the
+// tensor core, so one tile's softmax (MUFU / FMA pipes) runs under the other tile's contractions.
+//
+// Replaces mlx_video/models/ltx/attention.py:13-53 (mx.fast.scaled_dot_product_attention) for the video
+// self-attention, the text cross-attention and a2v of transformer.py:247-339.
+//
+//   warp 0       TMA producer: Q0, Q1 once; K and V tiles into 2-deep rings
+//   warp 1       MMA issuer (one thread):   S_t = Q_t K_j^T  (smem x smem)            -> TMEM S_t   (128 fp32 columns)
+//                                           O_t += P_t V_j   (P_t read from TMEM)     -> TMEM O_t   (dh fp32 columns)
+//   warps 2,3    idle (keep the softmax warps aligned to their TMEM lane quarters)
+//   warps 4..7   softmax of tile 0, one thread per query row: the whole 128-column score row lives in registers,
+//   warps 8..11  softmax of tile 1  so there is no cross-thread exchange; P_t is written back over S_t in TMEM as
+//                packed bf16 (no shared-memory round trip) and consumed by the next tcgen05.mma as its A operand.
+// Issue order per K/V tile j:  PV_0(j), S_0(j+1), PV_1(j), S_1(j+1)  — tile 0's softmax of j+1 overlaps tile 1's
+// MMAs and vice versa.  The running maximum is only moved when a row's tile maximum exceeds it by more than
+// 2^kTau (exponents stay in fp32 / bf16 range), so the O accumulator is almost never rescaled after tile 0.
+//
+// Ragged last wave: jobs = B*H*ceil(Tq/256) rarely divide the SM count.  The jobs of the last partial wave are
+// cut into n_split key ranges, one CTA each; those CTAs park unnormalised (O, m, l) in the workspace and
+// attention_combine_kernel merges them (log-sum-exp) into the output.
+#include <algorithm>
+#include <cstdlib>
+
+#include "attention.cuh"
+#include "ptx.cuh"
+
+namespace ltxb {
+
+constexpr int kPairThreads = 384;
+constexpr int kPairHeader = 1024;
+constexpr float kTau = 8.0f;  // log2 units
+#ifndef LTXB_ATTN_EMU
+#define LTXB_ATTN_EMU 2
+#endif
+constexpr float kMasked = -1.0e9f;  // score of an out-of-range key: finite, so the polynomial exp2 never sees -inf
+#ifndef LTXB_ATTN_CHUNK
+#define LTXB_ATTN_CHUNK 1
+#endif
+constexpr bool kChunkP = LTXB_ATTN_CHUNK != 0;  // signal P_t in two key halves so PV_t starts under the second half's exps
+constexpr int kEmu = LTXB_ATTN_EMU;  // of every 8 column pairs, how many take the FMA-pipe exp2
+constexpr int kRegsIssue = 104, kRegsSoftmax = 200;  // 128 * 104 + 256 * 200 <= 64 K registers
+
+// LTXB_ATTN_TRACE: CTA 0 records clock64() at the phase boundaries of its first 16 key tiles into the workspace
+// (long long [3 roles][16 tiles][8 events]; roles: softmax 0, softmax 1, MMA issuer) — scripts/attn_trace.py prints it.
+#ifdef LTXB_ATTN_TRACE
+#define TRACE(role, it, ev)                                                                                  \
+  do {                                                                                                       \
+    if (blockIdx.x == 0 && (it) < 16 && p.ws_o != nullptr)                                                   \
+      reinterpret_cast<long long*>(p.ws_o)[((role) * 16 + (it)) * 8 + (ev)] = clock64();                      \
+  } while (0)
+#else
+#define TRACE(role, it, ev) do {} while (0)
+#endif
+
+struct PairSmemHeader {
+  uint64_t q_full;
+  uint64_t k_full[2], k_empty[2];
+  uint64_t v_full[2], v_empty[2];
+  uint64_t s_full[2];   // S_t(j) complete              (MMA -> softmax t)
+  uint64_t p_full[2][2];  // P_t(j) keys [0,64) / [64,128) written, O_t rescaled (softmax t -> MMA); one arrival per warp
+  uint64_t pv_done[2];  // O_t += P_t(j) V_j complete   (MMA -> softmax t)
+  uint32_t tmem_base;
+};
+static_assert(sizeof(PairSmemHeader) <= kPairHeader, "header overflow");
+
+struct PairJob {
+  int b, h, q0, kv_lo, kv_hi, slot;  // slot < 0: whole job, normalised bf16 output
+};
+
+__device__ __forceinline__ PairJob decode_pair_job(const AttnParams& p, int cta) {
+  PairJob j;
+  const int n_kv = (p.Tk + 127) / 128;
+  int job;
+  if (cta < p.n_full) {
+    job = cta, j.slot = -1, j.kv_lo = 0, j.kv_hi = n_kv;
+  } else {
+    const int idx = cta - p.n_full;
+    job = p.n_full + idx / p.n_split;
+    const int part = idx % p.n_split;
+    j.slot = idx;
+    j.kv_lo = static_cast<int>(static_cast<long long>(part) * n_kv / p.n_split);
+    j.kv_hi = static_cast<int>(static_cast<long long>(part + 1) * n_kv / p.n_split);
+  }
+  const int bh = job / p.n_qp;
+  j.q0 = (job - bh * p.n_qp) * 256;
+  j.b = bh / p.H;
+  j.h = bh - j.b * p.H;
+  return j;
+}
+
+template <int kDh>
+__global__ void __launch_bounds__(kPairThreads, 1)
+attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                      const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  constexpr int kBlocks = kDh / 64;                       // 64-column (128 B) swizzle blocks per row
+  constexpr uint32_t kBlockBytes = 128 * 128;             // 128 rows x 128 B
+  constexpr uint32_t kTileBytes = kBlocks * kBlockBytes;  // one Q / K / V tile
+  constexpr uint32_t kColO = 256;                         // O_t at kColO + t*kDh; S_t (and P_t) at t*128
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  PairSmemHeader* hdr = reinterpret_cast<PairSmemHeader*>(smem);
+  uint8_t* sQ = smem + kPairHeader;   // 2 tiles
+  uint8_t* sK = sQ + 2 * kTileBytes;  // 2 stages
+  uint8_t* sV = sK + 2 * kTileBytes;  // 2 stages
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const PairJob job = decode_pair_job(p, blockIdx.x);
+  const int n_it = job.kv_hi - job.kv_lo;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(&hdr->q_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&hdr->k_full[i], 1);
+        mbar_init(&hdr->k_empty[i], 1);
+        mbar_init(&hdr->v_full[i], 1);
+        mbar_init(&hdr->v_empty[i], 1);
+        mbar_init(&hdr->s_full[i], 1);
+        mbar_init(&hdr->p_full[i][0], 4);
+        mbar_init(&hdr->p_full[i][1], 4);
+        mbar_init(&hdr->pv_done[i], 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<1>(&hdr->tmem_base, 512);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&hdr->tmem_base);
+  pdl_launch_dependents();
+  pdl_wait();
+
+  // the softmax threads hold a whole 128-column score row: they take registers from the producer / issuer warpgroup
+  if (warp < 4) {
+    reg_dealloc<kRegsIssue>();
+    if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&hdr->q_full, 2 * kTileBytes);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int j = 0; j < kBlocks; ++j)
+          tma_load_3d(sQ + t * kTileBytes + j * kBlockBytes, &tmap_q, &hdr->q_full, job.h * kDh + 64 * j, job.q0 + 128 * t, job.b);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const int row = (job.kv_lo + it) * 128;
+        mbar_wait(&hdr->k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&hdr->k_full[st], kTileBytes);
+#pragma unroll
+        for (int j = 0; j < kBlocks; ++j)
+          tma_load_3d(sK + st * kTileBytes + j * kBlockBytes, &tmap_k, &hdr->k_full[st], job.h * kDh + 64 * j, row, job.b);
+        mbar_wait(&hdr->v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&hdr->v_full[st], kTileBytes);
+#pragma unroll
+        for (int j = 0; j < kBlocks; ++j)
+          tma_load_3d(sV + st * kTileBytes + j * kBlockBytes, &tmap_v, &hdr->v_full[st], job.h * kDh + 64 * j, row, job.b);
+      }
+    }
+    } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(128, kDh, 0, 1);  // B = V is MN-major (dh contiguous)
+      auto issue_s = [&](int t, int it) {                        // K stage it&1 is full
+        const uint32_t q_addr = smem_u32(sQ + t * kTileBytes);
+        const uint32_t k_addr = smem_u32(sK + (it & 1) * kTileBytes);
+        const uint32_t d = tmem_base + t * 128;
+#pragma unroll
+        for (int kk = 0; kk < kDh / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * kBlockBytes + (kk & 3) * 32;
+          umma_bf16_ss<1>(d, make_smem_desc_sw128(q_addr + off, 16, 1024), make_smem_desc_sw128(k_addr + off, 16, 1024),
+                          idesc_s, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(&hdr->s_full[t]);
+      };
+      // O_t += P_t(it) V: keys [0,64) as soon as the first half of P_t is in TMEM, the rest under the second half's exps
+      auto issue_pv = [&](int t, int it) {  // V stage it&1 is full
+        const uint32_t v_addr = smem_u32(sV + (it & 1) * kTileBytes);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          if (kChunkP || hf == 1) {
+            mbar_wait(&hdr->p_full[t][hf], it & 1);
+            tc_fence_after_sync();
+          }
+          TRACE(2, it, t * 4 + hf);  // P_t half hf seen by the issuer
+#pragma unroll
+          for (int kk = 4 * hf; kk < 4 * hf + 4; ++kk)  // 16 keys per MMA = 8 packed TMEM columns of P; V: 16 kv rows = 2048 B
+            umma_bf16_ts(tmem_base + kColO + t * kDh, tmem_base + t * 128 + kk * 8,
+                         make_smem_desc_sw128(v_addr + kk * 2048, kBlockBytes, 1024), idesc_o, (it | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&hdr->pv_done[t]);
+        TRACE(2, it, t * 4 + 2);  // PV_t issued
+      };
+      mbar_wait(&hdr->q_full, 0);
+      mbar_wait(&hdr->k_full[0], 0);
+      tc_fence_after_sync();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      umma_commit(&hdr->k_empty[0]);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        const bool more = it + 1 < n_it;
+        mbar_wait(&hdr->v_full[st], (it >> 1) & 1);
+        issue_pv(0, it);
+        if (more) {  // S_0(it+1) overwrites P_0(it): the tensor pipe runs MMAs in issue order
+          mbar_wait(&hdr->k_full[st ^ 1], ((it + 1) >> 1) & 1);
+          tc_fence_after_sync();
+          issue_s(0, it + 1);
+          TRACE(2, it, 3);  // S_0(it+1) issued
+        }
+        issue_pv(1, it);
+        umma_commit(&hdr->v_empty[st]);
+        if (more) {
+          issue_s(1, it + 1);
+          TRACE(2, it, 7);  // S_1(it+1) issued
+          umma_commit(&hdr->k_empty[st ^ 1]);
+        }
+      }
+    }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue: one thread per query row =====================
+    reg_alloc<kRegsSoftmax>();
+    const int t = (warp - 4) >> 2;      // query tile of this warpgroup
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t t_s = t_lane + t * 128;
+    const uint32_t t_o = t_lane + kColO + t * kDh;
+    constexpr float kLog2e = 1.4426950408889634f;
+    float m = -INFINITY, l = 0.f;
+    for (int it = 0; it < n_it; ++it) {
+      if (lane == 0 && quarter == 0) TRACE(t, it, 0);  // start waiting for S_t(it)
+      mbar_wait(&hdr->s_full[t], it & 1);
+      tc_fence_after_sync();
+      if (lane == 0 && quarter == 0) TRACE(t, it, 1);  // S_t(it) ready
+      uint32_t sr[128];
+#pragma unroll
+      for (int c = 0; c < 128; c += 32) tmem_ld_x32(t_s + c, *reinterpret_cast<uint32_t(*)[32]>(&sr[c]));
+      tmem_wait_ld();
+      if (lane == 0 && quarter == 0) TRACE(t, it, 2);  // scores in registers
+
+      const int kv0 = (job.kv_lo + it) * 128;
+      const int kv_valid = p.Tk - kv0;
+      float sc = p.scale_log2;
+      if (p.kv_bias != nullptr) {  // rare (context masks): fold scale and bias into the scores first
+        const float* bias = p.kv_bias + static_cast<long long>(job.b) * p.Tk + kv0;
+#pragma unroll
+        for (int c = 0; c < 128; ++c) {
+          const float bv = (c < kv_valid) ? __ldg(bias + c) * kLog2e : 0.f;
+          sr[c] = __float_as_uint(fmaf(__uint_as_float(sr[c]), sc, bv));
+        }
+        sc = 1.0f;
+      }
+      if (kv_valid < 128) {
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if (c >= kv_valid) sr[c] = __float_as_uint(kMasked);
+      }
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 128; c += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mx[u] = fmaxf(mx[u], __uint_as_float(sr[c + u]));
+      }
+      const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sc;  // sc > 0
+      // move the running maximum only when it is exceeded by more than 2^kTau (or on the first valid tile); keep it an
+      // INTEGER (any stabiliser near the maximum will do) so that 2^(m - m') and the range reduction below are exact
+      const float m_new = (m_tile > m + kTau) ? fmaxf(ceilf(m_tile), -1048576.0f) : m;
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = (m_new == m) ? 1.0f : fast_exp2(m - m_use);  // m = -inf -> 0
+      // rescale the running O when some row of this warp moved its maximum (O is free once PV_t(it-1) is done)
+      if (it > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+        mbar_wait(&hdr->pv_done[t], (it - 1) & 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int c = 0; c < kDh; c += 32) {
+          uint32_t o[32];
+          tmem_ld_x32(t_o + c, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_x32(t_o + c, o);
+        }
+      }
+      // P = 2^(s*sc - m).  MUFU.EX2 (16 / clk / SM) is the scarcest unit of this kernel, so kEmu of every 8 column
+      // pairs are computed on the FMA pipe instead: n = round(x) through the 1.5*2^23 trick, f = x - n in
+      // [-0.5, 0.5], 2^f by a degree-3 minimax polynomial (7.5e-5 relative, far below the bf16 rounding of P),
+      // 2^n by an add into the exponent field.  Packed f32x2 arithmetic throughout.
+      if (lane == 0 && quarter == 0) TRACE(t, it, 3);  // maximum known
+      constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
+      const uint64_t sc2 = pack_f32x2(sc, sc);
+      const uint64_t negm2 = pack_f32x2(-m_use, -m_use);
+      const uint64_t c2 = pack_f32x2(kMagic - m_use, kMagic - m_use);  // exact: m_use is an integer below 2^22
+      const uint64_t neg1 = pack_f32x2(-1.0f, -1.0f);
+      const uint64_t k0 = pack_f32x2(0.99992807f, 0.99992807f), k1 = pack_f32x2(0.69326099f, 0.69326099f);
+      const uint64_t k2 = pack_f32x2(0.24261114f, 0.24261114f), k3 = pack_f32x2(0.05517167f, 0.05517167f);
+      uint64_t rs2[2] = {0ull, 0ull};
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int pi = 0; pi < 32; ++pi) {
+          const int c = half * 64 + 2 * pi;
+          const uint64_t s2 = pack_f32x2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));
+          float e0, e1;
+          if ((pi & 7) < kEmu) {
+            float x0, x1, p0, p1;
+            unpack_f32x2(fma_f32x2(s2, sc2, c2), x0, x1);  // kMagic + round(x)
+            x0 = fmaxf(x0, kMagic - 126.0f), x1 = fmaxf(x1, kMagic - 126.0f);
+            const uint64_t f = fma_f32x2(s2, sc2, fma_f32x2(pack_f32x2(x0, x1), neg1, c2));  // x - round(x)
+            unpack_f32x2(fma_f32x2(fma_f32x2(fma_f32x2(k3, f, k2), f, k1), f, k0), p0, p1);
+            e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(x0) << 23));
+            e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(x1) << 23));
+          } else {
+            float x0, x1;
+            unpack_f32x2(fma_f32x2(s2, sc2, negm2), x0, x1);
+            e0 = fast_exp2(x0), e1 = fast_exp2(x1);
+          }
+          rs2[pi & 1] = add_f32x2(rs2[pi & 1], pack_f32x2(e0, e1));
+          pk[pi] = pack_bf16x2(e0, e1);
+        }
+        tmem_st_x32(t_s + half * 32, pk);  // P_t over the first 64 columns of S_t
+        if (kChunkP || half == 1) {
+          tmem_wait_st();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&hdr->p_full[t][half]);
+        }
+        if (lane == 0 && quarter == 0) TRACE(t, it, 4 + half);  // P half signalled
+      }
+      float r0, r1, r2, r3;
+      unpack_f32x2(rs2[0], r0, r1);
+      unpack_f32x2(rs2[1], r2, r3);
+      l = l * alpha + ((r0 + r1) + (r2 + r3));
+      m = m_new;
+    }
+    // ---- epilogue ----
+    if (n_it > 0) {
+      mbar_wait(&hdr->pv_done[t], (n_it - 1) & 1);
+      tc_fence_after_sync();
+    }
+    const int row = job.q0 + t * 128 + r;
+    if (job.slot < 0) {
+      const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
+      __nv_bfloat16* orow = attn_out_row(p, job.b, row, job.h, kDh);
+#pragma unroll
+      for (int c = 0; c < kDh; c += 32) {
+        uint32_t o[32];
+        tmem_ld_x32(t_o + c, o);
+        tmem_wait_ld();
+        if (row < p.Tq) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
+            w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
+            w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
+            w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c + 8 * i) = w;
+          }
+        }
+      }
+    } else {
+      const long long prow = static_cast<long long>(job.slot) * 256 + t * 128 + r;
+      float* wo = p.ws_o + prow * kDh;
+      if (row < p.Tq) *reinterpret_cast<float2*>(p.ws_ml + prow * 2) = make_float2(m, l);
+#pragma unroll
+      for (int c = 0; c < kDh; c += 32) {
+        uint32_t o[32];
+        tmem_ld_x32(t_o + c, o);
+        tmem_wait_ld();
+        if (row < p.Tq) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<uint4*>(wo + c + 4 * i) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+// One warp per query row of a split job: O = sum_i 2^(m_i - M) O_i / sum_i 2^(m_i - M) l_i.
+template <int kDh>
+__global__ void __launch_bounds__(256) attention_combine_kernel(const AttnParams p, int n_left) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int kPer = kDh / 32;  // columns per lane
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int jl = gw >> 8, rr = gw & 255;
+  if (jl >= n_left) return;
+  const int jb = p.n_full + jl;
+  const int bh = jb / p.n_qp;
+  const int row = (jb - bh * p.n_qp) * 256 + rr;
+  if (row >= p.Tq) return;
+  const int b = bh / p.H, h = bh - b * p.H;
+  const long long prow0 = static_cast<long long>(jl) * p.n_split * 256 + rr;
+  float M = -INFINITY;
+  for (int i = 0; i < p.n_split; ++i) M = fmaxf(M, p.ws_ml[(prow0 + i * 256ll) * 2]);
+  float acc[kPer];
+#pragma unroll
+  for (int u = 0; u < kPer; ++u) acc[u] = 0.f;
+  float L = 0.f;
+  for (int i = 0; i < p.n_split; ++i) {
+    const long long pr = prow0 + i * 256ll;
+    const float2 ml = *reinterpret_cast<const float2*>(p.ws_ml + pr * 2);
+    const float w = (ml.x == -INFINITY) ? 0.f : fast_exp2(ml.x - M);
+    L += w * ml.y;
+    const float* src = p.ws_o + pr * kDh + lane * kPer;
+    if constexpr (kPer == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(src);
+      acc[0] += w * v.x, acc[1] += w * v.y, acc[2] += w * v.z, acc[3] += w * v.w;
+    } else {
+      const float2 v = *reinterpret_cast<const float2*>(src);
+      acc[0] += w * v.x, acc[1] += w * v.y;
+    }
+  }
+  const float inv = (L > 0.f) ? 1.0f / L : 0.f;
+  __nv_bfloat16* dst = attn_out_row(p, b, row, h, kDh) + lane * kPer;
+  if constexpr (kPer == 4) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv));
+  } else {
+    *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+  }
+}
+
+// ---- split-KV workspace: registered by the host framework (the library never allocates) -----------
+constexpr int kMaxDevices = 16;
+constexpr int kMaxSlots = 160;  // <= SM count
+struct AttnWorkspace {
+  float* base = nullptr;
+  long long bytes = 0;
+};
+static AttnWorkspace g_attn_ws[kMaxDevices];
+static long long attn_ws_bytes_for(int slots, int dh) { return static_cast<long long>(slots) * 256 * (dh + 2) * sizeof(float); }
+
+template <int kDh>
+static int launch_pair(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, AttnParams p,
+                       cudaStream_t stream) {
+  constexpr size_t kTileBytes = static_cast<size_t>(kDh / 64) * 128 * 128;
+  constexpr size_t smem = 1024 + kPairHeader + 6 * kTileBytes;
+  auto kernel = attention_pair_kernel<kDh>;
+  static bool configured = false;
+  if (!configured) {
+    LTXB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = true;
+  }
+  const int sms = num_sms();
+  LTXB_CHECK_SUPPORTED(sms > 0, "ltxb_attention_fwd: no device");
+  const int n_kv = (p.Tk + 127) / 128;
+  p.n_qp = (p.Tq + 255) / 256;
+  const long long jobs = static_cast<long long>(p.B) * p.H * p.n_qp;
+  LTXB_CHECK_SUPPORTED(jobs < (1ll << 30), "ltxb_attention_fwd: too many (batch, head, query tile) jobs");
+  // ragged last wave -> split its jobs over the keys so that one CTA per SM finishes it in 1/n_split of a wave
+  static const bool split_on = [] { const char* e = getenv("LTXB_ATTN_SPLIT"); return e == nullptr || atoi(e) != 0; }();
+  int dev = 0;
+  LTXB_CUDA(cudaGetDevice(&dev));
+  const int n_left = static_cast<int>(jobs % sms);
+  int n_split = 1;
+  if (split_on && n_left > 0 && dev < kMaxDevices && g_attn_ws[dev].base != nullptr) {
+    n_split = std::min(n_kv, sms / n_left);
+    if (n_split * n_left > kMaxSlots || attn_ws_bytes_for(n_split * n_left, kDh) > g_attn_ws[dev].bytes) n_split = 1;
+  }
+  if (n_split > 1) {
+    p.n_full = static_cast<int>(jobs - n_left);
+    p.n_split = n_split;
+    p.ws_o = g_attn_ws[dev].base;
+    p.ws_ml = p.ws_o + static_cast<long long>(n_split) * n_left * 256 * kDh;
+  } else {
+    p.n_full = static_cast<int>(jobs);
+    p.n_split = 1;
+#ifdef LTXB_ATTN_TRACE
+    if (dev < kMaxDevices) p.ws_o = g_attn_ws[dev].base;
+#endif
+  }
+  CUtensorMap tq, tk, tv;
+  const uint32_t box[3] = {64, 128, 1};
+  auto enc = [&](CUtensorMap* m, const void* base, long long ld, int T) {
+    const uint64_t dims[3] = {static_cast<uint64_t>(p.H) * kDh, static_cast<uint64_t>(T), static_cast<uint64_t>(p.B)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * static_cast<uint64_t>(T)};
+    return encode_tmap_bf16(m, base, 3, dims, strides, box);
+  };
+  int rc;
+  if ((rc = enc(&tq, Q, ldq, p.Tq))) return rc;
+  if ((rc = enc(&tk, K, ldk, p.Tk))) return rc;
+  if ((rc = enc(&tv, V, ldv, p.Tk))) return rc;
+  const int grid = p.n_full + (n_split > 1 ? n_left * n_split : 0);
+  LTXB_CUDA(launch_kernel(kernel, dim3(grid), dim3(kPairThreads), smem, stream, 1, tq, tk, tv, p));
+  if (n_split > 1)
+    LTXB_CUDA(launch_kernel(attention_combine_kernel<kDh>, dim3(n_left * 256 / 8), dim3(256), 0, stream, 1, p, n_left));
+  return LTXB_OK;
+}
+
+int launch_attention_pair(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+                          AttnParams p, int dh, cudaStream_t stream) {
+  if (dh == 128) return launch_pair<128>(Q, ldq, K, ldk, V, ldv, p, stream);
+  return launch_pair<64>(Q, ldq, K, ldk, V, ldv, p, stream);
+}
+
+}  // namespace ltxb
+
+using namespace ltxb;
+
+extern "C" int64_t ltxb_attention_workspace_bytes(void) { return attn_ws_bytes_for(kMaxSlots, 128); }
+
+extern "C" int ltxb_attention_set_workspace(void* workspace, int64_t bytes) {
+  int dev = 0;
+  LTXB_CUDA(cudaGetDevice(&dev));
+  LTXB_CHECK_SUPPORTED(dev >= 0 && dev < kMaxDevices, "ltxb_attention_set_workspace: device %d out of range", dev);
+  if (workspace == nullptr) {
+    g_attn_ws[dev] = AttnWorkspace{};
+    return LTXB_OK;
+  }
+  LTXB_CHECK_ARG(aligned16(workspace) && bytes > 0, "ltxb_attention_set_workspace: need a 16-byte aligned, non-empty buffer");
+  g_attn_ws[dev].base = reinterpret_cast<float*>(workspace);
+  g_attn_ws[dev].bytes = bytes;
+  return LTXB_OK;
+}

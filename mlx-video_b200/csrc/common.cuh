@@ -3,6 +3,7 @@
 // library loads on a box without a GPU driver).
 #pragma once
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -44,6 +45,7 @@ int num_sms();
 // Launch with programmatic stream serialization (PDL) so the kernel may begin while its predecessor in the
 // stream drains; all kernels of this library call pdl_wait() before touching global memory.  LTXB_PDL=0 disables.
 bool pdl_enabled();
+extern std::atomic<long long> g_kernel_launches;  // every kernel this library has launched (ltxb_kernel_launches)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                  int cluster_x, Args&&... args) {
@@ -68,6 +70,7 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   }
   cfg.attrs = attr;
   cfg.numAttrs = n;
+  g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

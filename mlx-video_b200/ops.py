@@ -14,7 +14,7 @@ from ._lib import Epilogue, check, lib
 _device_set: set = set()
 
 
-launches = 0          # kernels launched through this module since import (bench.py reports the delta)
+launches = 0          # kernels launched by the library since import (refreshed after every call; bench.py reports the delta)
 _profile = None       # optional list: when set, every launch is bracketed by CUDA events -> (name, flops_or_bytes, start, end)
 
 
@@ -28,15 +28,17 @@ def profile(enable: bool):
 def _call(name: str, work: float, *args) -> None:
     """One C-ABI call == one kernel launch on torch's current stream."""
     global launches
-    launches += 1
     fn = getattr(lib, name)
     if _profile is None:
-        check(fn(*args), name)
+        rc = fn(*args)
+        launches = lib.ltxb_kernel_launches()
+        check(rc, name)
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     rc = fn(*args)
     e1.record()
+    launches = lib.ltxb_kernel_launches()
     check(rc, name)
     _profile.append((name, work, e0, e1))
 
@@ -45,6 +47,7 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_attn_workspaces: dict = {}  # device index -> key-split scratch of the attention kernel (ragged last wave)
 _gemm_workspaces: dict = {}  # device index -> the stream-K scratch buffer registered with the library
 
 
@@ -62,6 +65,10 @@ def _prep(t: torch.Tensor) -> None:
             ws = torch.empty(lib.ltxb_gemm_workspace_bytes(), dtype=torch.uint8, device=t.device)
             check(lib.ltxb_gemm_set_workspace(ws.data_ptr(), ws.numel(), _stream()), "ltxb_gemm_set_workspace")
             _gemm_workspaces[idx] = ws
+        if idx not in _attn_workspaces:
+            ws = torch.empty(lib.ltxb_attention_workspace_bytes(), dtype=torch.uint8, device=t.device)
+            check(lib.ltxb_attention_set_workspace(ws.data_ptr(), ws.numel()), "ltxb_attention_set_workspace")
+            _attn_workspaces[idx] = ws
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:

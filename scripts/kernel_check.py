@@ -5,6 +5,7 @@ a failed check.  Groups are run in separate processes (a trapped kernel poisons 
 """
 import json
 import math
+import os
 import sys
 import time
 
@@ -163,6 +164,11 @@ def attn_case(B, Tq, Tk, H, dh, kind="rand", use_bias=False, seed=0):
         k = torch.zeros_like(k)
     if kind == "onehot":  # huge logits on one key -> O = V[that key]: isolates Q.K^T + indexing
         q = q * 8
+    if kind == "drift":  # logits grow with the key index: the running maximum moves in every tile (O rescale path)
+        u = torch.randn(1, D, device=dev, generator=g)
+        ramp = (torch.arange(Tk, device=dev).float() / Tk).repeat(B)[:, None]
+        q = (u + 0.1 * q.float()).bfloat16()
+        k = (u * ramp * 6.0 + 0.1 * k.float()).bfloat16()
     bias = None
     if use_bias:
         bias = torch.where(torch.rand(B, Tk, device=dev, generator=g) < 0.3, -1e9, 0.0).float().contiguous()
@@ -184,8 +190,17 @@ def group_attn_correct():
     attn_case(1, 128, 128, 1, 128, "onehot")
     attn_case(1, 256, 384, 2, 128, "rand")
     attn_case(2, 200, 72, 3, 128, "rand")
+    attn_case(1, 256, 128, 1, 128, "uniform")
+    attn_case(1, 256, 256, 1, 128, "onehot")
+    attn_case(1, 384, 512, 2, 128, "rand")
     attn_case(1, 1280, 1280, 32, 128, "rand")
+    attn_case(1, 1280, 1280, 32, 128, "drift")
+    attn_case(1, 640, 1024, 2, 128, "drift")
+    attn_case(1, 1280, 1024, 32, 128, "rand")
+    attn_case(2, 5184, 5184, 4, 128, "rand")
     attn_case(2, 320, 1024, 4, 128, "rand", use_bias=True)
+    attn_case(1, 5184, 68, 32, 64, "rand")
+    attn_case(1, 1000, 1000, 5, 64, "drift")
     attn_case(1, 128, 128, 1, 64, "uniform")
     attn_case(1, 128, 128, 2, 64, "rand")
     attn_case(1, 300, 68, 32, 64, "rand")
@@ -193,8 +208,9 @@ def group_attn_correct():
 
 
 def group_attn_perf():
-    for (B, T, Tk, H, dh) in [(1, 1280, 1280, 32, 128), (1, 5184, 5184, 32, 128), (1, 1280, 1024, 32, 128),
-                              (1, 5184, 1024, 32, 128), (1, 14080, 14080, 32, 128)]:
+    for (B, T, Tk, H, dh) in [(1, 1280, 1280, 32, 128), (1, 1280, 1024, 32, 128), (2, 5184, 5184, 32, 128),
+                              (2, 5184, 1024, 32, 128), (1, 14080, 14080, 32, 128), (1, 5184, 68, 32, 64),
+                              (1, 1280, 1280, 4, 128)]:
         D = H * dh
         q = torch.randn(B * T, D, device=dev).bfloat16()
         k = torch.randn(B * Tk, D, device=dev).bfloat16()
@@ -202,10 +218,12 @@ def group_attn_perf():
         out = torch.empty(B * T, D, device=dev, dtype=torch.bfloat16)
         fl = 4.0 * B * H * T * Tk * dh
         med, best = time_fn(lambda: ops.attention(q, k, v, out, B, T, Tk, H, dh, 1 / math.sqrt(dh)), iters=10)
-        emit(perf="ltxb_attn", T=T, Tk=Tk, ms=med, tflops=fl / med / 1e9)
+        emit(perf="ltxb_attn", B=B, T=T, Tk=Tk, H=H, dh=dh, us=round(med * 1e3, 1), tflops=round(fl / med / 1e9))
+        if os.environ.get("LTXB_SKIP_SDPA"):
+            continue
         q4, k4, v4 = (t.reshape(B, -1, H, dh).transpose(1, 2) for t in (q, k, v))
         med, best = time_fn(lambda: torch.nn.functional.scaled_dot_product_attention(q4, k4, v4), iters=10)
-        emit(perf="torch_sdpa", T=T, Tk=Tk, ms=med, tflops=fl / med / 1e9)
+        emit(perf="torch_sdpa", B=B, T=T, Tk=Tk, H=H, dh=dh, us=round(med * 1e3, 1), tflops=round(fl / med / 1e9))
 
 
 def group_elementwise():
