@@ -371,6 +371,12 @@ def main() -> int:
         t["ms"] += a.elapsed_time(bb)
         t["work"] += work
     prof_total = sum(t["ms"] for t in table.values())
+    shapes = {}  # GEMM launches grouped by their FLOP count (= by problem shape), for --kernel-table
+    for name, work, a, bb in prof:
+        if name == "ltxb_gemm_bf16":
+            t = shapes.setdefault(work, [0, 0.0])
+            t[0] += 1
+            t[1] += a.elapsed_time(bb)
 
     # ---------------- reduce over ranks (max time)
     times = torch.tensor([ms_total, e2e_ms, e2e_wall_ms], device=dev, dtype=torch.float64)
@@ -421,6 +427,8 @@ def main() -> int:
         if args.kernel_table:
             for k, v in line["kernels"].items():
                 print(f"{k:28s} {v['launches']:5d} launches {v['ms']:9.3f} ms {100 * v['share']:5.1f}%", file=sys.stderr)
+            for work, (n, ms) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
+                print(f"  gemm {work / 1e9:9.1f} GFLOP x {n:3d}: {ms / n * 1e3:8.1f} us each, {work * n / ms / 1e9:7.0f} TFLOP/s, {ms:7.3f} ms", file=sys.stderr)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

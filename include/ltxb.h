@@ -137,6 +137,14 @@ int ltxb_gate_residual(float* x, int64_t ldx, const void* y, int64_t ldy, int32_
 int ltxb_qknorm_rope(void* x, int64_t ldx, int32_t B, int32_t T, int32_t H, int32_t dh, const float* weight,
                      float eps, const float* cos_tab, const float* sin_tab, int32_t B_pe, void* stream);
 
+/* The same over n_seg independent column slices of one buffer in ONE launch: slice s is x + s*seg_stride (columns)
+ * with norm weight `weight + s*w_seg_stride` — q and k of the fused QKV buffer (n_seg = 2, attention.py:129-136), or
+ * the text keys of all 48 blocks in the stacked K/V buffer (n_seg = 48, no rotation).  weight2 (optional, same
+ * striding) is a second per-column factor multiplied in after the norm. */
+int ltxb_qknorm_rope_segments(void* x, int64_t ldx, int32_t n_seg, int64_t seg_stride, int32_t B, int32_t T, int32_t H,
+                              int32_t dh, const float* weight, int64_t w_seg_stride, const float* weight2, float eps,
+                              const float* cos_tab, const float* sin_tab, int32_t B_pe, void* stream);
+
 /* Same operation writing to a SEPARATE, head-grouped destination — the send buffer of the Ulysses
  * head-scatter all-to-all (new: the reference is single-device).  Head h of row r goes to
  *   out + (h / heads_per_group) * group_stride + r * ldo + (h % heads_per_group) * dh

@@ -53,6 +53,7 @@ SIGNATURES = {
     "ltxb_layernorm_modulate": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp, _i64, _vp, _vp, _i32, _vp, _vp]),
     "ltxb_gate_residual": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _i32, _vp, _i32, _vp, _vp]),
     "ltxb_qknorm_rope": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _i32, _vp]),
+    "ltxb_qknorm_rope_segments": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _f32, _vp, _vp, _i32, _vp]),
     "ltxb_qknorm_rope_scatter": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _i32, _vp]),
     "ltxb_qknorm_rope_scatter_peers": (C.c_int, [_vp, _i64, C.POINTER(_vp), _i32, _i64, _i32, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _i32, _vp]),
     "ltxb_peer_barrier": (C.c_int, [C.POINTER(_vp), _i32, _i32, _vp, _vp]),

@@ -229,11 +229,18 @@ __global__ void __launch_bounds__(128, kPer <= 2 ? 9 : 1)  // <= 56 registers: 9
 qknorm_rope_kernel(const __nv_bfloat16* x, long long ldx, __nv_bfloat16* out, long long ldo,  // may alias (in place)
                    int heads_per_group, long long group_stride, const PeerBases peers, int T, int H, int dh,
                    const float* __restrict__ weight,
-                   float eps, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, int B_pe) {
+                   float eps, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, int B_pe,
+                   long long seg_x_stride, long long seg_w_stride, const float* __restrict__ weight2) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[32];
   const long long row = blockIdx.x;
+  // segment blockIdx.y: an independent [rows, H*dh] column slice of the same buffer with its own norm weight
+  // (q and k of the fused QKV buffer; the text K of every block in the stacked K/V buffer)
+  x += blockIdx.y * seg_x_stride;
+  if (out != nullptr) out += blockIdx.y * seg_x_stride;
+  if (weight != nullptr) weight += blockIdx.y * seg_w_stride;
+  if (weight2 != nullptr) weight2 += blockIdx.y * seg_w_stride;
   const int half = dh / 2;
   const int tph = half / 8;  // work items per head: one item = 8 elements of each half of a head
   const int items = H * tph;
@@ -267,6 +274,13 @@ qknorm_rope_kernel(const __nv_bfloat16* x, long long ldx, __nv_bfloat16* out, lo
       float w1[8], w2[8];
       load8_ldg(weight + h * dh + off, w1);
       load8_ldg(weight + h * dh + half + off, w2);
+      if (weight2 != nullptr) {  // a second per-column factor folded in (the partner's norm weight)
+        float u1[8], u2[8];
+        load8_ldg(weight2 + h * dh + off, u1);
+        load8_ldg(weight2 + h * dh + half + off, u2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w1[i] *= u1[i], w2[i] *= u2[i];
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[j][i] *= rstd * w1[i], b[j][i] *= rstd * w2[i];
       if (cos_tab != nullptr) {
@@ -601,7 +615,8 @@ extern "C" int ltxb_gate_residual(float* x, int64_t ldx, const void* y, int64_t 
 static int qknorm_rope_launch(const void* x, int64_t ldx, void* out, const PeerBases& peers, int64_t ldo,
                               int32_t heads_per_group, int64_t group_stride, int32_t B, int32_t T, int32_t H, int32_t dh,
                               const float* weight, float eps, const float* cos_tab, const float* sin_tab, int32_t B_pe,
-                              void* stream);
+                              void* stream, int32_t n_seg = 1, int64_t seg_x_stride = 0, int64_t seg_w_stride = 0,
+                              const float* weight2 = nullptr);
 
 extern "C" int ltxb_qknorm_rope_scatter(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t heads_per_group,
                                         int64_t group_stride, int32_t B, int32_t T, int32_t H, int32_t dh,
@@ -629,8 +644,10 @@ extern "C" int ltxb_qknorm_rope_scatter_peers(const void* x, int64_t ldx, void* 
 static int qknorm_rope_launch(const void* x, int64_t ldx, void* out, const PeerBases& peers, int64_t ldo,
                               int32_t heads_per_group, int64_t group_stride, int32_t B, int32_t T, int32_t H, int32_t dh,
                               const float* weight, float eps, const float* cos_tab, const float* sin_tab, int32_t B_pe,
-                              void* stream) {
+                              void* stream, int32_t n_seg, int64_t seg_x_stride, int64_t seg_w_stride, const float* weight2) {
   LTXB_CHECK_ARG(x, "ltxb_qknorm_rope: null pointer");
+  LTXB_CHECK_ARG(n_seg >= 1 && n_seg <= 65535 && seg_x_stride % 8 == 0 && seg_w_stride % 4 == 0 && (weight2 == nullptr || aligned16(weight2)),
+                 "ltxb_qknorm_rope: bad segments n=%d", n_seg);
   if (B == 0 || T == 0) return LTXB_OK;
   LTXB_CHECK_ARG(B > 0 && T > 0 && H > 0, "ltxb_qknorm_rope: bad shape B=%d T=%d H=%d", B, T, H);
   LTXB_CHECK_SUPPORTED(dh == 64 || dh == 128, "ltxb_qknorm_rope: head dim %d not in {64,128}", dh);
@@ -649,8 +666,8 @@ static int qknorm_rope_launch(const void* x, int64_t ldx, void* out, const PeerB
   const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* oi = reinterpret_cast<__nv_bfloat16*>(out);
 #define LTXB_LAUNCH_QK(P)                                                                                             \
-  LTXB_CUDA(launch_kernel(qknorm_rope_kernel<P>, dim3(B * T), dim3(nthr), 0, st, 1, xi, ldx, oi, ldo, heads_per_group, \
-                          group_stride, peers, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe))
+  LTXB_CUDA(launch_kernel(qknorm_rope_kernel<P>, dim3(B * T, n_seg), dim3(nthr), 0, st, 1, xi, ldx, oi, ldo, heads_per_group, \
+                          group_stride, peers, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe, seg_x_stride, seg_w_stride, weight2))
   if (per == 1) LTXB_LAUNCH_QK(1);
   else if (per == 2) LTXB_LAUNCH_QK(2);
   else if (per == 4) LTXB_LAUNCH_QK(4);
@@ -665,6 +682,15 @@ extern "C" int ltxb_qknorm_rope(void* x, int64_t ldx, int32_t B, int32_t T, int3
                                 int32_t B_pe, void* stream) {
   LTXB_CHECK_ARG(weight, "ltxb_qknorm_rope: null weight");
   return ltxb_qknorm_rope_scatter(x, ldx, x, ldx, H, 0, B, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe, stream);
+}
+
+extern "C" int ltxb_qknorm_rope_segments(void* x, int64_t ldx, int32_t n_seg, int64_t seg_stride, int32_t B, int32_t T,
+                                         int32_t H, int32_t dh, const float* weight, int64_t w_seg_stride,
+                                         const float* weight2, float eps, const float* cos_tab, const float* sin_tab,
+                                         int32_t B_pe, void* stream) {
+  LTXB_CHECK_ARG(weight, "ltxb_qknorm_rope_segments: null weight");
+  return qknorm_rope_launch(x, ldx, x, PeerBases{}, ldx, H, 0, B, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe, stream, n_seg,
+                            seg_stride, w_seg_stride, weight2);
 }
 
 extern "C" int ltxb_timestep_embed(const float* t, int32_t n, float scale, int32_t dim, void* out, int64_t ldo,

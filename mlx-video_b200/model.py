@@ -12,6 +12,7 @@ supplies device memory and the stream.  There is no CPU path: CPU tensors raise 
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import replace
 from pathlib import Path
 from typing import Dict, Iterator, List, Optional, Tuple, Union
@@ -167,6 +168,40 @@ class LTXModel:
             i: BasicAVTransformerBlock(idx=i, video=vcfg, audio=acfg, rope_type=config.rope_type, norm_eps=config.norm_eps, device=dev)
             for i in range(config.num_layers)
         }
+        # memory layout for the hoisted text K/V projection: every block's attn2 to_k|to_v weight in ONE
+        # (L*2*inner, context_dim) matrix, k_norm weights in one (L, inner) table; the blocks hold views
+        self._text_kv = {}
+        stack = os.environ.get("LTXB_STACK_TEXT_KV", "1") != "0"  # 0: per-block K/V GEMMs (A/B runs)
+        if stack and config.model_type.is_video_enabled():
+            self._stack_text_kv("", "attn2")
+        if stack and config.model_type.is_audio_enabled():
+            self._stack_text_kv("audio_", "audio_attn2")
+
+    def _stack_text_kv(self, pre: str, name: str) -> None:
+        blocks = [getattr(b, name) for b in self.transformer_blocks.values()]
+        L, inner, cdim = len(blocks), blocks[0].inner_dim, blocks[0].context_dim
+        w = torch.zeros(L * 2 * inner, cdim, dtype=BF16, device=self.device)
+        b = torch.zeros(L * 2 * inner, dtype=F32, device=self.device)
+        kn = torch.ones(L, inner, dtype=F32, device=self.device)
+        for l, att in enumerate(blocks):
+            r = slice(l * 2 * inner, (l + 1) * 2 * inner)
+            att.kv_weight, att.kv_bias = w[r], b[r]
+            att.to_k = Linear(att.kv_weight[:inner], att.kv_bias[:inner])
+            att.to_v = Linear(att.kv_weight[inner:], att.kv_bias[inner:])
+            att.k_norm.weight = kn[l]
+        self._text_kv[pre] = (w, b, kn, blocks[0].heads, blocks[0].dim_head, blocks[0].k_norm.eps)
+
+    def _project_text_kv(self, pre: str, ctx: Tensor, cache: Optional[ContextCache]) -> Tensor:
+        """K|V of the text cross-attention of every block (attention.py:124-130 for attn2 of all 48 blocks): the
+        context is the same for all of them, so it is one (B*Tc, D) x (D, L*2*inner) GEMM and one norm launch."""
+        w, b, kn, H, dh, eps = self._text_kv[pre]
+        Bc, Tc = ctx.shape[0], ctx.shape[1]
+        shape = (Bc * Tc, w.shape[0])
+        kv = self.workspace.get(pre + "text_kv", shape, BF16, self.device) if cache is None else cache.stacked(shape, self.device)
+        if cache is None or not cache.valid:
+            ops.gemm(ctx.reshape(Bc * Tc, -1), w, b, kv)
+            ops.qknorm_rope_segments(kv, kn.shape[0], 2 * H * dh, Bc, Tc, H, dh, kn, eps)
+        return kv
 
     # ------------------------------------------------------------------ parameters
     def named_parameters(self) -> Iterator[Tuple[str, Tensor]]:
@@ -287,6 +322,7 @@ class LTXModel:
             ctx = cache.context_buffer((m.context.shape[0], m.context.shape[1], inner), self.device)
             if not cache.valid:
                 proj.linear2(proj.linear1(_as_bf16(m.context), mode=_lib.EPI_GELU_BF16), out=ctx)
+        text_kv = self._project_text_kv(pre, ctx, cache) if pre in self._text_kv else None
         mask = _kv_bias(m.context_mask, B, ctx.shape[1])
         pe = m.positional_embeddings
         if pe is None:
@@ -294,7 +330,7 @@ class LTXModel:
                                       self.use_middle_indices_grid, heads, self.rope_type, c.double_precision_rope)
         args = TransformerArgs(x=x, context=ctx, context_mask=mask, timesteps=mod.view(rb, rt, -1),
                                embedded_timestep=emb.view(rb, rt, -1), positional_embeddings=pe, enabled=m.enabled,
-                               timestep_index=index, context_cache=cache)
+                               timestep_index=index, context_cache=cache, text_kv=text_kv)
         if self._av:  # ltx.py:201-247
             cross_pe = precompute_freqs_cis(m.positions[:, 0:1].to(self.device), self.audio_cross_attention_dim,
                                             self.positional_embedding_theta, [self.cross_pe_max_pos], True, heads,

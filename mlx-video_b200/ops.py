@@ -332,6 +332,27 @@ def timestep_groups(t: torch.Tensor, cap: int):
     return values, index, count
 
 
+def qknorm_rope_segments(x: torch.Tensor, n_seg: int, seg_stride: int, B: int, T: int, H: int, dh: int, weight: torch.Tensor,
+                         eps: float, cos: Optional[torch.Tensor] = None, sin: Optional[torch.Tensor] = None,
+                         weight2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ONE launch over ``n_seg`` column slices x[:, s*seg_stride : s*seg_stride + H*dh] of a bf16 buffer, slice s
+    normalised with ``weight[s]`` (f32 [n_seg, H*dh], optionally times ``weight2[s]``) and rotated in place."""
+    _prep(x)
+    assert x.dtype == torch.bfloat16 and weight.dtype == torch.float32 and weight.is_contiguous()
+    assert tuple(weight.shape) == (n_seg, H * dh), f"segment weights {tuple(weight.shape)} vs ({n_seg}, {H * dh})"
+    assert (n_seg - 1) * seg_stride + H * dh <= x.shape[-1]
+    if weight2 is not None:
+        assert weight2.dtype == torch.float32 and weight2.is_contiguous() and weight2.shape == weight.shape
+    b_pe = 1
+    if cos is not None:
+        assert cos.dtype == torch.float32 and sin.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous()
+        assert cos.shape[1:] == (H, T, dh // 2), f"rope table {tuple(cos.shape)} vs (B,{H},{T},{dh // 2})"
+        b_pe = cos.shape[0]
+    _call("ltxb_qknorm_rope_segments", 0.0, x.data_ptr(), _ld(x), n_seg, seg_stride, B, T, H, dh, weight.data_ptr(), H * dh,
+          _ptr(weight2), eps, _ptr(cos), _ptr(sin), b_pe, _stream())
+    return x
+
+
 def qknorm_rope_scatter(x: torch.Tensor, out: torch.Tensor, slot: int, slots: int, groups: int, B: int, T: int, H: int,
                         dh: int, weight: Optional[torch.Tensor], eps: float, cos: Optional[torch.Tensor] = None,
                         sin: Optional[torch.Tensor] = None) -> torch.Tensor:

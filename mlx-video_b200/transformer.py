@@ -65,6 +65,9 @@ class TransformerArgs:
     enabled: bool = True
     timestep_index: Optional[Tensor] = None
     context_cache: Optional["ContextCache"] = None  # opt-in reuse of the text K/V across denoise steps
+    # text-cross-attention K|V of ALL blocks, k-norm applied: bf16 (B*Tc, L*2*inner), block l at columns
+    # [l*2*inner, (l+1)*2*inner) — one GEMM + one norm launch at the head of the forward (model.py) instead of 48 + 48
+    text_kv: Optional[Tensor] = None
 
 
 class ContextCache:
@@ -76,7 +79,7 @@ class ContextCache:
     def __init__(self) -> None:
         self.key = None
         self.context: Optional[Tensor] = None  # projected caption, bf16 (B, Tc, D)
-        self.kv: Dict[int, Tensor] = {}
+        self.kv: Dict[object, Tensor] = {}
         self.valid = False
 
     def retarget(self, key) -> None:
@@ -87,6 +90,14 @@ class ContextCache:
         if self.context is None or tuple(self.context.shape) != tuple(shape):
             self.context, self.valid = torch.empty(shape, dtype=BF16, device=device), False
         return self.context
+
+    def stacked(self, shape, device) -> Tensor:
+        """K|V of all blocks in one buffer (TransformerArgs.text_kv)."""
+        t = self.kv.get("all")
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = self.kv["all"] = torch.empty(shape, dtype=BF16, device=device)
+            self.valid = False
+        return t
 
     def entry(self, block_idx: int, shape, device) -> Tensor:
         t = self.kv.get(block_idx)
@@ -180,8 +191,10 @@ class Attention:
             self.kv_bias = torch.zeros(2 * inner, dtype=F32, **kw)
             self.to_k = Linear(self.kv_weight[:inner], self.kv_bias[:inner])
             self.to_v = Linear(self.kv_weight[inner:], self.kv_bias[inner:])
-        self.q_norm = RMSNormWeight(torch.ones(inner, dtype=F32, **kw), norm_eps)
-        self.k_norm = RMSNormWeight(torch.ones(inner, dtype=F32, **kw), norm_eps)
+        # q_norm | k_norm weights stored back to back: self-attention normalises and rotates q and k in ONE launch
+        self.qk_norm_weight = torch.ones(2, inner, dtype=F32, **kw)
+        self.q_norm = RMSNormWeight(self.qk_norm_weight[0], norm_eps)
+        self.k_norm = RMSNormWeight(self.qk_norm_weight[1], norm_eps)
         self.to_out = Linear(torch.zeros(query_dim, inner, dtype=BF16, **kw), torch.zeros(query_dim, dtype=F32, **kw))
 
     # -- the pieces, exposed separately so the sequence-parallel path can put its all-to-all between them
@@ -210,7 +223,10 @@ class Attention:
                     ops.gemm(context, self.kv_weight, self.kv_bias, kv)
             k, v = kv[:, :inner], kv[:, inner:]
         H, dh = self.heads, self.dim_head
-        if pe is not None:
+        if context is None and k_pe is None and self.k_norm.weight.data_ptr() == self.qk_norm_weight[1].data_ptr():
+            cs = (None, None) if pe is None else pe
+            ops.qknorm_rope_segments(qkv, 2, inner, B, Tq, H, dh, self.qk_norm_weight, self.q_norm.eps, cs[0], cs[1])
+        elif pe is not None:
             kp = pe if k_pe is None else k_pe
             ops.qknorm_rope(q, B, Tq, H, dh, self.q_norm.weight, self.q_norm.eps, pe[0], pe[1])
             if not kv_ready:
@@ -353,9 +369,14 @@ class BasicAVTransformerBlock:
         ops.rmsnorm_modulate(x2, nx, self.norm_eps)
         Tc = a.context.shape[1]
         cache = a.context_cache
-        kv_out = None if cache is None else cache.entry(self.idx, (a.context.shape[0] * Tc, 2 * attn2.inner_dim), x2.device)
+        if a.text_kv is not None:
+            w = 2 * attn2.inner_dim
+            kv_out, kv_ready = a.text_kv[:, self.idx * w:(self.idx + 1) * w], True
+        else:
+            kv_out = None if cache is None else cache.entry(self.idx, (a.context.shape[0] * Tc, 2 * attn2.inner_dim), x2.device)
+            kv_ready = cache is not None and cache.valid
         attn2.fused(ws, tag + ".attn2", nx, B, T, x2, context=a.context.reshape(-1, a.context.shape[-1]), Tk=Tc,
-                    kv_bias=a.context_mask, kv_out=kv_out, kv_ready=cache is not None and cache.valid)
+                    kv_bias=a.context_mask, kv_out=kv_out, kv_ready=kv_ready)
 
     def _ff(self, ws, tag, a: TransformerArgs, ff: FeedForward, table: Tensor) -> None:
         """x += ff(rms(x)(1+scale)+shift) * gate   (transformer.py:342-355)"""

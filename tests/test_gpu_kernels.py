@@ -158,6 +158,20 @@ def test_qknorm_rope_and_small_kernels():
         rot = torch.stack([a_ * cos - b_ * sin, b_ * cos + a_ * sin], dim=-2).permute(0, 2, 1, 3, 4).reshape(B * T, D)
         assert rel_l2(x.float(), rot) <= 4e-3
         assert torch.equal(qkv[:, :D].float(), qkv[:, :D].float()) and torch.isfinite(qkv.float()).all()
+    # segments: several column slices of one buffer, each with its own weight, in one launch == one call per slice
+    for B, T, H, dh, n_seg, stride, rope in [(1, 320, 32, 128, 2, 4096, True), (2, 40, 4, 64, 5, 512, False)]:
+        D = H * dh
+        buf = torch.randn(B * T, n_seg * stride + 64, device=DEV, generator=g).bfloat16()
+        ref = buf.clone()
+        wgt = 1 + 0.1 * torch.randn(n_seg, D, device=DEV, generator=g)
+        w2 = None if rope else 1 + 0.1 * torch.randn(n_seg, D, device=DEV, generator=g)
+        ang = torch.rand(B, H, T, dh // 2, device=DEV, generator=g) * 6.28
+        cs = (torch.cos(ang), torch.sin(ang)) if rope else (None, None)
+        ops.qknorm_rope_segments(buf, n_seg, stride, B, T, H, dh, wgt, 1e-6, cs[0], cs[1], weight2=w2)
+        for s_ in range(n_seg):
+            sl = ref[:, s_ * stride:s_ * stride + D]
+            ops.qknorm_rope(sl, B, T, H, dh, wgt[s_] if w2 is None else (wgt[s_] * w2[s_]).contiguous(), 1e-6, cs[0], cs[1])
+        assert rel_l2(buf.float(), ref.float()) <= (0.0 if w2 is None else 4e-3)
     t = torch.tensor([0.0, 0.05, 0.421875, 0.725, 1.0], device=DEV)
     feat = torch.empty(5, 256, device=DEV, dtype=torch.bfloat16)
     ops.timestep_embed(t, 1000.0, 256, feat)
