@@ -415,24 +415,37 @@ __global__ void __launch_bounds__(256) attention_combine_kernel(const AttnParams
   if (row >= p.Tq) return;
   const int b = bh / p.H, h = bh - b * p.H;
   const long long prow0 = static_cast<long long>(jl) * p.n_split * 256 + rr;
+  // (m_i, l_i) of the pieces: lanes take pieces in parallel, so the loads are one round trip instead of n_split
   float M = -INFINITY;
-  for (int i = 0; i < p.n_split; ++i) M = fmaxf(M, p.ws_ml[(prow0 + i * 256ll) * 2]);
+  for (int i = lane; i < p.n_split; i += 32) M = fmaxf(M, __ldcg(p.ws_ml + (prow0 + i * 256ll) * 2));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
   float acc[kPer];
 #pragma unroll
   for (int u = 0; u < kPer; ++u) acc[u] = 0.f;
   float L = 0.f;
-  for (int i = 0; i < p.n_split; ++i) {
-    const long long pr = prow0 + i * 256ll;
-    const float2 ml = *reinterpret_cast<const float2*>(p.ws_ml + pr * 2);
-    const float w = (ml.x == -INFINITY) ? 0.f : fast_exp2(ml.x - M);
-    L += w * ml.y;
-    const float* src = p.ws_o + pr * kDh + lane * kPer;
-    if constexpr (kPer == 4) {
-      const float4 v = *reinterpret_cast<const float4*>(src);
-      acc[0] += w * v.x, acc[1] += w * v.y, acc[2] += w * v.z, acc[3] += w * v.w;
-    } else {
-      const float2 v = *reinterpret_cast<const float2*>(src);
-      acc[0] += w * v.x, acc[1] += w * v.y;
+  for (int i0 = 0; i0 < p.n_split; i0 += 32) {
+    float w_mine = 0.f, wl_mine = 0.f;
+    if (i0 + lane < p.n_split) {
+      const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.ws_ml + (prow0 + (i0 + lane) * 256ll) * 2));
+      w_mine = (ml.x == -INFINITY) ? 0.f : fast_exp2(ml.x - M);
+      wl_mine = w_mine * ml.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wl_mine += __shfl_xor_sync(0xffffffffu, wl_mine, o);
+    L += wl_mine;
+    const int n = min(32, p.n_split - i0);
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {  // independent loads: the unrolled copies are in flight together
+      const float w = __shfl_sync(0xffffffffu, w_mine, i);
+      const float* src = p.ws_o + (prow0 + (i0 + i) * 256ll) * kDh + lane * kPer;
+      if constexpr (kPer == 4) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(src));
+        acc[0] += w * v.x, acc[1] += w * v.y, acc[2] += w * v.z, acc[3] += w * v.w;
+      } else {
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(src));
+        acc[0] += w * v.x, acc[1] += w * v.y;
+      }
     }
   }
   const float inv = (L > 0.f) ? 1.0f / L : 0.f;

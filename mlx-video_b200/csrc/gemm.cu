@@ -8,7 +8,7 @@
 //   * persistent kernel, one CTA (or one CTA pair, cta_group::2) per SM (pair), static tile striding,
 //     M-fastest tile order so concurrently resident tiles share the same W panels in L2;
 //   * warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+TMEM alloc),
-//     warps 2..5 = epilogue (TMEM -> registers -> global);
+//     warps 4..11 = epilogue (TMEM -> registers -> global), two per TMEM lane quarter;
 //   * smem ring of `num_stages` {A 128x64, W (BN/ctas)x64} bf16 tiles, 128-byte swizzle, filled by
 //     cp.async.bulk.tensor, consumed by tcgen05.mma straight from smem descriptors;
 //   * two TMEM accumulators (2 x BN fp32 columns) so the epilogue of tile i overlaps the main loop of
@@ -28,7 +28,11 @@ constexpr int kBlockM = 128;  // rows of the output tile owned by ONE CTA (TMEM 
 constexpr int kBlockK = 64;   // 64 bf16 = 128 B = one swizzle span
 constexpr int kUmmaK = 16;
 constexpr int kMaxStages = 8;
-constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kGemmThreads = 384;  // warp 0 TMA, warp 1 MMA, warps 2,3 idle, warps 4..11 epilogue (two per TMEM lane quarter)
+// 10 warps would cap every thread at 168 registers (3 warps on one scheduler) and the residual epilogue spilled;
+// with three full warpgroups the epilogue warps take what the producer / issuer warpgroup does not need
+// (setmaxnreg): 128 * 104 + 256 * 200 <= 64 K
+constexpr int kRegsIssue = 104, kRegsEpilogue = 200;
 constexpr int kEpiThreads = 256;
 constexpr int kSmemHeader = 1024;  // barriers + tmem pointer live in front of the tile ring
 constexpr int kTmemCols = 512;
@@ -152,12 +156,18 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, const uint32
   } else {  // LTXB_EPI_RESID_GATE_F32
     const float4* r4 = reinterpret_cast<const float4*>(p.resid + row * p.ldr + col);
     float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col);
+    // `out` normally IS `resid` (the residual stream is updated in place), so the compiler may not move a residual
+    // load above an earlier store: read the whole chunk first, or the chunk becomes kCols/4 serialised L2 round trips
+    // (measured: 79.8 -> 61.4 us for M=1280 N=4096 K=4096 together with the register re-balancing below)
+    float4 rr[kCols / 4];
+#pragma unroll
+    for (int i = 0; i < kCols / 4; ++i) rr[i] = r4[i];
     if (p.gate != nullptr) {
       const float4* g4 = reinterpret_cast<const float4*>(p.gate + grow * p.gate_ld + col);
       const float4* t4 = reinterpret_cast<const float4*>(p.gate_table != nullptr ? p.gate_table + col : nullptr);
 #pragma unroll
       for (int i = 0; i < kCols / 4; ++i) {
-        const float4 r = r4[i];
+        const float4 r = rr[i];
         float4 g = __ldg(g4 + i);
         if (p.gate_table != nullptr) {
           const float4 t = __ldg(t4 + i);
@@ -169,7 +179,7 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, const uint32
     } else {
 #pragma unroll
       for (int i = 0; i < kCols / 4; ++i) {
-        const float4 r = r4[i];
+        const float4 r = rr[i];
         o4[i] = make_float4(v[4 * i] + r.x, v[4 * i + 1] + r.y, v[4 * i + 2] + r.z, v[4 * i + 3] + r.w);
       }
     }
@@ -228,6 +238,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   pdl_launch_dependents();
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
+  if (warp < 4) {
+  reg_dealloc<kRegsIssue>();
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -296,16 +308,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++acc == 2) acc = 0, acc_phase ^= 1;
       }
     }
+  }
   } else {
     // ===================== epilogue warps =====================
+    reg_alloc<kRegsEpilogue>();
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
     // two warps share each lane quarter and split the tile's 32-column chunks between them: the epilogue is a
     // chain of dependent memory round trips per chunk, so doubling the warps halves its (exposed) latency
-    const int col_half = (warp - 2) >> 2;
+    const int col_half = (warp - 4) >> 2;
     const int n_chunks = (bn + 31) / 32;
     const int c_begin = (col_half == 0 ? 0 : (n_chunks + 1) / 2) * 32;
     const int c_end = min(bn, (col_half == 0 ? (n_chunks + 1) / 2 : n_chunks) * 32);
-    const bool epi_leader = (warp == 2 && lane == 0);
+    const bool epi_leader = (warp == 4 && lane == 0);
     const int row_in_cta = quarter * 32 + lane;
     uint32_t acc = 0, acc_phase = 0;
     auto release_acc = [&]() {  // all of this warp's TMEM reads of the accumulator have completed
