@@ -117,6 +117,20 @@ int ltxb_rmsnorm_modulate(const float* x, int64_t ldx, void* out, int64_t ldo, i
                           const float* table_scale, const float* table_shift, int32_t row_div,
                           const int32_t* row_index, void* stream);
 
+/* K3r  The residual add of a projection and the NEXT sub-layer's rms_norm + AdaLN in one pass over the fp32 row
+ *      (transformer.py:254 -> 256-257 and 257 -> 343-346):
+ *        x[r,:] += y[r,:] * g[r,:]                      (x updated in place; y bf16 [R,D] = projection output incl. bias)
+ *        out[r,:] = rms_norm(x[r,:]) * (1 + scale[r,:]) + shift[r,:]
+ *      g     = table_gate[:]  + mod[mrow(r), gate_off  + :]   (either part NULL / offset < 0 -> absent; both absent -> 1)
+ *      scale = table_scale[:] + mod[mrow(r), scale_off + :]   (likewise; both absent -> plain rms_norm)
+ *      The out-projection GEMM then keeps its bf16 epilogue (LTXB_EPI_BIAS_BF16) instead of LTXB_EPI_RESID_GATE_F32,
+ *      whose fp32 read-modify-write of the tile is exposed when there is one tile per SM pair (N = 4096). */
+int ltxb_residual_rmsnorm_modulate(float* x, int64_t ldx, const void* y, int64_t ldy, void* out, int64_t ldo, int32_t R,
+                                   int32_t D, float eps, const float* mod, int64_t ld_mod, int32_t gate_off,
+                                   int32_t scale_off, int32_t shift_off, const float* table_gate,
+                                   const float* table_scale, const float* table_shift, int32_t row_div,
+                                   const int32_t* row_index, void* stream);
+
 /* K6  nn.LayerNorm(affine=False) then x*(1+scale)+shift  (ltx.py:300,432-457)
  *   scale/shift[r,:] = table_*[:] + emb[mrow(r), :]   (emb = embedded_timestep f32 [*, D]) */
 int ltxb_layernorm_modulate(const float* x, int64_t ldx, void* out, int64_t ldo, int32_t R, int32_t D, float eps,

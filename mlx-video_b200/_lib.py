@@ -50,6 +50,7 @@ SIGNATURES = {
     "ltxb_gemm_workspace_bytes": (C.c_int64, []),
     "ltxb_gemm_set_workspace": (C.c_int, [_vp, _i64, _vp]),
     "ltxb_rmsnorm_modulate": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "ltxb_residual_rmsnorm_modulate": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "ltxb_layernorm_modulate": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp, _i64, _vp, _vp, _i32, _vp, _vp]),
     "ltxb_gate_residual": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _i32, _vp, _i32, _vp, _vp]),
     "ltxb_qknorm_rope": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _i32, _vp]),

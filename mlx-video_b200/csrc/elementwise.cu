@@ -73,23 +73,32 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
 // rms_norm / layer_norm + AdaLN modulate.  kLayerNorm=false: x*rsqrt(mean(x^2)+eps);  true: LayerNorm.
 // mod_scale / mod_shift point at the first column of the scale / shift slice of the modulation row.
 // ------------------------------------------------------------------------------------------------
-template <int kChunks, bool kLayerNorm>
+// kResidual: x += y * g first (y bf16 = the projection that precedes this norm, g = gate_table + gate_mod row, or 1),
+// the updated x is stored back and normalised in the same pass — the residual add of an out-projection and the
+// next sub-layer's norm read the same fp32 row, so the GEMM keeps its cheap bf16 epilogue and the row is read once.
+struct ResidualIn {
+  const __nv_bfloat16* y;
+  long long ldy;
+  const float* gate_mod;    // first column of the gate slice of the modulation rows, or null
+  const float* gate_table;  // or null
+};
+template <int kChunks, bool kLayerNorm, bool kResidual>
 __global__ void __launch_bounds__(kRowThreads, kChunks <= 4 ? 9 : 1)  // <= 56 registers: 9 rows per SM, 1280 tokens in ONE wave
-norm_modulate_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out, long long ldo,
+norm_modulate_kernel(float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out, long long ldo,
                      int D, float eps, const float* __restrict__ mod_scale, const float* __restrict__ mod_shift,
                      long long ld_mod, const float* __restrict__ table_scale, const float* __restrict__ table_shift,
-                     int row_div, const int* __restrict__ row_index) {
+                     int row_div, const int* __restrict__ row_index, const ResidualIn res) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[32];
   const long long row = blockIdx.x;
-  const float* xr = x + row * ldx;
+  float* xr = x + row * ldx;
   // narrow rows keep the whole modulation in registers too, so its loads are in flight together with x's
   // instead of after the reduction (the kernel is a chain of L2 round trips, not a bandwidth problem)
   constexpr bool kPrefetch = kChunks <= 1;  // wider rows would push the register count past one-wave occupancy
   const bool has_mod = (mod_scale != nullptr) || (table_scale != nullptr);
   long long mrow = 0;
-  if (mod_scale != nullptr) mrow = row_index != nullptr ? row_index[row] : row / row_div;
+  if (mod_scale != nullptr || (kResidual && res.gate_mod != nullptr)) mrow = row_index != nullptr ? row_index[row] : row / row_div;
   auto load_one = [&](const float* table, const float* mod, int c, float (&o)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = 0.f;
@@ -112,6 +121,20 @@ norm_modulate_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* 
     const int c = (threadIdx.x + j * kRowThreads) * 8;
     if (c < D) {
       load8(xr + c, v[j]);
+      if constexpr (kResidual) {
+        float y[8];
+        load8_bf16(res.y + row * res.ldy + c, y);
+        if (res.gate_mod != nullptr || res.gate_table != nullptr) {
+          float g[8];
+          load_one(res.gate_table, res.gate_mod, c, g);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[j][i] = fmaf(y[i], g[i], v[j][i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[j][i] += y[i];
+        }
+        store8(xr + c, v[j]);
+      }
       if constexpr (kPrefetch) {
         if (has_mod) {
           load_one(table_scale, mod_scale, c, psc[j]);
@@ -183,16 +206,17 @@ norm_modulate_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* 
   }
 }
 
-template <bool kLayerNorm>
-static int launch_norm_modulate(const float* x, long long ldx, void* out, long long ldo, int R, int D, float eps,
+template <bool kLayerNorm, bool kResidual = false>
+static int launch_norm_modulate(const float* x_in, long long ldx, void* out, long long ldo, int R, int D, float eps,
                                 const float* mod_scale, const float* mod_shift, long long ld_mod,
                                 const float* table_scale, const float* table_shift, int row_div,
-                                const int* row_index, cudaStream_t s) {
+                                const int* row_index, cudaStream_t s, ResidualIn res = ResidualIn{nullptr, 0, nullptr, nullptr}) {
   const int chunks = (D / 8 + kRowThreads - 1) / kRowThreads;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  float* x = const_cast<float*>(x_in);  // only the kResidual instantiation writes through it
 #define LTXB_LAUNCH_NM(C)                                                                                        \
-  LTXB_CUDA(launch_kernel(norm_modulate_kernel<C, kLayerNorm>, dim3(R), dim3(kRowThreads), 0, s, 1, x, ldx, o, ldo, D, eps, mod_scale, mod_shift, ld_mod, \
-                                                                 table_scale, table_shift, row_div, row_index))
+  LTXB_CUDA(launch_kernel(norm_modulate_kernel<C, kLayerNorm, kResidual>, dim3(R), dim3(kRowThreads), 0, s, 1, x, ldx, o, ldo, D, eps, mod_scale, mod_shift, ld_mod, \
+                                                                 table_scale, table_shift, row_div, row_index, res))
   if (chunks <= 1) LTXB_LAUNCH_NM(1);
   else if (chunks <= 2) LTXB_LAUNCH_NM(2);
   else if (chunks <= 4) LTXB_LAUNCH_NM(4);
@@ -613,6 +637,41 @@ extern "C" int ltxb_rmsnorm_modulate(const float* x, int64_t ldx, void* out, int
   return launch_norm_modulate<false>(x, ldx, out, ldo, R, D, eps, mod ? mod + scale_off : nullptr,
                                      mod ? mod + shift_off : nullptr, ld_mod, table_scale, table_shift,
                                      row_div > 0 ? row_div : 1, row_index, reinterpret_cast<cudaStream_t>(stream));
+}
+
+static int residual_norm_impl(float* x, int64_t ldx, const void* y, int64_t ldy, void* out, int64_t ldo,
+                              int32_t R, int32_t D, float eps, const float* mod, int64_t ld_mod, int32_t gate_off,
+                              int32_t scale_off, int32_t shift_off, const float* table_gate, const float* table_scale,
+                              const float* table_shift, int32_t row_div, const int32_t* row_index, void* stream) {
+  LTXB_CHECK_ARG(x && y && out, "ltxb_residual_norm_modulate: null pointer");
+  if (R == 0) return LTXB_OK;
+  LTXB_CHECK_ARG(R > 0 && D > 0, "ltxb_residual_norm_modulate: bad shape R=%d D=%d", R, D);
+  LTXB_CHECK_SUPPORTED(D % 8 == 0 && D <= 16 * 8 * kRowThreads, "ltxb_residual_norm_modulate: D=%d must be a multiple of 8, <= 16384", D);
+  LTXB_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(out) && ldx % 4 == 0 && ldy % 8 == 0 && ldo % 8 == 0,
+                 "ltxb_residual_norm_modulate: misaligned x / y / out");
+  LTXB_CHECK_ARG((table_scale == nullptr) == (table_shift == nullptr), "ltxb_residual_norm_modulate: scale / shift tables come in pairs");
+  LTXB_CHECK_ARG((scale_off >= 0) == (shift_off >= 0), "ltxb_residual_norm_modulate: scale / shift offsets come in pairs");
+  const bool use_mod = mod != nullptr && (gate_off >= 0 || scale_off >= 0);
+  if (use_mod) {
+    LTXB_CHECK_ARG(aligned16(mod) && ld_mod % 4 == 0 && (gate_off < 0 || gate_off % 4 == 0) && (scale_off < 0 || (scale_off % 4 == 0 && shift_off % 4 == 0)),
+                   "ltxb_residual_norm_modulate: modulation rows must be 16-byte aligned");
+    LTXB_CHECK_ARG(row_index || row_div >= 1, "ltxb_residual_norm_modulate: row_div must be >= 1");
+  }
+  if (table_gate) LTXB_CHECK_ARG(aligned16(table_gate), "ltxb_residual_norm_modulate: gate table misaligned");
+  ResidualIn res{reinterpret_cast<const __nv_bfloat16*>(y), ldy, (use_mod && gate_off >= 0) ? mod + gate_off : nullptr, table_gate};
+  const float* ms = (use_mod && scale_off >= 0) ? mod + scale_off : nullptr;
+  const float* mh = (use_mod && scale_off >= 0) ? mod + shift_off : nullptr;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return launch_norm_modulate<false, true>(x, ldx, out, ldo, R, D, eps, ms, mh, ld_mod, table_scale, table_shift, row_div > 0 ? row_div : 1, row_index, s, res);
+}
+
+extern "C" int ltxb_residual_rmsnorm_modulate(float* x, int64_t ldx, const void* y, int64_t ldy, void* out, int64_t ldo,
+                                              int32_t R, int32_t D, float eps, const float* mod, int64_t ld_mod,
+                                              int32_t gate_off, int32_t scale_off, int32_t shift_off,
+                                              const float* table_gate, const float* table_scale, const float* table_shift,
+                                              int32_t row_div, const int32_t* row_index, void* stream) {
+  return residual_norm_impl(x, ldx, y, ldy, out, ldo, R, D, eps, mod, ld_mod, gate_off, scale_off, shift_off, table_gate,
+                            table_scale, table_shift, row_div, row_index, stream);
 }
 
 extern "C" int ltxb_layernorm_modulate(const float* x, int64_t ldx, void* out, int64_t ldo, int32_t R, int32_t D,

@@ -172,6 +172,33 @@ def rmsnorm_modulate(
     return out
 
 
+def residual_rmsnorm_modulate(
+    x: torch.Tensor,
+    y: torch.Tensor,
+    out: torch.Tensor,
+    eps: float,
+    mod: Optional[torch.Tensor] = None,
+    gate_off: int = -1,
+    scale_off: int = -1,
+    shift_off: int = -1,
+    table_gate: Optional[torch.Tensor] = None,
+    table_scale: Optional[torch.Tensor] = None,
+    table_shift: Optional[torch.Tensor] = None,
+    row_div: int = 1,
+    row_index: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """x (f32, in place) += y (bf16) * gate; out (bf16) = rms_norm(x) * (1 + scale) + shift — one pass (ltxb.h K3r).
+    Offsets index the columns of ``mod``; a negative offset means that role takes nothing from ``mod``."""
+    _prep(x)
+    assert x.dtype == torch.float32 and y.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+    R, D = _rows(x), x.shape[-1]
+    assert _rows(y) == R and y.shape[-1] == D
+    _call("ltxb_residual_rmsnorm_modulate", 0.0, x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), out.data_ptr(), _ld(out), R, D,
+          eps, _ptr(mod), 0 if mod is None else _ld(mod), gate_off, scale_off, shift_off, _ptr(table_gate),
+          _ptr(table_scale), _ptr(table_shift), row_div, _ptr(row_index), _stream())
+    return out
+
+
 def layernorm_modulate(
     x: torch.Tensor,
     out: torch.Tensor,

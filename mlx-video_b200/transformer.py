@@ -19,6 +19,7 @@ Weights are bf16 ``(out, in)`` like nn.Linear; biases, norm weights and scale-sh
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, replace
 from typing import Dict, Iterator, Optional, Tuple
 
@@ -29,6 +30,9 @@ from .config import LTXRopeType, TransformerConfig
 
 Tensor = torch.Tensor
 BF16, F32 = torch.bfloat16, torch.float32
+# A/B switch (scripts/bench_ab.sh): 0 = the attention out-projections add their residual in the GEMM epilogue
+# (LTXB_EPI_RESID_GATE_F32) instead of handing it to the norm kernel that follows
+DEFER_RESIDUAL = os.environ.get("LTXB_DEFER_RESID", "1") != "0"
 
 
 @dataclass(frozen=True)
@@ -249,9 +253,11 @@ class Attention:
               context: Optional[Tensor] = None, Tk: int = 0, pe=None, k_pe=None, kv_bias: Optional[Tensor] = None,
               gate: Optional[Tensor] = None, gate_table: Optional[Tensor] = None, row_div: int = 1,
               row_index: Optional[Tensor] = None, seq_parallel=None, kv_out: Optional[Tensor] = None,
-              kv_ready: bool = False) -> None:
+              kv_ready: bool = False, defer: bool = False) -> Optional[Tensor]:
         """resid (f32 [B*Tq, query_dim]) += to_out(attention(...)) * gate, in place — the to_out GEMM's
-        epilogue carries bias, gate and residual add (transformer.py:254,257-261)."""
+        epilogue carries bias, gate and residual add (transformer.py:254,257-261).
+        ``defer=True``: the projection (bias included) is returned as bf16 instead and the CALLER adds it — the
+        next sub-layer's norm kernel does, in the pass that reads the row anyway (ops.residual_rmsnorm_modulate)."""
         group_cols = 0
         if seq_parallel is not None and context is None and self.is_self:
             # rows are sharded across ranks: projections local, heads <-> sequence all-to-all around the attention
@@ -259,8 +265,13 @@ class Attention:
         else:
             q, k, v = self.project(ws, tag, xq, B, Tq, context, Tk, pe, k_pe, kv_out, kv_ready)
             o = self.sdpa(ws, tag, q, k, v, B, Tq, Tq if context is None else Tk, kv_bias)
+        if defer:
+            y = ws.get(tag + ".y", (B * Tq, self.query_dim), BF16, resid.device)
+            ops.gemm(o, self.to_out.weight, self.to_out.bias, y, _lib.EPI_BIAS_BF16, a_group_cols=group_cols)
+            return y
         ops.gemm(o, self.to_out.weight, self.to_out.bias, resid, _lib.EPI_RESID_GATE_F32, resid=resid, gate=gate,
                  gate_table=gate_table, gate_row_div=row_div, gate_row_index=row_index, a_group_cols=group_cols)
+        return None
 
     def __call__(self, x: Tensor, context: Optional[Tensor] = None, mask: Optional[Tensor] = None, pe=None,
                  k_pe=None) -> Tensor:
@@ -354,8 +365,9 @@ class BasicAVTransformerBlock:
 
     # ------------------------------------------------------------------ stream pieces
     def _attn_pair(self, ws, tag, a: TransformerArgs, attn1: Attention, attn2: Attention, table: Tensor,
-                   seq_parallel=None) -> None:
-        """x += attn1(rms(x)(1+scale)+shift, pe) * gate ; x += attn2(rms(x), context)   (transformer.py:247-261)"""
+                   seq_parallel=None) -> Tensor:
+        """x += attn1(rms(x)(1+scale)+shift, pe) * gate ; x += attn2(rms(x), context)   (transformer.py:247-261).
+        The attn2 projection is RETURNED (bf16), not yet added: ``_add_pending`` or ``_ff`` adds it."""
         B, T, D = a.x.shape
         x2 = a.x.view(B * T, D)
         mod = a.timesteps.view(-1, a.timesteps.shape[-1])
@@ -364,9 +376,15 @@ class BasicAVTransformerBlock:
         # rows of the table / columns of the modulation: shift_msa, scale_msa, gate_msa (transformer.py:248)
         ops.rmsnorm_modulate(x2, nx, self.norm_eps, mod=mod, scale_off=D, shift_off=0, table_scale=table[1],
                              table_shift=table[0], row_div=div, row_index=idx)
-        attn1.fused(ws, tag + ".attn1", nx, B, T, x2, pe=a.positional_embeddings, gate=mod[:, 2 * D:3 * D],
-                    gate_table=table[2], row_div=div, row_index=idx, seq_parallel=seq_parallel)
-        ops.rmsnorm_modulate(x2, nx, self.norm_eps)
+        # the two out-projections keep the bf16 epilogue; their residual adds ride in the norm kernel that follows
+        if DEFER_RESIDUAL:
+            y1 = attn1.fused(ws, tag + ".attn1", nx, B, T, x2, pe=a.positional_embeddings, seq_parallel=seq_parallel, defer=True)
+            ops.residual_rmsnorm_modulate(x2, y1, nx, self.norm_eps, mod=mod, gate_off=2 * D, table_gate=table[2],
+                                          row_div=div, row_index=idx)  # x += attn1 * gate_msa ; nx = rms(x)
+        else:
+            attn1.fused(ws, tag + ".attn1", nx, B, T, x2, pe=a.positional_embeddings, gate=mod[:, 2 * D:3 * D],
+                        gate_table=table[2], row_div=div, row_index=idx, seq_parallel=seq_parallel)
+            ops.rmsnorm_modulate(x2, nx, self.norm_eps)
         Tc = a.context.shape[1]
         cache = a.context_cache
         if a.text_kv is not None:
@@ -375,18 +393,28 @@ class BasicAVTransformerBlock:
         else:
             kv_out = None if cache is None else cache.entry(self.idx, (a.context.shape[0] * Tc, 2 * attn2.inner_dim), x2.device)
             kv_ready = cache is not None and cache.valid
-        attn2.fused(ws, tag + ".attn2", nx, B, T, x2, context=a.context.reshape(-1, a.context.shape[-1]), Tk=Tc,
-                    kv_bias=a.context_mask, kv_out=kv_out, kv_ready=kv_ready)
+        return attn2.fused(ws, tag + ".attn2", nx, B, T, x2, context=a.context.reshape(-1, a.context.shape[-1]), Tk=Tc,
+                           kv_bias=a.context_mask, kv_out=kv_out, kv_ready=kv_ready, defer=DEFER_RESIDUAL)
 
-    def _ff(self, ws, tag, a: TransformerArgs, ff: FeedForward, table: Tensor) -> None:
-        """x += ff(rms(x)(1+scale)+shift) * gate   (transformer.py:342-355)"""
+    @staticmethod
+    def _add_pending(a: TransformerArgs, y: Optional[Tensor]) -> None:
+        """x += y for a deferred (ungated) projection that no norm kernel will pick up before x is read."""
+        if y is not None:
+            ops.gate_residual(a.x.view(-1, a.x.shape[-1]), y)
+
+    def _ff(self, ws, tag, a: TransformerArgs, ff: FeedForward, table: Tensor, pending: Optional[Tensor] = None) -> None:
+        """[x += pending ;] x += ff(rms(x)(1+scale)+shift) * gate   (transformer.py:342-355)"""
         B, T, D = a.x.shape
         x2 = a.x.view(B * T, D)
         mod = a.timesteps.view(-1, a.timesteps.shape[-1])
         div, idx = _row_map(a.x, a.timesteps, a.timestep_index)
         nx = ws.get(tag + ".nx", (B * T, D), BF16, x2.device)
-        ops.rmsnorm_modulate(x2, nx, self.norm_eps, mod=mod, scale_off=4 * D, shift_off=3 * D, table_scale=table[4],
-                             table_shift=table[3], row_div=div, row_index=idx)
+        if pending is not None:
+            ops.residual_rmsnorm_modulate(x2, pending, nx, self.norm_eps, mod=mod, scale_off=4 * D, shift_off=3 * D,
+                                          table_scale=table[4], table_shift=table[3], row_div=div, row_index=idx)
+        else:
+            ops.rmsnorm_modulate(x2, nx, self.norm_eps, mod=mod, scale_off=4 * D, shift_off=3 * D, table_scale=table[4],
+                                 table_shift=table[3], row_div=div, row_index=idx)
         ff.fused(ws, tag + ".ff", nx, x2, mod[:, 5 * D:6 * D], table[5], div, idx)
 
     def _cross_av(self, ws, v: TransformerArgs, a: TransformerArgs, seq_parallel=None) -> None:
@@ -439,16 +467,21 @@ class BasicAVTransformerBlock:
                 video = replace(video, x=video.x.clone())
             if run_ax:
                 audio = replace(audio, x=audio.x.clone())
+        yv = ya = None  # text-cross-attention projections still to be added to the streams
         if run_vx:
-            self._attn_pair(ws, "v", video, self.attn1, self.attn2, self.scale_shift_table, seq_parallel)
+            yv = self._attn_pair(ws, "v", video, self.attn1, self.attn2, self.scale_shift_table, seq_parallel)
         if run_ax:
-            self._attn_pair(ws, "a", audio, self.audio_attn1, self.audio_attn2, self.audio_scale_shift_table)
+            ya = self._attn_pair(ws, "a", audio, self.audio_attn1, self.audio_attn2, self.audio_scale_shift_table)
         if run_vx and run_ax:
+            # the audio<->video cross-attention reads both streams: they must be complete first
+            self._add_pending(video, yv)
+            self._add_pending(audio, ya)
+            yv = ya = None
             self._cross_av(ws, video, audio, seq_parallel)
         if run_vx:
-            self._ff(ws, "v", video, self.ff, self.scale_shift_table)
+            self._ff(ws, "v", video, self.ff, self.scale_shift_table, yv)
         if run_ax:
-            self._ff(ws, "a", audio, self.audio_ff, self.audio_scale_shift_table)
+            self._ff(ws, "a", audio, self.audio_ff, self.audio_scale_shift_table, ya)
         return video, audio
 
     def named_parameters(self, prefix: str) -> Iterator[Tuple[str, Tensor]]:

@@ -141,6 +141,39 @@ def test_rmsnorm_layernorm_modulate():
         assert rel_l2(out.float(), ln * (1 + table[1] + emb[idx.long()]) + table[0] + emb[idx.long()]) <= 4e-3
 
 
+def test_residual_rmsnorm_modulate():
+    """x += y * gate and the norm of the updated row in one pass == the two separate steps (fp32 torch reference):
+    x to fp32 rounding (1e-6), the normalised bf16 output to its own rounding (4e-3)."""
+    g = torch.Generator(device=DEV).manual_seed(5)
+    for R, D in [(1280, 4096), (68, 2048), (37, 512), (5, 1032), (3, 8192)]:
+        x0 = torch.randn(R, D, device=DEV, generator=g) * 3
+        y = torch.randn(R, D, device=DEV, generator=g).bfloat16()
+        mod = torch.randn(3, 6 * D, device=DEV, generator=g) * 0.1
+        table = torch.randn(6, D, device=DEV, generator=g) * 0.1
+        idx = torch.randint(0, 3, (R,), device=DEV, generator=g, dtype=torch.int32)
+        out = torch.empty(R, D, device=DEV, dtype=torch.bfloat16)
+        norm = lambda t: t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-6)  # noqa: E731
+        # gated residual, plain norm (attn1 out-projection -> attn2's norm)
+        x = x0.clone()
+        ops.residual_rmsnorm_modulate(x, y, out, 1e-6, mod=mod, gate_off=2 * D, table_gate=table[2], row_index=idx)
+        xr = x0 + y.float() * (table[2] + mod[idx.long(), 2 * D:3 * D])
+        assert rel_l2(x, xr) <= 1e-6 and rel_l2(out.float(), norm(xr)) <= 4e-3
+        # ungated residual, modulated norm (attn2 out-projection -> the FFN's norm); row divisor instead of an index
+        x = x0.clone()
+        div = 2
+        mod_b = torch.randn((R + div - 1) // div, 6 * D, device=DEV, generator=g) * 0.1
+        ops.residual_rmsnorm_modulate(x, y, out, 1e-6, mod=mod_b, scale_off=4 * D, shift_off=3 * D, table_scale=table[4],
+                                      table_shift=table[3], row_div=div)
+        xr = x0 + y.float()
+        rows = torch.arange(R, device=DEV) // div
+        ref = norm(xr) * (1 + table[4] + mod_b[rows, 4 * D:5 * D]) + table[3] + mod_b[rows, 3 * D:4 * D]
+        assert rel_l2(x, xr) <= 1e-6 and rel_l2(out.float(), ref) <= 4e-3
+        # nothing but the add
+        x = x0.clone()
+        ops.residual_rmsnorm_modulate(x, y, out, 1e-6)
+        assert rel_l2(x, xr) <= 1e-6 and rel_l2(out.float(), norm(xr)) <= 4e-3
+
+
 def test_qknorm_rope_and_small_kernels():
     g = torch.Generator(device=DEV).manual_seed(2)
     for B, T, H, dh in [(1, 320, 32, 128), (2, 68, 32, 64), (1, 77, 4, 128)]:
