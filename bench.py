@@ -147,7 +147,7 @@ def cpu_block_sample(T: int, Tc: int, budget_s: float = 15.0) -> dict:
     return dict(t_forward=48 * statistics.median(times) + s.t_prepost, cores=s.cores, sample=s.describe(times))
 
 
-def run_reference(args, wl, rank: int) -> None:
+def run_reference(args, wl, rank: int, result_out) -> None:
     """`--impl reference`: the reference's CPU implementation of the path.  The reference itself is MLX-only
     Python and cannot run here, so this is the oracle port (kind "port") on all host threads; every
     step is a bounded sample (one block of 48), extrapolated to the full forward."""
@@ -168,11 +168,21 @@ def run_reference(args, wl, rank: int) -> None:
             "config": {"workload": wl["desc"], "video_tokens": T, "text_tokens": wl["Tc"], "forwards_per_step": forwards},
             "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": s.cores, "kind": "port", "sample": s.describe(times)},
             "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=result_out, flush=True)
 
 
 # --------------------------------------------------------------------------------------------------
+def _json_only_stdout():
+    """Stdout carries exactly ONE JSON line: everything else any library prints there (NCCL's version banner under
+    torchrun, for one) is sent to stderr.  Returns the writer for the result line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main() -> int:
+    result_out = _json_only_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=16)
@@ -194,7 +204,7 @@ def main() -> int:
     if args.text_tokens:
         wl["Tc"] = args.text_tokens
     if args.impl == "reference":
-        run_reference(args, wl, rank)
+        run_reference(args, wl, rank, result_out)
         return 0
     if world != args.gpus:
         if args.gpus != 1 and world == 1:
@@ -429,7 +439,7 @@ def main() -> int:
                 print(f"{k:28s} {v['launches']:5d} launches {v['ms']:9.3f} ms {100 * v['share']:5.1f}%", file=sys.stderr)
             for work, (n, ms) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
                 print(f"  gemm {work / 1e9:9.1f} GFLOP x {n:3d}: {ms / n * 1e3:8.1f} us each, {work * n / ms / 1e9:7.0f} TFLOP/s, {ms:7.3f} ms", file=sys.stderr)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=result_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -41,7 +41,7 @@ constexpr int kEmu = LTXB_ATTN_EMU;  // of every 8 column pairs, how many take t
 constexpr int kRegsIssue = 104, kRegsSoftmax = 200;  // 128 * 104 + 256 * 200 <= 64 K registers
 
 // LTXB_ATTN_TRACE: CTA 0 records clock64() at the phase boundaries of its first 16 key tiles into the workspace
-// (long long [3 roles][16 tiles][8 events]; roles: softmax 0, softmax 1, MMA issuer) — scripts/attn_trace.py prints it.
+// (long long [4 roles][16 tiles][8 events]; roles: softmax 0, softmax 1, MMA issuer, CTA life cycle) — scripts/attn_trace.py prints it.
 #ifdef LTXB_ATTN_TRACE
 #define TRACE(role, it, ev)                                                                                  \
   do {                                                                                                       \
@@ -106,6 +106,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TRACE(3, 0, 0);  // kernel entry
   const PairJob job = decode_pair_job(p, blockIdx.x);
   const int n_it = job.kv_hi - job.kv_lo;
 
@@ -136,8 +137,10 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&hdr->tmem_base);
+  if (threadIdx.x == 0) TRACE(3, 0, 1);  // barriers + TMEM ready
   pdl_launch_dependents();
   pdl_wait();
+  if (threadIdx.x == 0) TRACE(3, 0, 2);  // predecessor kernel finished
 
   // the softmax threads hold a whole 128-column score row: they take registers from the producer / issuer warpgroup
   if (warp < 4) {
@@ -347,10 +350,12 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       m = m_new;
     }
     // ---- epilogue ----
+    if (lane == 0 && quarter == 0) TRACE(3, 0, 3 + t);  // softmax of the last key tile done
     if (n_it > 0) {
       mbar_wait(&hdr->pv_done[t], (n_it - 1) & 1);
       tc_fence_after_sync();
     }
+    if (lane == 0 && quarter == 0 && t == 0) TRACE(3, 0, 5);  // last PV done
     const int row = job.q0 + t * 128 + r;
     if (job.slot < 0) {
       const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
@@ -393,6 +398,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   __syncwarp();
   tc_fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) TRACE(3, 0, 6);  // output stored by every warp
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc<1>(tmem_base, 512);
@@ -415,37 +421,24 @@ __global__ void __launch_bounds__(256) attention_combine_kernel(const AttnParams
   if (row >= p.Tq) return;
   const int b = bh / p.H, h = bh - b * p.H;
   const long long prow0 = static_cast<long long>(jl) * p.n_split * 256 + rr;
-  // (m_i, l_i) of the pieces: lanes take pieces in parallel, so the loads are one round trip instead of n_split
   float M = -INFINITY;
-  for (int i = lane; i < p.n_split; i += 32) M = fmaxf(M, __ldcg(p.ws_ml + (prow0 + i * 256ll) * 2));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+  for (int i = 0; i < p.n_split; ++i) M = fmaxf(M, p.ws_ml[(prow0 + i * 256ll) * 2]);
   float acc[kPer];
 #pragma unroll
   for (int u = 0; u < kPer; ++u) acc[u] = 0.f;
   float L = 0.f;
-  for (int i0 = 0; i0 < p.n_split; i0 += 32) {
-    float w_mine = 0.f, wl_mine = 0.f;
-    if (i0 + lane < p.n_split) {
-      const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.ws_ml + (prow0 + (i0 + lane) * 256ll) * 2));
-      w_mine = (ml.x == -INFINITY) ? 0.f : fast_exp2(ml.x - M);
-      wl_mine = w_mine * ml.y;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wl_mine += __shfl_xor_sync(0xffffffffu, wl_mine, o);
-    L += wl_mine;
-    const int n = min(32, p.n_split - i0);
-#pragma unroll 4
-    for (int i = 0; i < n; ++i) {  // independent loads: the unrolled copies are in flight together
-      const float w = __shfl_sync(0xffffffffu, w_mine, i);
-      const float* src = p.ws_o + (prow0 + (i0 + i) * 256ll) * kDh + lane * kPer;
-      if constexpr (kPer == 4) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(src));
-        acc[0] += w * v.x, acc[1] += w * v.y, acc[2] += w * v.z, acc[3] += w * v.w;
-      } else {
-        const float2 v = __ldcg(reinterpret_cast<const float2*>(src));
-        acc[0] += w * v.x, acc[1] += w * v.y;
-      }
+  for (int i = 0; i < p.n_split; ++i) {
+    const long long pr = prow0 + i * 256ll;
+    const float2 ml = *reinterpret_cast<const float2*>(p.ws_ml + pr * 2);
+    const float w = (ml.x == -INFINITY) ? 0.f : fast_exp2(ml.x - M);
+    L += w * ml.y;
+    const float* src = p.ws_o + pr * kDh + lane * kPer;
+    if constexpr (kPer == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(src);
+      acc[0] += w * v.x, acc[1] += w * v.y, acc[2] += w * v.z, acc[3] += w * v.w;
+    } else {
+      const float2 v = *reinterpret_cast<const float2*>(src);
+      acc[0] += w * v.x, acc[1] += w * v.y;
     }
   }
   const float inv = (L > 0.f) ? 1.0f / L : 0.f;

@@ -39,14 +39,6 @@ __device__ __forceinline__ void load8_ldg(const float* p, float (&v)[8]) {
   const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
   v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
 }
-__device__ __forceinline__ void unpack8_bf16(const uint4 w, float (&v)[8]) {
-  const uint32_t u[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    v[2 * i] = __uint_as_float(u[i] << 16);
-    v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
-  }
-}
 __device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&v)[8]) {
   const uint4 w = *reinterpret_cast<const uint4*>(p);
   const uint32_t u[4] = {w.x, w.y, w.z, w.w};
@@ -294,56 +286,18 @@ qknorm_rope_kernel(const __nv_bfloat16* x, long long ldx, __nv_bfloat16* out, lo
   const int items = H * tph;
   const long long bb = (B_pe == 1) ? 0 : row / T;
   const long long t = row % T;
-  // Everything that does not need the row statistic happens BEFORE the reduction: the norm weight and the rotation
-  // are linear in x, so out = rstd * rotate(x * w).  All global loads of a row are then in flight together (one L2
-  // round trip per CTA instead of two: the kernel is a latency chain, not a bandwidth problem).
   float a[kPer][8], b[kPer][8];
-  uint4 ra[kPer], rb[kPer];  // the row's own elements are requested first, packed (4 registers per 8 elements)
-#pragma unroll
-  for (int j = 0; j < kPer; ++j) {
-    const int item = threadIdx.x + j * blockDim.x;
-    if (item < items) {
-      const __nv_bfloat16* p1 = x + row * ldx + (item / tph) * dh + (item % tph) * 8;
-      ra[j] = *reinterpret_cast<const uint4*>(p1);
-      rb[j] = *reinterpret_cast<const uint4*>(p1 + half);
-    }
-  }
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < kPer; ++j) {
     const int item = threadIdx.x + j * blockDim.x;
     if (item < items) {
       const int h = item / tph, off = (item % tph) * 8;
-      unpack8_bf16(ra[j], a[j]);
-      unpack8_bf16(rb[j], b[j]);
+      const __nv_bfloat16* p1 = x + row * ldx + h * dh + off;
+      load8_bf16(p1, a[j]);
+      load8_bf16(p1 + half, b[j]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) s += a[j][i] * a[j][i] + b[j][i] * b[j][i];
-      if (weight != nullptr) {
-        float w1[8], w2[8];
-        load8_ldg(weight + h * dh + off, w1);
-        load8_ldg(weight + h * dh + half + off, w2);
-        if (weight2 != nullptr) {  // a second per-column factor folded in (the partner's norm weight)
-          float u1[8], u2[8];
-          load8_ldg(weight2 + h * dh + off, u1);
-          load8_ldg(weight2 + h * dh + half + off, u2);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) w1[i] *= u1[i], w2[i] *= u2[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[j][i] *= w1[i], b[j][i] *= w2[i];
-        if (cos_tab != nullptr) {
-          const long long tab = ((bb * H + h) * T + t) * half + off;
-          float c[8], sn[8];
-          load8_ldg(cos_tab + tab, c);
-          load8_ldg(sin_tab + tab, sn);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float f = a[j][i] * c[i] - sn[i] * b[j][i];
-            const float g = b[j][i] * c[i] + sn[i] * a[j][i];
-            a[j][i] = f, b[j][i] = g;
-          }
-        }
-      }
     }
   }
   float rstd = 1.f;
@@ -357,8 +311,30 @@ qknorm_rope_kernel(const __nv_bfloat16* x, long long ldx, __nv_bfloat16* out, lo
     if (item >= items) continue;
     const int h = item / tph, off = (item % tph) * 8;
     if (weight != nullptr) {
+      float w1[8], w2[8];
+      load8_ldg(weight + h * dh + off, w1);
+      load8_ldg(weight + h * dh + half + off, w2);
+      if (weight2 != nullptr) {  // a second per-column factor folded in (the partner's norm weight)
+        float u1[8], u2[8];
+        load8_ldg(weight2 + h * dh + off, u1);
+        load8_ldg(weight2 + h * dh + half + off, u2);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[j][i] *= rstd, b[j][i] *= rstd;
+        for (int i = 0; i < 8; ++i) w1[i] *= u1[i], w2[i] *= u2[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[j][i] *= rstd * w1[i], b[j][i] *= rstd * w2[i];
+      if (cos_tab != nullptr) {
+        const long long tab = ((bb * H + h) * T + t) * half + off;
+        float c[8], sn[8];
+        load8_ldg(cos_tab + tab, c);
+        load8_ldg(sin_tab + tab, sn);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float f = a[j][i] * c[i] - sn[i] * b[j][i];
+          const float g = b[j][i] * c[i] + sn[i] * a[j][i];
+          a[j][i] = f, b[j][i] = g;
+        }
+      }
     }
     // head h lands in group h / heads_per_group (one group per destination rank of the Ulysses all-to-all)
     // ... and with peer bases the group IS the destination GPU: the store goes straight over NVLink into that

@@ -19,7 +19,7 @@ timeout 300 python scripts/attn_sweep.py > $out/attn_sweep.txt 2>&1; cat $out/at
 [ "$2" = "skip-ncu" ] && exit 0
 K='regex:^(gemm_bf16|attention|norm_modulate|qknorm_rope|gate_residual|timestep|rope_table|silu_bf16|cast_|euler_step)'
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base function -k "$K" -c 1400 --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base function -k "$K" -c 1520 --csv \
     --log-file $out/launches.csv $CMD > $out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
 CMD2="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph --layers 4"
