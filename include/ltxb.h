@@ -242,6 +242,13 @@ int ltxb_attention_fwd_peers(const void* Q, int64_t ldq, const void* K, int64_t 
                              void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, int64_t ldo, int32_t Tq,
                              int32_t Tk, int32_t H, int32_t dh, float scale, void* stream);
 
+/* N3  LoRA merged into a non-quantised bf16 weight, the path the reference takes for such checkpoints
+ *     (lora.py:93-129 via generate.py:2997-3007):  w[r,c] = bf16( w[r,c] + bf16(delta[r,c] * strength) )
+ *     delta f32 [R,C] = B (out, rank) . A (rank, in), produced by ltxb_gemm_bf16 (LTXB_EPI_BIAS_F32, no bias) with
+ *     a = B and W = A^T, rank zero-padded to a multiple of 64.  Both roundings of the reference are kept. */
+int ltxb_lora_merge_bf16(void* w, int64_t ldw, const float* delta, int64_t ldd, int64_t R, int32_t C, float strength,
+                         void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * a21/a22 sampler-side elementwise (utils.py:404-440; generate.py:1255,1283,1288-1301)
  *   CFG combine + to_denoised + fp32 Euler in one pass over the latent:

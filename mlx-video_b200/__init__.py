@@ -11,6 +11,7 @@ from . import _lib, ops  # noqa: F401  (loads libltxb.so)
 from ._lib import LtxbError  # noqa: F401
 from .config import (AttentionType, LTXModelConfig, LTXModelType, LTXRopeType, TransformerConfig,  # noqa: F401
                      production_config)
+from .lora import LoraSpec, apply_lora_to_model, apply_lora_to_weights  # noqa: F401
 from .model import AdaLayerNormSingle, LTXModel, PixArtAlphaTextProjection, X0Model, to_denoised  # noqa: F401
 from .rope import precompute_freqs_cis  # noqa: F401
 from .transformer import (Attention, BasicAVTransformerBlock, FeedForward, Modality, TransformerArgs,  # noqa: F401

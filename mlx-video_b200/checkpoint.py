@@ -4,7 +4,7 @@ expects.  Mirrors the key mapping of the reference's ``LTXModel.sanitize`` / ``f
 transformer; the embeddings connectors live in the text encoder; upstream names carry ``.to_out.0.``,
 ``.ff.net.0.proj.``, ``.ff.net.2.``, ``.linear_1.`` / ``.linear_2.``.  Already-sanitised files (no prefix) load
 as they are.  Pre-quantised MLX checkpoints (``.scales`` / ``.biases`` siblings, ltx.py:641-725) are rejected:
-quantised linears are row N3, not built.
+quantised linears (row N3) are not built; LoRA files are handled by ``lora.py``.
 """
 from __future__ import annotations
 

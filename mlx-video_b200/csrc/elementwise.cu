@@ -458,6 +458,26 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float*
     for (long long i = n8 * 8; i < n; ++i) out[i] = __bfloat162float(x[i]);
 }
 
+// LoRA merge into a bf16 weight (lora.py:119-127): w = bf16(w + bf16(delta * strength)) — the reference's two roundings
+__global__ void __launch_bounds__(256)
+lora_merge_kernel(__nv_bfloat16* __restrict__ w, long long ldw, const float* __restrict__ delta, long long ldd,
+                  long long R, int C, float strength) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int cpr = C / 8;
+  const long long total = R * cpr;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const long long row = i / cpr;
+    const int c = static_cast<int>(i - row * cpr) * 8;
+    float wv[8], dv[8];
+    load8_bf16(w + row * ldw + c, wv);
+    load8(delta + row * ldd + c, dv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wv[k] += __bfloat162float(__float2bfloat16_rn(dv[k] * strength));
+    store8_bf16(w + row * ldw + c, wv);
+  }
+}
+
 // CFG combine + to_denoised + mask blend + fp32 Euler (utils.py:404-440; generate.py:1255-1301)
 __global__ void euler_step_kernel(float* __restrict__ x, const float* __restrict__ v_pos,
                                   const float* __restrict__ v_neg, float cfg_scale,
@@ -819,6 +839,19 @@ extern "C" int ltxb_cast_bf16_to_f32(const void* x, float* out, int64_t n, void*
   LTXB_CHECK_ARG(aligned16(x) && aligned16(out), "ltxb_cast_bf16_to_f32: misaligned");
   LTXB_CUDA(launch_kernel(cast_bf16_f32_kernel, dim3(grid_for(n / 8 + 1, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, 
       reinterpret_cast<const __nv_bfloat16*>(x), out, n / 8, n));
+  return LTXB_OK;
+}
+
+extern "C" int ltxb_lora_merge_bf16(void* w, int64_t ldw, const float* delta, int64_t ldd, int64_t R, int32_t C,
+                                    float strength, void* stream) {
+  LTXB_CHECK_ARG(w && delta, "ltxb_lora_merge_bf16: null pointer");
+  if (R == 0) return LTXB_OK;
+  LTXB_CHECK_ARG(R > 0 && C > 0 && C % 8 == 0, "ltxb_lora_merge_bf16: bad shape R=%lld C=%d (C must be a multiple of 8)", static_cast<long long>(R), C);
+  LTXB_CHECK_ARG(aligned16(w) && aligned16(delta) && ldw % 8 == 0 && ldd % 4 == 0 && ldw >= C && ldd >= C,
+                 "ltxb_lora_merge_bf16: misaligned operands / leading dimensions");
+  LTXB_CUDA(launch_kernel(lora_merge_kernel, dim3(grid_for(R * (C / 8), 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1,
+                          reinterpret_cast<__nv_bfloat16*>(w), static_cast<long long>(ldw), delta, static_cast<long long>(ldd),
+                          static_cast<long long>(R), C, strength));
   return LTXB_OK;
 }
 

@@ -236,6 +236,16 @@ def gate_residual(
     return x
 
 
+def lora_merge(w: torch.Tensor, delta: torch.Tensor, strength: float) -> torch.Tensor:
+    """w (bf16 [R, C], row-strided view allowed) <- bf16(w + bf16(delta * strength)) in place (ltxb.h N3)."""
+    _prep(w)
+    assert w.dtype == torch.bfloat16 and delta.dtype == torch.float32 and w.dim() == 2 and delta.shape == w.shape
+    assert w.stride(1) == 1 and delta.stride(1) == 1
+    _call("ltxb_lora_merge_bf16", 0.0, w.data_ptr(), w.stride(0), delta.data_ptr(), delta.stride(0), w.shape[0], w.shape[1],
+          strength, _stream())
+    return w
+
+
 def qknorm_rope(
     x: torch.Tensor,
     B: int,

@@ -628,3 +628,62 @@ def small_config(model_type=LTXModelType.VideoOnly, num_layers=2, heads=4, audio
     return OracleConfig(model_type=model_type, num_attention_heads=heads, attention_head_dim=128, num_layers=num_layers,
                         cross_attention_dim=heads * 128, caption_channels=256, audio_num_attention_heads=audio_heads,
                         audio_attention_head_dim=64, audio_cross_attention_dim=audio_heads * 64, audio_caption_channels=256)
+
+
+# --------------------------------------------------------------------------------------------------
+# LoRA merge into non-quantised base weights (the path generate.py:2997-3007 takes when the
+# checkpoint is not quantised).  Restates mlx_video/lora.py:18-129; pinned by tests/golden/lora.npz, which
+# oracle/make_golden_lora.py produced by running that file itself.
+# --------------------------------------------------------------------------------------------------
+def lora_sanitize_prefix(prefix: str) -> str:
+    """lora.py:18-33: strip the PyTorch prefixes, apply the renames of LTXModel.sanitize."""
+    for p in ("model.diffusion_model.", "diffusion_model."):
+        if prefix.startswith(p):
+            prefix = prefix[len(p):]
+    for old, new in ((".to_out.0.", ".to_out."), (".ff.net.0.proj.", ".ff.proj_in."), (".ff.net.2.", ".ff.proj_out."),
+                     (".audio_ff.net.0.proj.", ".audio_ff.proj_in."), (".audio_ff.net.2.", ".audio_ff.proj_out."),
+                     (".linear_1.", ".linear1."), (".linear_2.", ".linear2.")):
+        prefix = prefix.replace(old, new)
+    return prefix
+
+
+def lora_candidate_keys(base_raw: str, base_sanitized: str) -> List[str]:
+    """lora.py:72-90: the weight-dict keys a LoRA pair may refer to, in the reference's order of preference."""
+    cand = [base_sanitized, base_raw]
+    if base_raw.startswith("diffusion_model."):
+        cand.append(f"model.{base_raw}")
+    if base_sanitized and not base_sanitized.startswith("model."):
+        cand += [f"diffusion_model.{base_sanitized}", f"model.diffusion_model.{base_sanitized}"]
+    seen, out = set(), []
+    for k in cand:
+        if k not in seen:
+            seen.add(k)
+            out.append(k)
+    return out
+
+
+def lora_pairs(lora_sd: Dict[str, Tensor]):
+    """lora.py:56-69: (base key raw, base key sanitised, A (r, in), B (out, r)) in the file's key order."""
+    for key in lora_sd:
+        if not key.endswith(".lora_A.weight"):
+            continue
+        key_b = key[: -len(".lora_A.weight")] + ".lora_B.weight"
+        if key_b not in lora_sd:
+            continue
+        base = key.replace(".lora_A.weight", ".weight")
+        yield base, lora_sanitize_prefix(base), lora_sd[key], lora_sd[key_b]
+
+
+def apply_lora_to_weights(weights: Dict[str, Tensor], loras) -> Dict[str, Tensor]:
+    """lora.py:93-129.  ``loras``: iterable of (state dict, strength), applied in order:
+    delta = (B @ A in fp32) * strength, cast to the weight's dtype, added in the weight's dtype."""
+    updated = dict(weights)
+    for lora_sd, strength in loras:
+        for base_raw, base_san, A, B in lora_pairs(lora_sd):
+            key = next((k for k in lora_candidate_keys(base_raw, base_san) if k in updated), None)
+            if key is None:
+                continue
+            w = updated[key]
+            delta = (B.float() @ A.float()) * strength
+            updated[key] = w + delta.to(w.dtype)
+    return updated

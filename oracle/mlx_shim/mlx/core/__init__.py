@@ -110,6 +110,10 @@ def _w(t):
     return array(t)
 
 
+def matmul(a, b):
+    return _w(_unwrap(a) @ _unwrap(b))
+
+
 def reshape(a, shape):
     return _w(_unwrap(a).reshape(tuple(shape)))
 
