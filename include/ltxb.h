@@ -249,6 +249,18 @@ int ltxb_attention_fwd_peers(const void* Q, int64_t ldq, const void* K, int64_t 
 int ltxb_lora_merge_bf16(void* w, int64_t ldw, const float* delta, int64_t ldd, int64_t R, int32_t C, float strength,
                          void* stream);
 
+/* N3  MLX affine group-quantised linears (pre-quantised 4/8-bit checkpoints: ltx.py:614-725 swaps the linears named by
+ *     ".scales" tensors for nn.QuantizedLinear, whose forward is mx.quantized_matmul).  On a GPU that keeps all 25.8 GB
+ *     of bf16 weights resident the packed form buys nothing at M >= 1280 rows (the GEMMs are tensor-bound), so the
+ *     checkpoint is expanded ONCE at load — exactly what MLX's matrix kernels do per tile — and the bf16 GEMM runs:
+ *         out[r,c] = bf16( scales[r, c/G] * q[r,c] + biases[r, c/G] )
+ *     wq: uint32 [R, C*bits/32] (ldq words per row), level c of a row in bits [bits*(c % (32/bits)), ...) of word
+ *     c / (32/bits);  scales / biases: bf16 (aux_f32 = 0) or f32 (aux_f32 = 1) [R, C/G] (lds elements per row);
+ *     out: bf16 [R, C] (ldo, may be a row view of fused q|k|v storage).  bits in {2,4,8}, G in {32,64,128}. */
+int ltxb_dequant_affine_bf16(const uint32_t* wq, int64_t ldq, const void* scales, const void* biases, int64_t lds,
+                             int32_t aux_f32, void* out, int64_t ldo, int64_t R, int32_t C, int32_t group_size,
+                             int32_t bits, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * a21/a22 sampler-side elementwise (utils.py:404-440; generate.py:1255,1283,1288-1301)
  *   CFG combine + to_denoised + fp32 Euler in one pass over the latent:

@@ -70,6 +70,7 @@ SIGNATURES = {
     "ltxb_attention_workspace_bytes": (C.c_int64, []),
     "ltxb_attention_set_workspace": (C.c_int, [_vp, _i64]),
     "ltxb_lora_merge_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _f32, _vp]),
+    "ltxb_dequant_affine_bf16": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
     "ltxb_euler_step": (C.c_int, [_vp, _vp, _vp, _f32, _vp, _f32, _f32, _vp, _vp, _i64, _i32, _vp, _vp]),
 }
 

@@ -478,6 +478,50 @@ lora_merge_kernel(__nv_bfloat16* __restrict__ w, long long ldw, const float* __r
   }
 }
 
+// MLX affine group quantisation -> bf16 (the checkpoints ltx.py:641-725 loads into nn.QuantizedLinear; mx.dequantize):
+//   out[r, c] = bf16( scales[r, c/G] * q[r, c] + biases[r, c/G] ),  q = BITS-wide level c of row r, 32/BITS levels per
+//   uint32 word, lowest bits first.  One thread = 8 consecutive columns (one 128-bit store; they share one group).
+template <int BITS, bool F32_AUX>
+__global__ void __launch_bounds__(256)
+dequant_affine_kernel(const uint32_t* __restrict__ wq, long long ldq, const void* __restrict__ scales,
+                      const void* __restrict__ biases, long long lds, __nv_bfloat16* __restrict__ out, long long ldo,
+                      long long R, int C, int group) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int cpr = C / 8;
+  const long long total = R * cpr;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const long long row = i / cpr;
+    const int c = static_cast<int>(i - row * cpr) * 8;
+    const long long aux = row * lds + c / group;
+    float s, b;
+    if constexpr (F32_AUX) {
+      s = static_cast<const float*>(scales)[aux];
+      b = static_cast<const float*>(biases)[aux];
+    } else {
+      s = __bfloat162float(static_cast<const __nv_bfloat16*>(scales)[aux]);
+      b = __bfloat162float(static_cast<const __nv_bfloat16*>(biases)[aux]);
+    }
+    const uint32_t* wrow = wq + row * ldq;
+    unsigned long long bits64;  // the 8 levels of this thread, lowest first
+    if constexpr (BITS == 8) {
+      const uint2 w = *reinterpret_cast<const uint2*>(wrow + c / 4);
+      bits64 = (static_cast<unsigned long long>(w.y) << 32) | w.x;
+    } else if constexpr (BITS == 4) {
+      bits64 = wrow[c / 8];
+    } else {
+      bits64 = (wrow[c / 16] >> ((c & 8) * 2)) & 0xffffu;
+    }
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float q = static_cast<float>(static_cast<unsigned>(bits64 >> (k * BITS)) & ((1u << BITS) - 1u));
+      v[k] = __fadd_rn(__fmul_rn(s, q), b);  // two roundings like scales * q + biases (exact product for bf16 scales)
+    }
+    store8_bf16(out + row * ldo + c, v);
+  }
+}
+
 // CFG combine + to_denoised + mask blend + fp32 Euler (utils.py:404-440; generate.py:1255-1301)
 __global__ void euler_step_kernel(float* __restrict__ x, const float* __restrict__ v_pos,
                                   const float* __restrict__ v_neg, float cfg_scale,
@@ -852,6 +896,36 @@ extern "C" int ltxb_lora_merge_bf16(void* w, int64_t ldw, const float* delta, in
   LTXB_CUDA(launch_kernel(lora_merge_kernel, dim3(grid_for(R * (C / 8), 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1,
                           reinterpret_cast<__nv_bfloat16*>(w), static_cast<long long>(ldw), delta, static_cast<long long>(ldd),
                           static_cast<long long>(R), C, strength));
+  return LTXB_OK;
+}
+
+extern "C" int ltxb_dequant_affine_bf16(const uint32_t* wq, int64_t ldq, const void* scales, const void* biases, int64_t lds,
+                                        int32_t aux_f32, void* out, int64_t ldo, int64_t R, int32_t C, int32_t group_size,
+                                        int32_t bits, void* stream) {
+  LTXB_CHECK_ARG(wq && scales && biases && out, "ltxb_dequant_affine_bf16: null pointer");
+  if (R == 0) return LTXB_OK;
+  LTXB_CHECK_SUPPORTED(bits == 2 || bits == 4 || bits == 8, "ltxb_dequant_affine_bf16: bits=%d (2, 4 and 8 are built)", bits);
+  LTXB_CHECK_SUPPORTED(group_size == 32 || group_size == 64 || group_size == 128,
+                       "ltxb_dequant_affine_bf16: group_size=%d (32, 64 and 128 are built)", group_size);
+  LTXB_CHECK_ARG(R > 0 && C > 0 && C % group_size == 0, "ltxb_dequant_affine_bf16: bad shape R=%lld C=%d group=%d",
+                 static_cast<long long>(R), C, group_size);
+  LTXB_CHECK_ARG(ldq >= static_cast<int64_t>(C) * bits / 32 && lds >= C / group_size && ldo >= C && ldo % 8 == 0 &&
+                     aligned16(out) && (reinterpret_cast<uintptr_t>(wq) & 7u) == 0 && (bits != 8 || ldq % 2 == 0),
+                 "ltxb_dequant_affine_bf16: misaligned operands / leading dimensions");
+  auto launch = [&](auto kernel) {
+    return launch_kernel(kernel, dim3(grid_for(R * (C / 8), 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, wq,
+                         static_cast<long long>(ldq), scales, biases, static_cast<long long>(lds),
+                         reinterpret_cast<__nv_bfloat16*>(out), static_cast<long long>(ldo), static_cast<long long>(R), C, group_size);
+  };
+  if (aux_f32) {
+    if (bits == 8) LTXB_CUDA(launch(dequant_affine_kernel<8, true>));
+    else if (bits == 4) LTXB_CUDA(launch(dequant_affine_kernel<4, true>));
+    else LTXB_CUDA(launch(dequant_affine_kernel<2, true>));
+  } else {
+    if (bits == 8) LTXB_CUDA(launch(dequant_affine_kernel<8, false>));
+    else if (bits == 4) LTXB_CUDA(launch(dequant_affine_kernel<4, false>));
+    else LTXB_CUDA(launch(dequant_affine_kernel<2, false>));
+  }
   return LTXB_OK;
 }
 

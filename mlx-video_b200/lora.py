@@ -1,18 +1,22 @@
-"""LoRA on the B200 path (the LoRA half).
+"""LoRA on the B200 path.
 
-Mirror of the reference's ``mlx_video/lora.py`` for NON-quantised base weights — the case this path serves
-(quantised MLX checkpoints are rejected at load, checkpoint.py).  For those the reference merges every LoRA into the
-weights before the model is built (``apply_lora_to_weights``, lora.py:93-129, called at generate.py:2997-3007); its
-runtime ``LoRAAdapter`` (lora.py:188-217) only exists to protect quantised bases and is therefore not needed here.
-A merged weight costs nothing per denoise step, which is the right trade on a GPU that holds the 25.8 GB of weights
-resident: the stage-2 distilled LoRA of the two-stage pipelines is merged once at stage switch.
+Mirror of the reference's ``mlx_video/lora.py``: same names and argument meaning — ``LoraSpec``, ``load_lora_state``,
+``has_quantized_weights``, ``apply_lora_to_weights`` (dict in, dict out) and ``apply_lora_to_model`` (an already loaded
+model, in place).  Both of the reference's modes end in the same thing here, a merged bf16 device weight:
 
-Same names and argument meaning as the reference: ``LoraSpec``, ``load_lora_state``, ``apply_lora_to_weights``
-(dict in, dict out), ``apply_lora_to_model`` (here: merge in place into an already loaded model — the device-side
-shortcut that skips the host round trip of the dict form).  The arithmetic runs through the C ABI:
-delta = B . A on the tensor cores (``ltxb_gemm_bf16``, fp32 accumulation and output), then
-``ltxb_lora_merge_bf16`` applies the reference's two roundings, w = bf16(w + bf16(delta * strength)).
-A and B are taken in bf16 (LTX-2 LoRA files are bf16; fp32 files lose their extra mantissa bits here).
+* non-quantised checkpoints — the reference merges every LoRA into the weights before the model is built
+  (``apply_lora_to_weights``, lora.py:93-129, called at generate.py:3007): w = bf16(w + bf16((B.A) * strength));
+* quantised checkpoints — the reference must not touch the packed weights, so it wraps the linears in runtime
+  ``LoRAAdapter``s, y + ((x A^T) B^T) * strength (lora.py:188-275, generate.py:2999-3023).  On this path quantised
+  linears were already expanded to bf16 at load (``ltxb_dequant_affine_bf16``, checkpoint.py), nothing is re-quantised,
+  and ``apply_lora_to_model`` merges into the expanded weight: the same sum W x + s B A x with one bf16 rounding of
+  W + s B A instead of one of the adapter's output; it costs nothing per denoise step (pinned by
+  tests/golden/quant.npz ``velocity_lora``, produced by the reference's adapters).
+
+A merged weight is the right trade on a GPU that holds the 25.8 GB of weights resident: the stage-2 distilled LoRA of
+the two-stage pipelines is merged once at stage switch.  The arithmetic runs through the C ABI: delta = B . A on the
+tensor cores (``ltxb_gemm_bf16``, fp32 accumulation and output), then ``ltxb_lora_merge_bf16`` applies the reference's
+two roundings.  A and B are taken in bf16 (LTX-2 LoRA files are bf16; fp32 files lose their extra mantissa bits here).
 """
 from __future__ import annotations
 
@@ -109,6 +113,8 @@ def apply_lora_to_weights(weights: Dict[str, Tensor], lora_specs: Iterable[LoraS
                           device="cuda") -> Dict[str, Tensor]:
     """lora.py:93-129: a new dict with every LoRA of ``lora_specs`` merged, in order, into the weights they name.
     Touched weights come back as bf16 tensors on ``device`` (what ``LTXModel.load_weights`` stores anyway)."""
+    if has_quantized_weights(weights):  # generate.py:2999-3004 never merges into packed weights
+        raise ValueError("quantised weights (.scales / .biases): load the model first, then apply_lora_to_model()")
     updated = dict(weights)
     for spec in lora_specs:
         lora_sd = load_lora_state(spec.path)

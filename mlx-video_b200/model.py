@@ -226,12 +226,20 @@ class LTXModel:
     def num_parameters(self) -> int:
         return sum(t.numel() for _, t in self.named_parameters())
 
-    def load_weights(self, weights: Dict[str, Tensor], strict: bool = True) -> None:
+    def load_weights(self, weights: Dict[str, Tensor], strict: bool = True, quant_meta: Optional[dict] = None) -> None:
         """Copy a state dict (reference names) into the device layout.  Strict: every model parameter
-        must be present (ValueError otherwise, ltx.py:874-881) and unknown keys are an error."""
+        must be present (ValueError otherwise, ltx.py:874-881) and unknown keys are an error.
+        MLX affine-quantised linears (``X.weight`` uint32 beside ``X.scales`` / ``X.biases``, the tensors
+        ``nn.QuantizedLinear`` holds after ltx.py:641-725) are expanded to bf16 on the device at this point
+        (``ltxb_dequant_affine_bf16``); group size and bits follow from the tensor shapes and must agree with
+        ``quant_meta`` (the checkpoint's quantization.json, ltx.py:649-668) when that is given."""
+        from .checkpoint import quant_layout
+
         params = self.parameters()
+        quantised = {k[: -len(".scales")] for k in weights if k.endswith(".scales")}
+        aux = {f"{b}{suffix}" for b in quantised for suffix in (".scales", ".biases")}
         missing = [k for k in params if k not in weights]
-        extra = [k for k in weights if k not in params]
+        extra = [k for k in weights if k not in params and not (k in aux and k.rsplit(".", 1)[0] + ".weight" in params)]
         if strict and missing:
             raise ValueError(f"Missing {len(missing)} parameters: {missing[:8]}{'...' if len(missing) > 8 else ''}")
         if strict and extra:
@@ -240,9 +248,23 @@ class LTXModel:
             src = weights.get(name)
             if src is None:
                 continue
+            base = name[: -len(".weight")] if name.endswith(".weight") else None
+            if base in quantised:
+                scales, biases = weights[f"{base}.scales"], weights.get(f"{base}.biases")
+                if biases is None:
+                    raise ValueError(f"quantised linear {base} has .scales but no .biases")
+                group_size, bits = quant_layout(name, tuple(src.shape), tuple(scales.shape), tuple(dst.shape), quant_meta)
+                aux_dtype = BF16 if scales.dtype == BF16 else F32  # f16 scales are widened (plumbing), bf16 / f32 are read as stored
+                dev = dst.device
+                ops.dequant_affine(src.to(dev).contiguous(), scales.to(dev, aux_dtype).contiguous(),
+                                   biases.to(dev, aux_dtype).contiguous(), dst, group_size, bits)
+                continue
+            if src.dtype in (torch.uint32, torch.int32, torch.uint8):
+                raise ValueError(f"{name} is an integer tensor without .scales / .biases siblings")
             if tuple(src.shape) != tuple(dst.shape):
                 raise ValueError(f"shape mismatch for {name}: checkpoint {tuple(src.shape)} vs model {tuple(dst.shape)}")
             dst.copy_(src.to(device=dst.device, dtype=dst.dtype))  # plumbing: H2D copy + storage cast
+        self.clear_caches()  # projected-context caches and captured graphs belong to the old weights
 
     def init_random(self, seed: int = 0, table_std: float = 0.02) -> "LTXModel":
         """Random-init weights of the reference architecture, generated on the device (there is no
@@ -268,13 +290,27 @@ class LTXModel:
     @classmethod
     def from_pretrained(cls, model_path, config: LTXModelConfig, strict: bool = True,
                         weights_override: Optional[Dict[str, Tensor]] = None, device=None) -> "LTXModel":
-        """ltx.py:535-885 (loading only; quantised checkpoints are out of scope): reads safetensors
-        file(s), renames upstream keys (``sanitize_key``), casts to the device layout."""
-        from .checkpoint import load_transformer_weights
+        """ltx.py:535-885: reads safetensors file(s), renames upstream keys, rounds fp32 tensors to bf16 values
+        (ltx.py:613-615), expands MLX-quantised linears (ltx.py:641-725), IGNORES tensors the configured model does
+        not have (audio weights beside a video-only config, ltx.py:739-740) and, when ``strict``, raises ValueError
+        for every parameter the file(s) did not supply (ltx.py:874-881).  ``weights_override``: tensors already in
+        memory (unified weights / LoRA merges, ltx.py:617-623); those must be the complete set when ``strict``."""
+        from .checkpoint import checkpoint_files, load_transformer_weights, read_quantization_meta, sanitize_state_dict
 
         model = cls(config, device=device)
-        weights = load_transformer_weights(model_path, config) if weights_override is None else dict(weights_override)
-        model.load_weights(weights, strict=strict)
+        if weights_override is not None:
+            model.load_weights(sanitize_state_dict(dict(weights_override)), strict=strict)
+            return model
+        expected = set(model.parameters())
+        expected |= {k[: -len("weight")] + suffix for k in expected if k.endswith(".weight") for suffix in ("scales", "biases")}
+        weights = load_transformer_weights(model_path, config, expected=expected)
+        meta = read_quantization_meta(checkpoint_files(model_path)[0]) if any(k.endswith(".scales") for k in weights) else None
+        try:
+            model.load_weights(weights, strict=strict, quant_meta=meta)
+        except ValueError as e:
+            if str(e).startswith("Missing "):
+                raise ValueError(str(e).replace(" parameters:", " parameters after load (sample:", 1) + ").") from None
+            raise
         return model
 
     # ------------------------------------------------------------------ preprocessors (ltx.py:33-247)

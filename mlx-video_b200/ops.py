@@ -246,6 +246,27 @@ def lora_merge(w: torch.Tensor, delta: torch.Tensor, strength: float) -> torch.T
     return w
 
 
+def dequant_affine(packed: torch.Tensor, scales: torch.Tensor, biases: torch.Tensor, out: torch.Tensor, group_size: int,
+                   bits: int) -> torch.Tensor:
+    """out (bf16 [R, C], row-strided view allowed) <- scales * q + biases of an MLX affine-quantised weight
+    (packed uint32 / int32 [R, C*bits/32]; scales, biases bf16 or f32 [R, C/group_size]) (ltxb.h N3)."""
+    _prep(out)
+    for t in (packed, scales, biases):
+        if not t.is_cuda:
+            raise _lib.LtxbError("ltxb ops need CUDA tensors; there is no CPU fallback on this path")
+    assert out.dtype == torch.bfloat16 and out.dim() == 2 and out.stride(1) == 1
+    assert packed.dtype in (torch.uint32, torch.int32) and packed.dim() == 2 and packed.stride(1) == 1
+    assert scales.dtype == biases.dtype and scales.dtype in (torch.bfloat16, torch.float32)
+    assert scales.shape == biases.shape and scales.stride() == biases.stride() and scales.stride(1) == 1
+    R, Cc = out.shape
+    if packed.shape != (R, Cc * bits // 32) or scales.shape != (R, Cc // group_size):
+        raise ValueError(f"quantised tensors {tuple(packed.shape)} / {tuple(scales.shape)} do not describe a "
+                         f"{R}x{Cc} weight at {bits} bits, group {group_size}")
+    _call("ltxb_dequant_affine_bf16", 0.0, packed.data_ptr(), packed.stride(0), scales.data_ptr(), biases.data_ptr(),
+          scales.stride(0), int(scales.dtype == torch.float32), out.data_ptr(), out.stride(0), R, Cc, group_size, bits, _stream())
+    return out
+
+
 def qknorm_rope(
     x: torch.Tensor,
     B: int,

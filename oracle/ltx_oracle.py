@@ -687,3 +687,82 @@ def apply_lora_to_weights(weights: Dict[str, Tensor], loras) -> Dict[str, Tensor
             delta = (B.float() @ A.float()) * strength
             updated[key] = w + delta.to(w.dtype)
     return updated
+
+
+# --------------------------------------------------------------------------------------------------
+# MLX affine group quantisation (the quantised half).  The reference never does this
+# arithmetic itself: ``LTXModel.from_pretrained`` (ltx.py:641-725) swaps the linears named by the checkpoint's
+# ``.scales`` tensors for ``nn.QuantizedLinear`` through ``nn.quantize`` and the forward is
+# ``mx.quantized_matmul`` — third-party mlx==0.30.1 (uv.lock:760-761), absent here.  Restated from MLX's published
+# definition (``mx.quantize`` / ``mx.dequantize`` docs, mode="affine"):
+#     w[o, g*G + j] ~= scales[o, g] * q[o, g*G + j] + biases[o, g],      q in [0, 2^bits - 1]
+#   packing: 32/bits consecutive q of a row share one uint32, element j of the word in bits [bits*j, bits*(j+1))
+#   (lowest bits first) -> weight (out, in*bits/32) uint32, scales / biases (out, in/G) in the weight's dtype.
+# ``affine_dequantize`` is the load path and exact by definition.  ``affine_quantize`` only manufactures test
+# checkpoints (converting is offline tooling, out of scope); it follows the published fallback algorithm
+# (per group: range/(2^bits-1), sign chosen so the larger-magnitude edge is the bias, scale re-fitted so that
+# edge/scale is an integer) — parity of the LOAD path does not depend on it.
+# --------------------------------------------------------------------------------------------------
+def affine_quantize(w: Tensor, group_size: int = 64, bits: int = 4) -> Tuple[np.ndarray, Tensor, Tensor]:
+    """-> (packed uint32 ndarray (out, in*bits/32), scales, biases (out, in/group) in w.dtype)."""
+    assert w.dim() == 2 and w.shape[1] % group_size == 0 and 32 % bits == 0
+    n_bins = float((1 << bits) - 1)
+    g = w.reshape(w.shape[0], -1, group_size)
+    w_max = g.amax(-1, keepdim=True).float()
+    w_min = g.amin(-1, keepdim=True).float()
+    mask = w_min.abs() > w_max.abs()
+    scales = torch.clamp((w_max - w_min) / n_bins, min=1e-7)
+    scales = torch.where(mask, scales, -scales)
+    edge = torch.where(mask, w_min, w_max)
+    q0 = torch.round(edge / scales)
+    scales = torch.where(q0 != 0, edge / torch.where(q0 != 0, q0, torch.ones_like(q0)), scales)
+    biases = torch.where(q0 == 0, torch.zeros_like(edge), edge)
+    scales, biases = scales.to(w.dtype), biases.to(w.dtype)  # stored in the weight's dtype ...
+    q = torch.clamp(torch.round((g.float() - biases.float()) / scales.float()), 0, n_bins)  # ... and used as stored
+    per = 32 // bits
+    qi = q.reshape(w.shape[0], -1, per).to(torch.int64).numpy().astype(np.uint64)
+    shifts = (np.arange(per, dtype=np.uint64) * np.uint64(bits))
+    packed = (qi << shifts).sum(-1).astype(np.uint32)
+    return packed, scales.squeeze(-1), biases.squeeze(-1)
+
+
+def affine_unpack(packed: np.ndarray, bits: int) -> np.ndarray:
+    """uint32 (out, in*bits/32) -> integer levels (out, in) as int64."""
+    per = 32 // bits
+    shifts = (np.arange(per, dtype=np.uint32) * np.uint32(bits))
+    q = (packed.astype(np.uint32)[..., None] >> shifts) & np.uint32((1 << bits) - 1)
+    return q.reshape(packed.shape[0], -1).astype(np.int64)
+
+
+def affine_dequantize(packed: np.ndarray, scales: Tensor, biases: Tensor, group_size: int = 64, bits: int = 4) -> Tensor:
+    """fp32 (out, in): scales * q + biases with scales / biases up-cast to fp32 (one fused multiply-add has no
+    intermediate rounding: q <= 255 and an 8-bit-mantissa scale multiply exactly in fp32)."""
+    q = torch.from_numpy(affine_unpack(np.asarray(packed), bits)).float()
+    out_f, in_f = q.shape
+    assert scales.shape == (out_f, in_f // group_size) == biases.shape, (scales.shape, q.shape, group_size)
+    s = scales.float().repeat_interleave(group_size, dim=1)
+    b = biases.float().repeat_interleave(group_size, dim=1)
+    return q * s + b
+
+
+def quant_params_from_shapes(packed_cols: int, n_groups: int, in_features: int) -> Tuple[int, int]:
+    """(group_size, bits) implied by the tensor shapes of one quantised linear."""
+    return in_features // n_groups, packed_cols * 32 // in_features
+
+
+def dequantize_state_dict(weights: Dict[str, object], in_features: Dict[str, int]) -> Dict[str, Tensor]:
+    """A state dict holding MLX-quantised linears (``X.weight`` uint32 + ``X.scales`` + ``X.biases``) -> plain fp32
+    weights for ``OracleLTXModel``; ``in_features[name]`` is the linear's input width (from the model's shapes)."""
+    out: Dict[str, Tensor] = {}
+    for k, v in weights.items():
+        if k.endswith(".scales") or k.endswith(".biases"):
+            continue
+        base = k[: -len(".weight")] if k.endswith(".weight") else None
+        if base is not None and f"{base}.scales" in weights:
+            packed = np.asarray(v)
+            s, b = weights[f"{base}.scales"], weights[f"{base}.biases"]
+            gs, bits = quant_params_from_shapes(packed.shape[1], s.shape[1], in_features[k])
+            out[k] = affine_dequantize(packed, s, b, gs, bits)
+        else:
+            out[k] = v if isinstance(v, Tensor) else torch.from_numpy(np.asarray(v))
+    return out

@@ -9,7 +9,8 @@ import torch as _torch
 
 Dtype = _torch.dtype
 float32, float16, bfloat16 = _torch.float32, _torch.float16, _torch.bfloat16
-int32, int64, uint8, uint32, bool_ = _torch.int32, _torch.int64, _torch.uint8, _torch.int64, _torch.bool
+int32, int64, uint8, uint32, bool_ = _torch.int32, _torch.int64, _torch.uint8, _torch.int64, _torch.bool  # uint32 lives in int64
+uint16 = _torch.uint16
 
 
 def _unwrap(x):
@@ -276,6 +277,60 @@ random = _NS(
     seed=lambda s: _torch.manual_seed(s),
 )
 metal = _NS(start_capture=lambda *a, **k: None, stop_capture=lambda *a, **k: None)
+
+
+def view(a, dtype):
+    """mx.view: reinterpret the bytes.  uint32 arrays are held as int64 values in this shim."""
+    t = _unwrap(a)
+    if t.dtype == _torch.int64:  # a uint32 array
+        if dtype == uint32:
+            return _w(t)
+        raw = _torch.from_numpy(t.numpy().astype(_np.uint32).view(_np.int32).copy())
+        return _w(raw.view(dtype))
+    return _w(t.view(dtype))
+
+
+# ---- affine group quantisation (mx.quantize / mx.dequantize / mx.quantized_matmul, mode="affine"), from the
+# published definition: w ~= scales * q + biases per group of `group_size` along the last axis, 32/bits levels per
+# uint32 word, lowest bits first; scales / biases in the input dtype.
+def quantize(w, group_size=64, bits=4, mode="affine"):
+    t = _unwrap(w)
+    rows, cols = t.shape
+    n_bins = float((1 << bits) - 1)
+    g = t.reshape(rows, cols // group_size, group_size)
+    hi, lo = g.max(-1, keepdim=True).values.float(), g.min(-1, keepdim=True).values.float()
+    mask = lo.abs() > hi.abs()
+    scales = _torch.maximum((hi - lo) / n_bins, _torch.tensor(1e-7))
+    scales = _torch.where(mask, scales, -scales)
+    edge = _torch.where(mask, lo, hi)
+    q0 = _torch.round(edge / scales)
+    scales = _torch.where(q0 != 0, edge / _torch.where(q0 != 0, q0, _torch.ones_like(q0)), scales)
+    biases = _torch.where(q0 == 0, _torch.zeros_like(edge), edge)
+    scales, biases = scales.to(t.dtype), biases.to(t.dtype)
+    q = _torch.clamp(_torch.round((g.float() - biases.float()) / scales.float()), 0, n_bins).to(_torch.int64)
+    per = 32 // bits
+    q = q.reshape(rows, cols // per, per)
+    packed = (q << (_torch.arange(per) * bits)).sum(-1)
+    return _w(packed), _w(scales.squeeze(-1)), _w(biases.squeeze(-1))
+
+
+def dequantize(w, scales, biases, group_size=64, bits=4, mode="affine"):
+    p, s, b = _unwrap(w), _unwrap(scales), _unwrap(biases)
+    per = 32 // bits
+    q = (p.unsqueeze(-1) >> (_torch.arange(per) * bits)) & ((1 << bits) - 1)
+    q = q.reshape(p.shape[0], -1, group_size).float()
+    out = q * s.float().unsqueeze(-1) + b.float().unsqueeze(-1)
+    return _w(out.reshape(p.shape[0], -1).to(s.dtype))
+
+
+def quantized_matmul(x, w, scales, biases, transpose=True, group_size=64, bits=4, mode="affine"):
+    """x @ dequantize(w)^T (transpose=True), products accumulated in fp32, result in x's dtype."""
+    t = _unwrap(x)
+    dt = _torch.promote_types(t.dtype, _unwrap(scales).dtype)  # mlx: result_type(x, scales, biases); operands cast to it
+    sc, bi = _w(_unwrap(scales).to(dt)), _w(_unwrap(biases).to(dt))
+    wd = _unwrap(dequantize(w, sc, bi, group_size, bits)).float()  # the matrix kernels dequantise tiles into that dtype
+    y = t.float() @ (wd.t() if transpose else wd)
+    return _w(y.to(dt))
 
 
 def load(*a, **k):

@@ -105,6 +105,8 @@ def test_checkpoint_key_mapping_and_safetensors_roundtrip(tmp_path):
     got = ck.load_transformer_weights(tmp_path)
     assert sorted(got) == ["patchify_proj.weight", "transformer_blocks.0.attn1.to_out.bias"]
     assert torch.equal(got["patchify_proj.weight"], tensors[P + "patchify_proj.weight"])
-    save_file({P + "x.weight": torch.zeros(2), P + "x.scales": torch.zeros(2)}, str(tmp_path / "q.safetensors"))
-    with pytest.raises(ValueError, match="quantised"):
-        ck.load_transformer_weights(tmp_path / "q.safetensors")
+    # in an upstream-layout file only prefixed tensors are the transformer's (ltx.py:548-553)
+    save_file({P + "patchify_proj.bias": torch.zeros(2), "patchify_proj.weight": torch.zeros(2, 2)}, str(tmp_path / "u.safetensors"))
+    assert sorted(ck.load_transformer_weights(tmp_path / "u.safetensors")) == ["patchify_proj.bias"]
+    with pytest.raises(FileNotFoundError):
+        ck.load_transformer_weights(tmp_path / "empty_dir_that_does_not_exist")
