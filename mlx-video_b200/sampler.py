@@ -3,8 +3,9 @@ the per-step call into ``LTXModel``.
 
 Mirrors the reference's ``mlx_video/generate.py``: ``create_position_grid`` :470-525,
 ``create_audio_position_grid`` :528-551, ``compute_audio_frames`` :554-557, ``ltx2_scheduler`` :410-467,
-constants :339-353, ``denoise_distilled`` :564-881, ``denoise_dev`` :1060-1327 (same argument names and
-meaning).  Grids and schedules are host numpy like the reference (integer / index work: bit-exact).
+constants :339-353, ``denoise_distilled`` :564-881, ``denoise_audio_only`` :888-1058, ``denoise_dev`` :1060-1327,
+``denoise_dev_av`` :1330-1703 (same argument names and meaning; pinned by tests/golden/sampler.npz, which the
+reference's own four loops produced).  Grids and schedules are host numpy like the reference (integer / index work: bit-exact).
 The per-step latent update — CFG combine, x0 = x - sigma v, conditioning-mask blend, fp32 Euler
 (utils.py:404-440; generate.py:1255,1283-1301) — is one fused kernel (``ltxb_euler_step``) on fp32
 latents kept token-major (B, T, C) for the whole loop.
@@ -255,3 +256,99 @@ def denoise_dev(latents: Tensor, positions, text_embeddings_pos: Tensor, text_em
         _advance(x, v_pos.contiguous(), sigma, sigma_next, v_neg=None if v_neg is None else v_neg.contiguous(),
                  cfg_scale=cfg_scale, mask=mask, clean=clean)
     return _from_tokens(x, (b, c, f, h, w), dtype)
+
+
+def _audio_to_tokens(audio_latents: Tensor) -> Tensor:
+    """(B, 8, Ta, 16) -> fp32 (B, Ta, 128) token-major (generate.py:806-807). Layout plumbing."""
+    ab, ac, at, af = audio_latents.shape
+    return audio_latents.permute(0, 2, 1, 3).reshape(ab, at, ac * af).to(torch.float32).contiguous()
+
+
+def _audio_from_tokens(tokens: Tensor, shape, dtype) -> Tensor:
+    ab, ac, at, af = shape
+    return tokens.reshape(ab, at, ac, af).permute(0, 2, 1, 3).to(dtype).contiguous()
+
+
+def denoise_audio_only(audio_latents: Tensor, audio_positions, audio_embeddings: Tensor, transformer: LTXModel,
+                       sigmas: Sequence[float], verbose: bool = False, eval_interval: int = 1, compile_step: bool = False,
+                       compile_shapeless: bool = False, fp32_euler: bool = True, ui_phase: str = "audio_denoise") -> Tensor:
+    """generate.py:888-1058 — distilled-style loop of an AudioOnly transformer (no CFG).  audio_latents (B, 8, Ta, 16)."""
+    dev = transformer.device
+    sig = [float(s) for s in (sigmas.tolist() if hasattr(sigmas, "tolist") else sigmas)]
+    audio_positions = _dev(audio_positions, dev)
+    xa = _audio_to_tokens(audio_latents.to(dev))
+    ones = torch.ones(xa.shape[0], xa.shape[1], dtype=torch.float32, device=dev)
+    rope_a = _audio_rope(transformer, audio_positions)
+    ctx = audio_embeddings.to(dev)
+    for i in range(len(sig) - 1):
+        am = Modality(latent=xa, timesteps=ones * sig[i], positions=audio_positions, context=ctx, context_mask=None,
+                      enabled=True, positional_embeddings=rope_a)
+        _, va = transformer(video=None, audio=am)
+        _advance(xa, va.contiguous(), sig[i], sig[i + 1])
+    return _audio_from_tokens(xa, audio_latents.shape, audio_latents.dtype)
+
+
+def denoise_dev_av(video_latents: Tensor, audio_latents: Tensor, video_positions, audio_positions,
+                   video_embeddings_pos: Tensor, video_embeddings_neg: Tensor, audio_embeddings_pos: Tensor,
+                   audio_embeddings_neg: Tensor, transformer: LTXModel, sigmas, cfg_scale: float = 4.0, verbose: bool = False,
+                   video_state: Optional[LatentState] = None, eval_interval: int = 1, compile_step: bool = False,
+                   compile_shapeless: bool = False, cfg_batch: bool = False, ui_phase: str = "denoise",
+                   cfg_parallel=None) -> Tuple[Tensor, Tensor]:
+    """generate.py:1330-1703 — dev pipeline of the joint audio+video model: classifier-free guidance on BOTH
+    velocities.  ``cfg_batch``: cond and uncond as one B=2 forward (:1572-1598); ``cfg_parallel``
+    (parallel.CFGParallel): on two rank groups, the two velocities exchanged over NCCL."""
+    dev = transformer.device
+    dtype = video_latents.dtype
+    if video_state is not None:
+        video_latents = video_state.latent
+    sig = [float(s) for s in (sigmas.tolist() if hasattr(sigmas, "tolist") else sigmas)]
+    use_cfg = cfg_scale != 1.0
+    cfg_batch = cfg_batch and use_cfg and cfg_parallel is None
+    b, c, f, h, w = video_latents.shape
+    T = f * h * w
+    video_positions, audio_positions = _dev(video_positions, dev), _dev(audio_positions, dev)
+    x = _to_tokens(video_latents.to(dev))
+    xa = _audio_to_tokens(audio_latents.to(dev))
+    ab, at = xa.shape[:2]
+    mask = _token_mask(video_state, b, f, h, w, dev)
+    clean = _to_tokens(video_state.clean_latent.to(dev)) if video_state is not None else None
+    ts_mask = torch.ones(b, T, dtype=torch.float32, device=dev) if mask is None else mask
+    a_ones = torch.ones(ab, at, dtype=torch.float32, device=dev)
+    rope_v, rope_a = _video_rope(transformer, video_positions), _audio_rope(transformer, audio_positions)
+    vp, vn = video_embeddings_pos.to(dev), video_embeddings_neg.to(dev)
+    ap, an = audio_embeddings_pos.to(dev), audio_embeddings_neg.to(dev)
+
+    def twice(t: Tensor) -> Tensor:
+        return torch.cat([t, t], dim=0)
+
+    if cfg_batch:
+        vctx, actx = torch.cat([vp, vn], 0), torch.cat([ap, an], 0)
+        vpos2, apos2 = twice(video_positions), twice(audio_positions)
+        rope_v2 = rope_v if rope_v[0].shape[0] == 1 else (twice(rope_v[0]), twice(rope_v[1]))
+        rope_a2 = rope_a if rope_a[0].shape[0] == 1 else (twice(rope_a[0]), twice(rope_a[1]))
+
+    def forward(vctx_, actx_):
+        return transformer(video=Modality(x, ts, video_positions, vctx_, True, None, rope_v),
+                           audio=Modality(xa, ats, audio_positions, actx_, True, None, rope_a))
+
+    for i in range(len(sig) - 1):
+        sigma, sigma_next = sig[i], sig[i + 1]
+        ts, ats = ts_mask * sigma, a_ones * sigma
+        v_neg = a_neg = None
+        if cfg_parallel is not None and use_cfg:
+            mine_v, mine_a = forward(vp, ap) if cfg_parallel.is_cond else forward(vn, an)
+            v_pos, v_neg = cfg_parallel.exchange(mine_v)
+            a_pos, a_neg = cfg_parallel.exchange(mine_a)
+        elif cfg_batch:
+            vv, aa = transformer(video=Modality(twice(x), twice(ts), vpos2, vctx, True, None, rope_v2),
+                                 audio=Modality(twice(xa), twice(ats), apos2, actx, True, None, rope_a2))
+            v_pos, v_neg, a_pos, a_neg = vv[:b], vv[b:], aa[:ab], aa[ab:]
+        else:
+            v_pos, a_pos = forward(vp, ap)
+            if use_cfg:
+                v_neg, a_neg = forward(vn, an)
+        _advance(x, v_pos.contiguous(), sigma, sigma_next, v_neg=None if v_neg is None else v_neg.contiguous(),
+                 cfg_scale=cfg_scale, mask=mask, clean=clean)
+        _advance(xa, a_pos.contiguous(), sigma, sigma_next, v_neg=None if a_neg is None else a_neg.contiguous(),
+                 cfg_scale=cfg_scale)
+    return _from_tokens(x, (b, c, f, h, w), dtype), _audio_from_tokens(xa, audio_latents.shape, audio_latents.dtype)

@@ -766,3 +766,181 @@ def dequantize_state_dict(weights: Dict[str, object], in_features: Dict[str, int
         else:
             out[k] = v if isinstance(v, Tensor) else torch.from_numpy(np.asarray(v))
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Denoise loops — the direct callers of the forward.  Restate the eager
+# (compile_step=False) branches of mlx_video/generate.py: ``denoise_distilled`` :564-881, ``denoise_audio_only``
+# :888-1058, ``denoise_dev`` :1060-1327, ``denoise_dev_av`` :1330-1703.  Pinned by tests/golden/sampler.npz, which
+# oracle/make_golden_sampler.py produced by running those four functions themselves over the shim.
+# Latents keep the reference layouts: video (B, C, F, H, W), audio (B, 8, Ta, 16).
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class LatentState:  # conditioning/latent.py: latent, clean conditioning latent, per-frame mask (B,1,F,1,1), 1 = denoise
+    latent: Tensor
+    clean_latent: Tensor
+    denoise_mask: Tensor
+
+
+def _video_rope(model: "OracleLTXModel", positions: Tensor):
+    c = model.config
+    return precompute_freqs_cis(positions, c.inner_dim, c.positional_embedding_theta, list(c.positional_embedding_max_pos),
+                                c.use_middle_indices_grid, c.num_attention_heads, c.rope_type, c.double_precision_rope)
+
+
+def _audio_rope(model: "OracleLTXModel", positions: Tensor):
+    c = model.config
+    return precompute_freqs_cis(positions, c.audio_inner_dim, c.positional_embedding_theta,
+                                list(c.audio_positional_embedding_max_pos), c.use_middle_indices_grid,
+                                c.audio_num_attention_heads, c.rope_type, c.double_precision_rope)
+
+
+def _video_tokens(latents: Tensor) -> Tensor:  # generate.py:792
+    b, c = latents.shape[:2]
+    return latents.reshape(b, c, -1).transpose(1, 2)
+
+
+def _audio_tokens(latents: Tensor) -> Tensor:  # generate.py:806-807
+    ab, ac, at, af = latents.shape
+    return latents.permute(0, 2, 1, 3).reshape(ab, at, ac * af)
+
+
+def _audio_from_tokens(v: Tensor, shape) -> Tensor:  # generate.py:826-827
+    ab, ac, at, af = shape
+    return v.reshape(ab, at, ac, af).permute(0, 2, 1, 3)
+
+
+def _timestep_mask(state: Optional[LatentState], b: int, f: int, h: int, w: int, dtype) -> Tensor:  # generate.py:597-606
+    if state is None:
+        return torch.ones(b, f * h * w, dtype=dtype)
+    return state.denoise_mask.reshape(b, 1, f, 1, 1).expand(b, 1, f, h, w).reshape(b, f * h * w).to(dtype)
+
+
+def _step(latents: Tensor, denoised: Tensor, sigma: float, sigma_next: float) -> Tensor:  # generate.py:832-846
+    return euler_step(latents, denoised, sigma, sigma_next) if sigma_next > 0 else denoised
+
+
+def denoise_distilled(latents, positions, text_embeddings, model: "OracleLTXModel", sigmas, state: Optional[LatentState] = None,
+                      audio_latents=None, audio_positions=None, audio_embeddings=None):
+    """generate.py:564-881 (no CFG; optional joint audio)."""
+    dtype = latents.dtype
+    enable_audio = audio_latents is not None
+    if state is not None:
+        latents = state.latent
+    sig = [float(s) for s in sigmas]
+    sig_t = torch.tensor(sig, dtype=dtype)
+    b, c, f, h, w = latents.shape
+    tmask = _timestep_mask(state, b, f, h, w, dtype)
+    rope_v = _video_rope(model, positions)
+    if enable_audio:
+        if audio_positions is None or audio_embeddings is None:
+            raise ValueError("audio_positions/audio_embeddings must be provided when audio_latents is enabled")
+        amask = torch.ones(audio_latents.shape[0], audio_latents.shape[2], dtype=dtype)
+        rope_a = _audio_rope(model, audio_positions)
+    for i in range(len(sig) - 1):
+        vm = Modality(_video_tokens(latents), sig_t[i] * tmask, positions, text_embeddings, True, None, rope_v)
+        am = Modality(_audio_tokens(audio_latents), sig_t[i] * amask, audio_positions, audio_embeddings, True, None,
+                      rope_a) if enable_audio else None
+        v, va = model(vm, am)
+        den = to_denoised(latents, v.transpose(1, 2).reshape(b, c, f, h, w), sig_t[i])
+        if state is not None:
+            den = apply_denoise_mask(den, state.clean_latent, state.denoise_mask)
+        latents = _step(latents, den, sig[i], sig[i + 1])
+        if enable_audio and va is not None:
+            aden = to_denoised(audio_latents, _audio_from_tokens(va, audio_latents.shape), sig_t[i])
+            audio_latents = _step(audio_latents, aden, sig[i], sig[i + 1])
+    return latents, (audio_latents if enable_audio else None)
+
+
+def denoise_audio_only(audio_latents, audio_positions, audio_embeddings, model: "OracleLTXModel", sigmas):
+    """generate.py:888-1058 (AudioOnly transformer, no CFG)."""
+    dtype = audio_latents.dtype
+    sig = [float(s) for s in sigmas]
+    sig_t = torch.tensor(sig, dtype=dtype)
+    amask = torch.ones(audio_latents.shape[0], audio_latents.shape[2], dtype=dtype)
+    rope_a = _audio_rope(model, audio_positions)
+    for i in range(len(sig) - 1):
+        am = Modality(_audio_tokens(audio_latents), sig_t[i] * amask, audio_positions, audio_embeddings, True, None, rope_a)
+        _, va = model(None, am)
+        aden = to_denoised(audio_latents, _audio_from_tokens(va, audio_latents.shape), sig_t[i])
+        audio_latents = _step(audio_latents, aden, sig[i], sig[i + 1])
+    return audio_latents
+
+
+def denoise_dev(latents, positions, text_embeddings_pos, text_embeddings_neg, model: "OracleLTXModel", sigmas,
+                cfg_scale: float = 4.0, state: Optional[LatentState] = None, cfg_batch: bool = False):
+    """generate.py:1060-1327 (CFG; ``cfg_batch`` = cond and uncond as one B=2 forward, :1239-1255)."""
+    dtype = latents.dtype
+    if state is not None:
+        latents = state.latent
+    sig = [float(s) for s in (sigmas.tolist() if hasattr(sigmas, "tolist") else sigmas)]
+    sig_t = torch.tensor(sig, dtype=torch.float32).to(dtype)
+    use_cfg = cfg_scale != 1.0
+    cfg_batch = cfg_batch and use_cfg
+    b, c, f, h, w = latents.shape
+    tmask = _timestep_mask(state, b, f, h, w, dtype)
+    rope = _video_rope(model, positions)
+    for i in range(len(sig) - 1):
+        flat, ts = _video_tokens(latents), sig_t[i] * tmask
+        if cfg_batch:
+            vv, _ = model(Modality(torch.cat([flat, flat], 0), torch.cat([ts, ts], 0), positions.expand(2 * b, *positions.shape[1:]),
+                                   torch.cat([text_embeddings_pos, text_embeddings_neg], 0), True, None,
+                                   tuple(t.expand(2 * b, *t.shape[1:]) for t in rope)), None)
+            v = cfg_combine(vv[:b], vv[b:], cfg_scale)
+        else:
+            v, _ = model(Modality(flat, ts, positions, text_embeddings_pos, True, None, rope), None)
+            if use_cfg:
+                vn, _ = model(Modality(flat, ts, positions, text_embeddings_neg, True, None, rope), None)
+                v = cfg_combine(v, vn, cfg_scale)
+        den = to_denoised(latents, v.transpose(1, 2).reshape(b, c, f, h, w), sig_t[i])
+        if state is not None:
+            den = apply_denoise_mask(den, state.clean_latent, state.denoise_mask)
+        latents = _step(latents, den, sig[i], sig[i + 1])
+    return latents
+
+
+def denoise_dev_av(video_latents, audio_latents, video_positions, audio_positions, video_embeddings_pos, video_embeddings_neg,
+                   audio_embeddings_pos, audio_embeddings_neg, model: "OracleLTXModel", sigmas, cfg_scale: float = 4.0,
+                   video_state: Optional[LatentState] = None, cfg_batch: bool = False):
+    """generate.py:1330-1703 (CFG on both modalities of the joint audio+video model)."""
+    dtype = video_latents.dtype
+    if video_state is not None:
+        video_latents = video_state.latent
+    sig = [float(s) for s in (sigmas.tolist() if hasattr(sigmas, "tolist") else sigmas)]
+    sig_t = torch.tensor(sig, dtype=torch.float32).to(dtype)
+    use_cfg = cfg_scale != 1.0
+    cfg_batch = cfg_batch and use_cfg
+    b, c, f, h, w = video_latents.shape
+    ab = audio_latents.shape[0]
+    tmask = _timestep_mask(video_state, b, f, h, w, dtype)
+    amask = torch.ones(ab, audio_latents.shape[2], dtype=dtype)
+    rope_v, rope_a = _video_rope(model, video_positions), _audio_rope(model, audio_positions)
+
+    def twice(t: Tensor) -> Tensor:
+        return torch.cat([t, t], 0)
+
+    for i in range(len(sig) - 1):
+        vflat, aflat = _video_tokens(video_latents), _audio_tokens(audio_latents)
+        vts, ats = sig_t[i] * tmask, sig_t[i] * amask
+        if cfg_batch:
+            vv, av = model(Modality(twice(vflat), twice(vts), video_positions.expand(2 * b, *video_positions.shape[1:]),
+                                    torch.cat([video_embeddings_pos, video_embeddings_neg], 0), True, None,
+                                    tuple(t.expand(2 * b, *t.shape[1:]) for t in rope_v)),
+                           Modality(twice(aflat), twice(ats), audio_positions.expand(2 * ab, *audio_positions.shape[1:]),
+                                    torch.cat([audio_embeddings_pos, audio_embeddings_neg], 0), True, None,
+                                    tuple(t.expand(2 * ab, *t.shape[1:]) for t in rope_a)))
+            v, va = cfg_combine(vv[:b], vv[b:], cfg_scale), cfg_combine(av[:ab], av[ab:], cfg_scale)
+        else:
+            v, va = model(Modality(vflat, vts, video_positions, video_embeddings_pos, True, None, rope_v),
+                          Modality(aflat, ats, audio_positions, audio_embeddings_pos, True, None, rope_a))
+            if use_cfg:
+                vn, van = model(Modality(vflat, vts, video_positions, video_embeddings_neg, True, None, rope_v),
+                                Modality(aflat, ats, audio_positions, audio_embeddings_neg, True, None, rope_a))
+                v, va = cfg_combine(v, vn, cfg_scale), cfg_combine(va, van, cfg_scale)
+        vden = to_denoised(video_latents, v.transpose(1, 2).reshape(b, c, f, h, w), sig_t[i])
+        aden = to_denoised(audio_latents, _audio_from_tokens(va, audio_latents.shape), sig_t[i])
+        if video_state is not None:
+            vden = apply_denoise_mask(vden, video_state.clean_latent, video_state.denoise_mask)
+        video_latents = _step(video_latents, vden, sig[i], sig[i + 1])
+        audio_latents = _step(audio_latents, aden, sig[i], sig[i + 1])
+    return video_latents, audio_latents

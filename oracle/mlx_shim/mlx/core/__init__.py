@@ -157,6 +157,14 @@ def concatenate(arrs, axis=0):
     return _w(_torch.cat([_unwrap(a) for a in arrs], dim=axis))
 
 
+def split(a, indices_or_sections, axis=0):
+    """mx.split: an int = that many equal sections; a list = split points."""
+    t = _unwrap(a)
+    if isinstance(indices_or_sections, int):
+        return [_w(x) for x in _torch.chunk(t, indices_or_sections, dim=axis)]
+    return [_w(x) for x in _torch.tensor_split(t, list(indices_or_sections), dim=axis)]
+
+
 def stack(arrs, axis=0):
     return _w(_torch.stack([_unwrap(a) for a in arrs], dim=axis))
 
