@@ -266,6 +266,18 @@ class LTXModel:
             dst.copy_(src.to(device=dst.device, dtype=dst.dtype))  # plumbing: H2D copy + storage cast
         self.clear_caches()  # projected-context caches and captured graphs belong to the old weights
 
+    def sanitize(self, weights: Dict[str, Tensor]) -> Dict[str, Tensor]:
+        """ltx.py:508-533: upstream (``model.diffusion_model.*``) names -> parameter names; every tensor without that
+        prefix, and the embeddings connectors, are dropped.  Values are passed through untouched."""
+        from .checkpoint import PREFIX, sanitize_key
+
+        out: Dict[str, Tensor] = {}
+        for key, value in weights.items():
+            name = sanitize_key(key) if key.startswith(PREFIX) else None
+            if name is not None:
+                out[name] = value
+        return out
+
     def init_random(self, seed: int = 0, table_std: float = 0.02) -> "LTXModel":
         """Random-init weights of the reference architecture, generated on the device (there is no
         checkpoint offline): Linear U(+-1/sqrt(in)) like nn.Linear, norm weights 1 + 0.1 N(0,1), tables

@@ -110,3 +110,16 @@ def test_checkpoint_key_mapping_and_safetensors_roundtrip(tmp_path):
     assert sorted(ck.load_transformer_weights(tmp_path / "u.safetensors")) == ["patchify_proj.bias"]
     with pytest.raises(FileNotFoundError):
         ck.load_transformer_weights(tmp_path / "empty_dir_that_does_not_exist")
+
+
+def test_model_sanitize_matches_reference_key_mapping():
+    """LTXModel.sanitize (ltx.py:508-533) needs no device: unbound call on a bare object."""
+    from mlx_video_b200.model import LTXModel
+
+    P = "model.diffusion_model."
+    w = {P + "transformer_blocks.0.attn1.to_out.0.weight": 1, P + "transformer_blocks.0.ff.net.2.bias": 2,
+         P + "caption_projection.linear_1.weight": 3, P + "audio_embeddings_connector.x": 4, "vae.decoder.w": 5,
+         "patchify_proj.weight": 6}
+    got = LTXModel.sanitize(None, w)
+    assert got == {"transformer_blocks.0.attn1.to_out.weight": 1, "transformer_blocks.0.ff.proj_out.bias": 2,
+                   "caption_projection.linear1.weight": 3}
