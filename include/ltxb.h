@@ -262,6 +262,36 @@ int ltxb_dequant_affine_bf16(const uint32_t* wq, int64_t ldq, const void* scales
                              int32_t bits, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * N4  latent 2x spatial upsampler between the pipeline stages (mlx_video/models/ltx/upsampler.py).
+ *     Activations: f32, channels-last [N, D, H, W, C].  Every convolution is ltxb_gemm_bf16 over the rows built here.
+ * ---------------------------------------------------------------------------------------------- */
+/* Conv3d / nn.Conv2d operand (upsampler.py:51-72,149,163; mx.conv3d, stride 1, "same" zero padding):
+ *   out bf16 [N*D*H*W, kd*kh*kw*C], out[m, ((kz*kh + ky)*kw + kx)*C + c] = x[n, d+kz-kd/2, h+ky-kh/2, w+kx-kw/2, c]
+ *   — the K order of the reference's weight layout (C_out, kd, kh, kw, C_in), which is therefore the GEMM's W as stored.
+ *   kd = 1 gives the frame-by-frame 2-D convolution of SpatialRationalResampler.  C % 8 == 0, odd kernel sizes. */
+int ltxb_im2col_cl(const float* x, void* out, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C, int32_t kd, int32_t kh,
+                   int32_t kw, void* stream);
+
+/* GroupNorm3d (upsampler.py:85-114: f32 statistics per sample and group over S = D*H*W positions x C/G channels,
+ * population variance, eps inside the sqrt) fused with what follows it in ResBlock3D / LatentUpsampler
+ * (upsampler.py:189-197,258-262):  out = silu?( (x - mean_g) * rstd_g * weight[c] + bias[c] [+ resid] ).
+ *   x, out, resid: f32 [N, S, C] (out may alias x);  two launches (per-chunk partial sums, then one pass).
+ *   workspace: caller-owned scratch of ltxb_groupnorm_workspace_bytes(N, S, G) bytes.  C <= 1024, C % G == 0, G <= 64. */
+int64_t ltxb_groupnorm_workspace_bytes(int32_t N, int64_t S, int32_t G);
+int ltxb_groupnorm_silu(const float* x, float* out, int32_t N, int64_t S, int32_t C, int32_t G, float eps, const float* weight,
+                        const float* bias, const float* resid, int32_t silu, void* workspace, int64_t workspace_bytes,
+                        void* stream);
+
+/* PixelShuffle2D(2) (upsampler.py:124-139): x f32 [F, H, W, 4*Co] -> out f32 [F, 2H, 2W, Co], input channel (co*2 + rh)*2 + rw. */
+int ltxb_pixel_shuffle2(const float* x, float* out, int64_t F, int32_t H, int32_t W, int32_t Co, void* stream);
+
+/* The layout moves of LatentUpsampler.__call__ (upsampler.py:250,290) carrying upsample_latents' un- / re-normalisation
+ * (upsampler.py:305-314): to_channels_last != 0: x f32 (B, C, S) -> out (B, S, C), out = x * scale[c] + shift[c];
+ * else x (B, S, C) -> out (B, C, S), out = (x - shift[c]) / scale[c].  scale = shift = NULL: plain transposition. */
+int ltxb_latent_layout(const float* x, float* out, const float* scale, const float* shift, int64_t B, int32_t C, int64_t S,
+                       int32_t to_channels_last, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * a21/a22 sampler-side elementwise (utils.py:404-440; generate.py:1255,1283,1288-1301)
  *   CFG combine + to_denoised + fp32 Euler in one pass over the latent:
  *     v  = v_pos + (cfg_scale - 1) (v_pos - v_neg)           (v_neg NULL -> v = v_pos)

@@ -14,5 +14,6 @@ from .config import (AttentionType, LTXModelConfig, LTXModelType, LTXRopeType, T
 from .lora import LoraSpec, apply_lora_to_model, apply_lora_to_weights  # noqa: F401
 from .model import AdaLayerNormSingle, LTXModel, PixArtAlphaTextProjection, X0Model, to_denoised  # noqa: F401
 from .rope import precompute_freqs_cis  # noqa: F401
+from .upsampler import LatentUpsampler, load_upsampler, upsample_latents  # noqa: F401
 from .transformer import (Attention, BasicAVTransformerBlock, FeedForward, Modality, TransformerArgs,  # noqa: F401
                           Workspace)

@@ -71,6 +71,11 @@ SIGNATURES = {
     "ltxb_attention_set_workspace": (C.c_int, [_vp, _i64]),
     "ltxb_lora_merge_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _f32, _vp]),
     "ltxb_dequant_affine_bf16": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
+    "ltxb_im2col_cl": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "ltxb_groupnorm_workspace_bytes": (C.c_int64, [_i32, _i64, _i32]),
+    "ltxb_groupnorm_silu": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _i32, _vp, _i64, _vp]),
+    "ltxb_pixel_shuffle2": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "ltxb_latent_layout": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _i32, _vp]),
     "ltxb_euler_step": (C.c_int, [_vp, _vp, _vp, _f32, _vp, _f32, _f32, _vp, _vp, _i64, _i32, _vp, _vp]),
 }
 

@@ -246,6 +246,59 @@ def lora_merge(w: torch.Tensor, delta: torch.Tensor, strength: float) -> torch.T
     return w
 
 
+def im2col_cl(x: torch.Tensor, out: torch.Tensor, kd: int, kh: int, kw: int) -> torch.Tensor:
+    """x f32 channels-last (N, D, H, W, C) -> out bf16 [N*D*H*W, kd*kh*kw*C]: the conv's GEMM operand (ltxb.h N4)."""
+    _prep(x)
+    N, D, H, W, Cc = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
+    assert out.shape == (N * D * H * W, kd * kh * kw * Cc)
+    _call("ltxb_im2col_cl", 0.0, x.data_ptr(), out.data_ptr(), N, D, H, W, Cc, kd, kh, kw, _stream())
+    return out
+
+
+_gn_workspaces: dict = {}  # device index -> GroupNorm partial-sum scratch (grown on demand; torch owns the memory)
+
+
+def groupnorm_silu(x: torch.Tensor, out: torch.Tensor, groups: int, eps: float, weight: torch.Tensor, bias: torch.Tensor,
+                   resid: Optional[torch.Tensor] = None, silu: bool = True) -> torch.Tensor:
+    """out = silu?(GroupNorm(x) * weight + bias [+ resid]) on f32 (N, S, C) (channels-last, any number of middle axes)."""
+    _prep(x)
+    for t in (x, out, weight, bias, resid):
+        assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
+    N, Cc = x.shape[0], x.shape[-1]
+    S = x.numel() // (N * Cc)
+    need = lib.ltxb_groupnorm_workspace_bytes(N, S, groups)
+    ws = _gn_workspaces.get(x.device.index)
+    if ws is None or ws.numel() < need:
+        ws = _gn_workspaces[x.device.index] = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=x.device)
+    _call("ltxb_groupnorm_silu", 0.0, x.data_ptr(), out.data_ptr(), N, S, Cc, groups, eps, weight.data_ptr(), bias.data_ptr(),
+          _ptr(resid), int(silu), ws.data_ptr(), ws.numel(), _stream())
+    return out
+
+
+def pixel_shuffle2(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """x f32 (F, H, W, 4*Co) -> out f32 (F, 2H, 2W, Co)."""
+    _prep(x)
+    F_, H, W, C4 = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous() and out.shape == (F_, 2 * H, 2 * W, C4 // 4)
+    _call("ltxb_pixel_shuffle2", 0.0, x.data_ptr(), out.data_ptr(), F_, H, W, C4 // 4, _stream())
+    return out
+
+
+def latent_layout(x: torch.Tensor, out: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
+                  to_channels_last: bool) -> torch.Tensor:
+    """(B, C, S) <-> (B, S, C) on f32, with the per-channel (un)normalisation of upsample_latents folded in."""
+    _prep(x)
+    for t in (x, out, scale, shift):
+        assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
+    if to_channels_last:
+        B, Cc, S = x.shape
+    else:
+        B, S, Cc = x.shape
+    _call("ltxb_latent_layout", 0.0, x.data_ptr(), out.data_ptr(), _ptr(scale), _ptr(shift), B, Cc, S, int(to_channels_last), _stream())
+    return out
+
+
 def dequant_affine(packed: torch.Tensor, scales: torch.Tensor, biases: torch.Tensor, out: torch.Tensor, group_size: int,
                    bits: int) -> torch.Tensor:
     """out (bf16 [R, C], row-strided view allowed) <- scales * q + biases of an MLX affine-quantised weight

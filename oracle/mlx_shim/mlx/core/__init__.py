@@ -198,6 +198,35 @@ def mean(a, axis=None, keepdims=False):
     return _w(t.mean() if axis is None else t.mean(dim=axis, keepdim=keepdims))
 
 
+def var(a, axis=None, keepdims=False, ddof=0):
+    """mx.var: population variance by default (ddof=0)."""
+    t = _unwrap(a)
+    if axis is None:
+        return _w(t.var(correction=ddof))
+    return _w(t.var(dim=axis, keepdim=keepdims, correction=ddof))
+
+
+def _conv_nd(x, w, stride, padding, dilation, groups, nd):
+    """mx.conv2d / mx.conv3d: channels-last input (N, *spatial, C_in), weight (C_out, *kernel, C_in / groups);
+    cross-correlation like torch's conv, computed in the promoted dtype."""
+    t, k = _unwrap(x), _unwrap(w)
+    dt = _torch.promote_types(t.dtype, k.dtype)
+    perm_in = (0, nd + 1) + tuple(range(1, nd + 1))          # -> channels first
+    perm_w = (0, nd + 1) + tuple(range(1, nd + 1))
+    perm_out = (0,) + tuple(range(2, nd + 2)) + (1,)          # -> channels last
+    fn = _torch.nn.functional.conv3d if nd == 3 else _torch.nn.functional.conv2d
+    y = fn(t.to(dt).permute(*perm_in), k.to(dt).permute(*perm_w), None, stride, padding, dilation, groups)
+    return _w(y.permute(*perm_out).contiguous())
+
+
+def conv3d(x, w, stride=1, padding=0, dilation=1, groups=1):
+    return _conv_nd(x, w, stride, padding, dilation, groups, 3)
+
+
+def conv2d(x, w, stride=1, padding=0, dilation=1, groups=1):
+    return _conv_nd(x, w, stride, padding, dilation, groups, 2)
+
+
 def power(a, b):
     a, b = _unwrap(a), _unwrap(b)
     if not isinstance(a, _torch.Tensor):
@@ -282,6 +311,7 @@ def _sdpa(q, k, v, *, scale, mask=None):
 fast = _NS(rms_norm=_rms_norm, scaled_dot_product_attention=_sdpa)
 random = _NS(
     normal=lambda shape, dtype=float32, key=None: _w(_torch.randn(tuple(shape)).to(dtype)),
+    uniform=lambda low=0.0, high=1.0, shape=(), dtype=float32, key=None: _w((_torch.rand(tuple(shape)) * (high - low) + low).to(dtype)),
     seed=lambda s: _torch.manual_seed(s),
 )
 metal = _NS(start_capture=lambda *a, **k: None, stop_capture=lambda *a, **k: None)
@@ -341,5 +371,10 @@ def quantized_matmul(x, w, scales, biases, transpose=True, group_size=64, bits=4
     return _w(y.to(dt))
 
 
-def load(*a, **k):
-    raise NotImplementedError("mlx shim: checkpoint IO is out of scope for golden generation")
+def load(path, *a, **k):
+    """mx.load of a safetensors file -> dict of arrays (the only format the reference's loaders hand it here)."""
+    if not str(path).endswith(".safetensors"):
+        raise NotImplementedError("mlx shim: only safetensors files")
+    from safetensors.torch import load_file
+
+    return {key: _w(t) for key, t in load_file(str(path)).items()}

@@ -113,6 +113,23 @@ class Linear(Module):
         return mx.array(_torch.nn.functional.linear(x._t.to(dt), w.to(dt), None if b is None else b.to(dt)))
 
 
+class Conv2d(Module):
+    """mlx nn.Conv2d: NHWC input, weight (out, kh, kw, in), default init U(+-1/sqrt(in*kh*kw)), zero bias."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True):
+        super().__init__()
+        ks = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
+        k = 1.0 / _math.sqrt(in_channels * ks[0] * ks[1])
+        self.weight = mx.array((_torch.rand(out_channels, ks[0], ks[1], in_channels // groups) * 2 - 1) * k)
+        if bias:
+            self.bias = mx.zeros((out_channels,))
+        self.stride, self.padding, self.dilation, self.groups = stride, padding, dilation, groups
+
+    def __call__(self, x):
+        y = mx.conv2d(x, self.weight, self.stride, self.padding, self.dilation, self.groups)
+        return y + self.bias if "bias" in self.__dict__ else y
+
+
 class RMSNorm(Module):
     def __init__(self, dims, eps=1e-5):
         super().__init__()
