@@ -3,7 +3,7 @@
 // cores: activations stay channels-last fp32 [N, D, H, W, C]; `im2col_cl_kernel` gathers the (zero-padded) taps of every
 // output position into a bf16 row [kd*kh*kw*C] — the reference's weight layout (C_out, kd, kh, kw, C_in) IS the GEMM's
 // W [N, K] operand, so no weight shuffle exists — and ltxb_gemm_bf16 (bias epilogue, fp32 out) does the contraction.
-// Around it: GroupNorm (two passes: per-chunk partial sums, then normalise + affine [+ residual] + SiLU in one pass),
+// Around it: GroupNorm (per-chunk partial sums, a fold into mean / rstd, then normalise + affine [+ residual] + SiLU in one pass),
 // pixel shuffle, and the channels-first <-> channels-last moves that also carry the VAE un-/re-normalisation.
 // All memory-bound, 128-bit vectorised where the layout allows; sizes are tiny next to the DiT (one call per video).
 #include "common.cuh"
@@ -17,7 +17,9 @@ static int conv_grid_for(long long work_items, int threads) {
   return static_cast<int>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 
-// out[m, ((kz*kh + ky)*kw + kx)*C + c] = x[n, d+kz-pd, h+ky-ph, w+kx-pw, c] (0 outside), m = ((n*D + d)*H + h)*W + w
+// out[m, ((kz*kh + ky)*kw + kx)*C + c] = x[n, d+kz-pd, h+ky-ph, w+kx-pw, c] (0 outside), m = ((n*D + d)*H + h)*W + w.
+// One warp per output position: the position is decoded once, every tap is a contiguous C-channel run (fp32 in,
+// bf16 out, 32 B read / 16 B written per lane and step) — the stores of a warp cover whole 512-byte spans of the row.
 __global__ void __launch_bounds__(256)
 im2col_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int D, int H, int W, int C, int kd,
                  int kh, int kw) {
@@ -25,29 +27,38 @@ im2col_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, i
   pdl_wait();
   const int c8 = C / 8, taps = kd * kh * kw;
   const int pd = kd / 2, ph = kh / 2, pw = kw / 2;
+  const int lane = threadIdx.x & 31;
   const long long M = static_cast<long long>(N) * D * H * W;
-  const long long total = M * taps * c8;
-  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
-    const int cc = static_cast<int>(i % c8);
-    long long r = i / c8;
-    const int tap = static_cast<int>(r % taps);
-    const long long m = r / taps;
-    const int kx = tap % kw, ky = (tap / kw) % kh, kz = tap / (kw * kh);
+  for (long long m = blockIdx.x * 8ll + (threadIdx.x >> 5); m < M; m += 8ll * gridDim.x) {
     const int w = static_cast<int>(m % W);
     long long q = m / W;
     const int h = static_cast<int>(q % H);
     q /= H;
     const int d = static_cast<int>(q % D);
     const long long n = q / D;
-    const int sd = d + kz - pd, sh = h + ky - ph, sw = w + kx - pw;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (sd >= 0 && sd < D && sh >= 0 && sh < H && sw >= 0 && sw < W) {
-      const float* src = x + (((n * D + sd) * H + sh) * static_cast<long long>(W) + sw) * C + cc * 8;
-      const float4 a = *reinterpret_cast<const float4*>(src);
-      const float4 b = *reinterpret_cast<const float4*>(src + 4);
-      v.x = pack_bf16x2(a.x, a.y), v.y = pack_bf16x2(a.z, a.w), v.z = pack_bf16x2(b.x, b.y), v.w = pack_bf16x2(b.z, b.w);
+    __nv_bfloat16* orow = out + m * taps * static_cast<long long>(C);
+    int tap = 0;
+    for (int kz = 0; kz < kd; ++kz) {
+      const int sd = d + kz - pd;
+      for (int ky = 0; ky < kh; ++ky) {
+        const int sh = h + ky - ph;
+        for (int kx = 0; kx < kw; ++kx, ++tap) {
+          const int sw = w + kx - pw;
+          const bool inside = sd >= 0 && sd < D && sh >= 0 && sh < H && sw >= 0 && sw < W;
+          const float* src = x + (((n * D + sd) * H + sh) * static_cast<long long>(W) + sw) * C;  // only dereferenced when inside
+          __nv_bfloat16* dst = orow + static_cast<long long>(tap) * C;
+          for (int cc = lane; cc < c8; cc += 32) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (inside) {
+              const float4 a = *reinterpret_cast<const float4*>(src + cc * 8);
+              const float4 b = *reinterpret_cast<const float4*>(src + cc * 8 + 4);
+              v.x = pack_bf16x2(a.x, a.y), v.y = pack_bf16x2(a.z, a.w), v.z = pack_bf16x2(b.x, b.y), v.w = pack_bf16x2(b.z, b.w);
+            }
+            *reinterpret_cast<uint4*>(dst + cc * 8) = v;
+          }
+        }
+      }
     }
-    *reinterpret_cast<uint4*>(out + (m * taps + tap) * static_cast<long long>(C) + cc * 8) = v;
   }
 }
 
@@ -79,29 +90,50 @@ groupnorm_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial
   }
 }
 
-// pass 2: y = silu?( (x - mean_g) * rstd_g * weight[c] + bias[c] [+ resid] ), fp32 in place or out of place.
-// Every CTA first folds the chunk partials of its sample (in double, fixed order) into mean / rstd per group.
+// pass 2: the chunk partials of every (sample, group) folded into (mean, rstd) — in double, fixed order, 8 threads per
+// group — so that the apply pass reads 2 floats per group instead of walking all partials in every CTA
+__global__ void __launch_bounds__(256)
+groupnorm_finalize_kernel(const float2* __restrict__ partial, float2* __restrict__ stats, int chunks, int S, int C, int G, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ double s_a[256], s_b[256];
+  const int n = blockIdx.x;
+  const int g = threadIdx.x >> 3, j = threadIdx.x & 7;  // 32 groups x 8 lanes per pass
+  for (int g0 = 0; g0 < G; g0 += 32) {
+    double a = 0.0, b = 0.0;
+    if (g0 + g < G) {
+      for (int k = j; k < chunks; k += 8) {
+        const float2 p = partial[(static_cast<long long>(n) * chunks + k) * G + g0 + g];
+        a += p.x, b += p.y;
+      }
+    }
+    s_a[threadIdx.x] = a, s_b[threadIdx.x] = b;
+    __syncthreads();
+    if (j == 0 && g0 + g < G) {
+      for (int t = 1; t < 8; ++t) a += s_a[threadIdx.x + t], b += s_b[threadIdx.x + t];
+      const double cnt = static_cast<double>(S) * (C / G);
+      const double mean = a / cnt;
+      const double var = fmax(b / cnt - mean * mean, 0.0);
+      stats[static_cast<long long>(n) * G + g0 + g] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+    }
+    __syncthreads();
+  }
+}
+
+// pass 3: y = silu?( (x - mean_g) * rstd_g * weight[c] + bias[c] [+ resid] ), fp32 in place or out of place.
 template <bool kResidual, bool kSilu>
 __global__ void __launch_bounds__(256)
-groupnorm_apply_kernel(const float* __restrict__ x, float* __restrict__ out, const float2* __restrict__ partial, int chunks,
+groupnorm_apply_kernel(const float* __restrict__ x, float* __restrict__ out, const float2* __restrict__ stats,
                        const float* __restrict__ weight, const float* __restrict__ bias, const float* __restrict__ resid,
-                       int S, int C, int G, float eps, int rows_per_cta) {
+                       int S, int C, int G, int rows_per_cta) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_mean[64], s_rstd[64];
   const int n = blockIdx.y;
   const int cpg = C / G;
   for (int g = threadIdx.x; g < G; g += 256) {
-    double a = 0.0, b = 0.0;
-    for (int k = 0; k < chunks; ++k) {
-      const float2 p = partial[(static_cast<long long>(n) * chunks + k) * G + g];
-      a += p.x, b += p.y;
-    }
-    const double cnt = static_cast<double>(S) * cpg;
-    const double mean = a / cnt;
-    const double var = fmax(b / cnt - mean * mean, 0.0);
-    s_mean[g] = static_cast<float>(mean);
-    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float2 st = stats[static_cast<long long>(n) * G + g];
+    s_mean[g] = st.x, s_rstd[g] = st.y;
   }
   __syncthreads();
   const int c4 = C / 4;
@@ -185,35 +217,38 @@ extern "C" int ltxb_im2col_cl(const float* x, void* out, int32_t N, int32_t D, i
   LTXB_CHECK_ARG(N > 0 && D > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "ltxb_im2col_cl: bad shape (C must be a multiple of 8)");
   LTXB_CHECK_ARG(kd >= 1 && kh >= 1 && kw >= 1 && (kd & 1) && (kh & 1) && (kw & 1), "ltxb_im2col_cl: odd kernel sizes only (same padding)");
   LTXB_CHECK_ARG(aligned16(x) && aligned16(out), "ltxb_im2col_cl: misaligned");
-  const long long work = static_cast<long long>(N) * D * H * W * kd * kh * kw * (C / 8);
-  LTXB_CUDA(launch_kernel(im2col_cl_kernel, dim3(conv_grid_for(work, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, x,
+  const long long rows = static_cast<long long>(N) * D * H * W;  // one warp per output position, 8 per CTA
+  LTXB_CUDA(launch_kernel(im2col_cl_kernel, dim3(conv_grid_for(rows * 32, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, x,
                           reinterpret_cast<__nv_bfloat16*>(out), N, D, H, W, C, kd, kh, kw));
   return LTXB_OK;
 }
 
+constexpr int kGnRows = 16;  // rows per CTA: 320 CTAs per sample at 5 x 32 x 32 positions
 extern "C" int64_t ltxb_groupnorm_workspace_bytes(int32_t N, int64_t S, int32_t G) {
-  const long long chunks = (S + 63) / 64;
-  return static_cast<int64_t>(N) * chunks * G * sizeof(float2);
+  const long long chunks = (S + kGnRows - 1) / kGnRows;
+  return static_cast<int64_t>(N) * (chunks + 1) * G * sizeof(float2);  // per-chunk partials + the (mean, rstd) table
 }
 
 extern "C" int ltxb_groupnorm_silu(const float* x, float* out, int32_t N, int64_t S, int32_t C, int32_t G, float eps,
                                    const float* weight, const float* bias, const float* resid, int32_t silu, void* workspace,
                                    int64_t workspace_bytes, void* stream) {
   LTXB_CHECK_ARG(x && out && weight && bias && workspace, "ltxb_groupnorm_silu: null pointer");
-  LTXB_CHECK_ARG(N > 0 && S > 0 && S < (1ll << 31) && C > 0 && G > 0 && G <= 64 && C % G == 0 && C % 4 == 0 && C <= kGnMaxC,
+  LTXB_CHECK_ARG(N > 0 && N <= 65535 && S > 0 && S < (1ll << 31) && C > 0 && G > 0 && G <= 64 && C % G == 0 && C % 4 == 0 && C <= kGnMaxC,
                  "ltxb_groupnorm_silu: bad shape N=%d S=%lld C=%d G=%d (C <= %d, C %% G == 0, C %% 4 == 0, G <= 64)", N,
                  static_cast<long long>(S), C, G, kGnMaxC);
   LTXB_CHECK_ARG(aligned16(x) && aligned16(out) && aligned16(weight) && aligned16(bias) && aligned16(workspace) &&
                      (resid == nullptr || aligned16(resid)), "ltxb_groupnorm_silu: misaligned");
   LTXB_CHECK_ARG(workspace_bytes >= ltxb_groupnorm_workspace_bytes(N, S, G), "ltxb_groupnorm_silu: workspace too small");
-  const int rows = 64;
-  const int chunks = static_cast<int>((S + rows - 1) / rows);
+  const int chunks = static_cast<int>((S + kGnRows - 1) / kGnRows);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   float2* partial = reinterpret_cast<float2*>(workspace);
-  LTXB_CUDA(launch_kernel(groupnorm_stats_kernel, dim3(chunks, N), dim3(256), 0, s, 1, x, partial, static_cast<int>(S), C, G, rows));
+  float2* stats = partial + static_cast<long long>(N) * chunks * G;
+  LTXB_CUDA(launch_kernel(groupnorm_stats_kernel, dim3(chunks, N), dim3(256), 0, s, 1, x, partial, static_cast<int>(S), C, G, kGnRows));
+  LTXB_CUDA(launch_kernel(groupnorm_finalize_kernel, dim3(N), dim3(256), 0, s, 1, static_cast<const float2*>(partial), stats, chunks,
+                          static_cast<int>(S), C, G, eps));
 #define LTXB_GN_APPLY(R, A)                                                                                               \
-  LTXB_CUDA(launch_kernel(groupnorm_apply_kernel<R, A>, dim3(chunks, N), dim3(256), 0, s, 1, x, out, static_cast<const float2*>(partial), \
-                          chunks, weight, bias, resid, static_cast<int>(S), C, G, eps, rows))
+  LTXB_CUDA(launch_kernel(groupnorm_apply_kernel<R, A>, dim3(chunks, N), dim3(256), 0, s, 1, x, out, static_cast<const float2*>(stats), \
+                          weight, bias, resid, static_cast<int>(S), C, G, kGnRows))
   if (resid != nullptr) {
     if (silu) LTXB_GN_APPLY(true, true); else LTXB_GN_APPLY(true, false);
   } else {
