@@ -1,5 +1,7 @@
 #!/bin/bash
 # Timing experiment: the hot GEMM shapes with the default library and with variant builds named on the command line.
+# (The skip-A / skip-W timing macros used for profiles/r1e/gemm_operand_delivery_exp.txt live in
+#  profiles/r1e/quad_multicast_experiment.patch, not in the product sources.)
 # Usage: bash scripts/gemm_exp.sh <tag> <variant> [<variant> ...]   (variants are libltxb_<variant>.so; "base" = libltxb.so)
 tag=$1; shift
 out=gpurun_out/$tag; mkdir -p $out
