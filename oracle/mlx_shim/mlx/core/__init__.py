@@ -69,7 +69,29 @@ class array:
             idx = tuple(_unwrap(i) for i in idx)
         else:
             idx = _unwrap(idx)
+        # mlx (like numpy) allows negative slice steps; torch does not: reverse those axes with flip
+        items = idx if isinstance(idx, tuple) else (idx,)
+        if any(isinstance(i, slice) and i.step is not None and i.step < 0 for i in items):
+            t, fixed, axis = self._t, [], 0
+            for i in items:
+                if i is None:
+                    fixed.append(i)
+                    continue
+                if isinstance(i, slice) and i.step is not None and i.step < 0:
+                    sel = list(range(t.shape[axis]))[i]
+                    t = t.index_select(axis, _torch.tensor(sel, dtype=_torch.long))
+                    fixed.append(slice(None))
+                else:
+                    fixed.append(i)
+                if not isinstance(i, int):
+                    axis += 1
+                else:
+                    axis += 1
+            return array(t[tuple(fixed)])
         return array(self._t[idx])
+
+    def flatten(self):
+        return array(self._t.flatten())
 
     def __array__(self, dtype=None):
         a = self._t.detach().float().numpy() if self._t.dtype == _torch.bfloat16 else self._t.detach().numpy()
@@ -171,6 +193,14 @@ def stack(arrs, axis=0):
 
 def repeat(a, repeats, axis=None):
     return _w(_torch.repeat_interleave(_unwrap(a), repeats, dim=axis))
+
+
+def tile(a, reps):
+    return _w(_unwrap(a).repeat(*reps))
+
+
+def full(shape, vals, dtype=float32):
+    return _w(_torch.full(tuple(shape), float(_unwrap(vals)) if not isinstance(vals, (int, float)) else vals, dtype=dtype))
 
 
 def broadcast_to(a, shape):

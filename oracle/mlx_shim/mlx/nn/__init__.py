@@ -130,6 +130,23 @@ class Conv2d(Module):
         return y + self.bias if "bias" in self.__dict__ else y
 
 
+class Conv3d(Module):
+    """mlx nn.Conv3d: NDHWC input, weight (out, kd, kh, kw, in), default init U(+-1/sqrt(in*kd*kh*kw)), zero bias."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, bias=True):
+        super().__init__()
+        ks = (kernel_size,) * 3 if isinstance(kernel_size, int) else tuple(kernel_size)
+        k = 1.0 / _math.sqrt(in_channels * ks[0] * ks[1] * ks[2])
+        self.weight = mx.array((_torch.rand(out_channels, *ks, in_channels) * 2 - 1) * k)
+        if bias:
+            self.bias = mx.zeros((out_channels,))
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+
+    def __call__(self, x):
+        y = mx.conv3d(x, self.weight, self.stride, self.padding, self.dilation)
+        return y + self.bias if "bias" in self.__dict__ else y
+
+
 class RMSNorm(Module):
     def __init__(self, dims, eps=1e-5):
         super().__init__()
