@@ -62,15 +62,15 @@ bool pdl_enabled() {
 }
 
 int num_sms() {
-  static int sms = -1;
-  if (sms < 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    sms = v;
-  }
-  return sms;
+  static int sms[kMaxDeviceSlots] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  const bool cached = dev >= 0 && dev < kMaxDeviceSlots;
+  if (cached && sms[dev] > 0) return sms[dev];
+  int v = 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  if (cached) sms[dev] = v;
+  return v;
 }
 
 }  // namespace ltxb

@@ -317,10 +317,9 @@ static int launch_attention(const void* Q, long long ldq, const void* K, long lo
   constexpr size_t kTileBytes = static_cast<size_t>(kDh / 64) * 128 * 128;
   constexpr size_t smem = 1024 + kAttnHeader + 5 * kTileBytes + 2 * 128 * 128;
   auto kernel = attention_kernel<kDh>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;  // per instantiation and device
+  if (configured.first()) {
     LTXB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = true;
   }
   CUtensorMap tq, tk, tv;
   const uint32_t box[3] = {64, 128, 1};

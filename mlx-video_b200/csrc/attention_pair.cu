@@ -405,6 +405,362 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   }
 }
 
+// ================================================================================================================
+// attention_pair64_kernel: the same job layout (two 128-row query tiles per CTA, key-split ragged wave), but the
+// scores are produced in 64-KEY STEPS into DOUBLE-BUFFERED TMEM tiles, so S_t(s+1) is on the tensor pipe a whole step
+// ahead of its softmax.
+//
+// Why (profiles/r1e/attn_ncu_5184.md + the source-level samples of that report): in attention_pair_kernel S_t(j+1)
+// overwrites P_t(j) in TMEM, so it can only be issued after PV_t(j); 52 % of the softmax warps' samples (31.5 % of all)
+// sat on the wait for that S tile while no pipe was saturated (tensor 52 %, MUFU 40 %).  Here the chain per query tile is
+// softmax(s) -> P(s) -> PV(s); S(s+1) is already in the other buffer when softmax(s) ends.
+//
+// TMEM (512 columns, all used at dh = 128): score buffer (tile t, buffer b) at (t*2 + b)*64 — 64 fp32 columns = 64 keys;
+// P(s) is written back over its first 32 columns as packed bf16 — and O_t at 256 + t*dh.
+// K / V stay 128-key TMA tiles in 2-deep smem rings; step s uses key rows [64*(s&1), +64) of tile s>>1.
+//   warp 0      TMA producer (Q0, Q1 once; K, V tiles)
+//   warp 1      MMA issuer.  Per step s:  S_0(s+1), S_1(s+1), then PV_0(s) / PV_1(s) in the order their P arrives
+//   warps 2,3   idle (keep the softmax warps aligned to their TMEM lane quarters)
+//   warps 4..7  softmax of tile 0, warps 8..11 of tile 1: one thread per query row, 64 scores per step in registers
+// ================================================================================================================
+struct Pair64Header {
+  uint64_t q_full;
+  uint64_t k_full[2], k_empty[2];
+  uint64_t v_full[2], v_empty[2];
+  uint64_t s_full[2][2];  // S_t(s) complete in buffer s&1          (MMA -> softmax t)
+  uint64_t p_full[2][2];  // P_t(s) written over buffer s&1         (softmax t -> MMA); one arrival per warp
+  uint64_t pv_done[2];    // O_t += P_t(s) V(s) complete, per step  (MMA -> softmax t)
+  uint32_t tmem_base;
+};
+static_assert(sizeof(Pair64Header) <= kPairHeader, "header overflow");
+
+template <int kDh>
+__global__ void __launch_bounds__(kPairThreads, 1)
+attention_pair64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                        const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  constexpr int kBlocks = kDh / 64;                       // 64-column (128 B) swizzle blocks per row
+  constexpr uint32_t kBlockBytes = 128 * 128;             // 128 rows x 128 B
+  constexpr uint32_t kTileBytes = kBlocks * kBlockBytes;  // one Q / K / V tile
+  constexpr uint32_t kColO = 256;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Pair64Header* hdr = reinterpret_cast<Pair64Header*>(smem);
+  uint8_t* sQ = smem + kPairHeader;   // 2 tiles
+  uint8_t* sK = sQ + 2 * kTileBytes;  // 2 stages
+  uint8_t* sV = sK + 2 * kTileBytes;  // 2 stages
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TRACE(3, 0, 0);  // kernel entry
+  const PairJob job = decode_pair_job(p, blockIdx.x);
+  const int n_kt = job.kv_hi - job.kv_lo;                               // 128-key K / V tiles of this CTA
+  const int s_lo = 2 * job.kv_lo;                                       // first 64-key step (global index)
+  const int n_steps = min(2 * job.kv_hi, (p.Tk + 63) / 64) - s_lo;      // the last tile may hold a single step
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(&hdr->q_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&hdr->k_full[i], 1);
+        mbar_init(&hdr->k_empty[i], 1);
+        mbar_init(&hdr->v_full[i], 1);
+        mbar_init(&hdr->v_empty[i], 1);
+        mbar_init(&hdr->pv_done[i], 1);
+        for (int j = 0; j < 2; ++j) {
+          mbar_init(&hdr->s_full[i][j], 1);
+          mbar_init(&hdr->p_full[i][j], 4);
+        }
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<1>(&hdr->tmem_base, 512);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&hdr->tmem_base);
+  if (threadIdx.x == 0) TRACE(3, 0, 1);  // barriers + TMEM ready
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) TRACE(3, 0, 2);  // predecessor kernel finished
+
+  if (warp < 4) {
+    reg_dealloc<kRegsIssue>();
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&hdr->q_full, 2 * kTileBytes);
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int j = 0; j < kBlocks; ++j)
+            tma_load_3d(sQ + t * kTileBytes + j * kBlockBytes, &tmap_q, &hdr->q_full, job.h * kDh + 64 * j, job.q0 + 128 * t, job.b);
+        for (int lt = 0; lt < n_kt; ++lt) {
+          const int st = lt & 1;
+          const uint32_t ph = (lt >> 1) & 1;
+          const int row = (job.kv_lo + lt) * 128;
+          mbar_wait(&hdr->k_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&hdr->k_full[st], kTileBytes);
+#pragma unroll
+          for (int j = 0; j < kBlocks; ++j)
+            tma_load_3d(sK + st * kTileBytes + j * kBlockBytes, &tmap_k, &hdr->k_full[st], job.h * kDh + 64 * j, row, job.b);
+          mbar_wait(&hdr->v_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&hdr->v_full[st], kTileBytes);
+#pragma unroll
+          for (int j = 0; j < kBlocks; ++j)
+            tma_load_3d(sV + st * kTileBytes + j * kBlockBytes, &tmap_v, &hdr->v_full[st], job.h * kDh + 64 * j, row, job.b);
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+        const uint32_t idesc_o = make_idesc_bf16(128, kDh, 0, 1);  // B = V is MN-major (dh contiguous)
+        // S_t(i) = Q_t . K[64 key rows of step i]^T into buffer i&1 (the K stage of tile i>>1 must be full)
+        auto issue_s = [&](int t, int i) {
+          const uint32_t q_addr = smem_u32(sQ + t * kTileBytes);
+          const uint32_t k_addr = smem_u32(sK + ((i >> 1) & 1) * kTileBytes) + (i & 1) * (64 * 128);  // rows 64.. of every block
+          const uint32_t d = tmem_base + (t * 2 + (i & 1)) * 64;
+#pragma unroll
+          for (int kk = 0; kk < kDh / 16; ++kk) {
+            const uint32_t off = (kk >> 2) * kBlockBytes + (kk & 3) * 32;
+            umma_bf16_ss<1>(d, make_smem_desc_sw128(q_addr + off, 16, 1024), make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_s,
+                            kk != 0 ? 1u : 0u);
+          }
+          umma_commit(&hdr->s_full[t][i & 1]);
+        };
+        // O_t += P_t(i) . V[64 key rows of step i]  (P read from TMEM buffer i&1; the V stage of tile i>>1 must be full)
+        auto issue_pv = [&](int t, int i) {
+          const uint32_t v_addr = smem_u32(sV + ((i >> 1) & 1) * kTileBytes);
+          const uint32_t p_tmem = tmem_base + (t * 2 + (i & 1)) * 64;
+#pragma unroll
+          for (int kq = 0; kq < 4; ++kq) {  // 16 keys per MMA = 8 packed TMEM columns of P; V: 16 key rows = 2048 B
+            const int kk = 4 * (i & 1) + kq;
+            umma_bf16_ts(tmem_base + kColO + t * kDh, p_tmem + kq * 8, make_smem_desc_sw128(v_addr + kk * 2048, kBlockBytes, 1024),
+                         idesc_o, (i | kq) != 0 ? 1u : 0u);
+          }
+          umma_commit(&hdr->pv_done[t]);
+        };
+        mbar_wait(&hdr->q_full, 0);
+        mbar_wait(&hdr->k_full[0], 0);
+        tc_fence_after_sync();
+        issue_s(0, 0);
+        issue_s(1, 0);
+        for (int i = 0; i < n_steps; ++i) {
+          const int lt = i >> 1;
+          const bool more = i + 1 < n_steps;
+          if (more) {
+            if (i & 1) {  // step i+1 opens the next key tile
+              mbar_wait(&hdr->k_full[(lt + 1) & 1], ((lt + 1) >> 1) & 1);
+              tc_fence_after_sync();
+            }
+            // S_t(i+1) goes into the buffer P_t(i-1) lived in: PV_t(i-1) was issued one iteration ago and the tensor
+            // pipe runs MMAs in issue order, so no wait is needed — the scores are a step ahead of their softmax
+            issue_s(0, i + 1);
+            issue_s(1, i + 1);
+            if ((i & 1) == 0) umma_commit(&hdr->k_empty[lt & 1]);  // both halves of K tile lt have been contracted
+            TRACE(2, i, 3);
+          }
+          if ((i & 1) == 0) {  // first step of a key tile: its V must have landed before the first PV
+            mbar_wait(&hdr->v_full[lt & 1], (lt >> 1) & 1);
+            tc_fence_after_sync();
+          }
+          // PV of the two query tiles in the order their P arrives
+          const uint32_t par = (i >> 1) & 1;
+          bool d0 = false, d1 = false;
+          const long long t0 = clock64();
+          uint32_t spins = 0;
+          while (!(d0 && d1)) {
+            if (!d0 && mbar_try_wait(&hdr->p_full[0][i & 1], par)) {
+              tc_fence_after_sync();
+              issue_pv(0, i);
+              TRACE(2, i, 0);
+              d0 = true;
+            }
+            if (!d1 && mbar_try_wait(&hdr->p_full[1][i & 1], par)) {
+              tc_fence_after_sync();
+              issue_pv(1, i);
+              TRACE(2, i, 4);
+              d1 = true;
+            }
+            if ((++spins & 0x3ff) == 0 && clock64() - t0 > LTXB_WATCHDOG_CYCLES) {
+              printf("ltxb: attention issuer watchdog: block %d step %d waits for P (%d %d)\n", (int)blockIdx.x, i, (int)d0, (int)d1);
+              __trap();
+            }
+          }
+          if (!more || (i & 1) == 1) umma_commit(&hdr->v_empty[lt & 1]);  // V tile lt is done
+        }
+      }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue: one thread per query row, 64 keys per step ==========
+    reg_alloc<kRegsSoftmax>();
+    const int t = (warp - 4) >> 2;      // query tile of this warpgroup
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t t_o = t_lane + kColO + t * kDh;
+    constexpr float kLog2e = 1.4426950408889634f;
+    float m = -INFINITY, l = 0.f;
+    for (int i = 0; i < n_steps; ++i) {
+      const uint32_t t_s = t_lane + (t * 2 + (i & 1)) * 64;
+      if (lane == 0 && quarter == 0) TRACE(t, i, 0);  // start waiting for S_t(i)
+      mbar_wait(&hdr->s_full[t][i & 1], (i >> 1) & 1);
+      tc_fence_after_sync();
+      if (lane == 0 && quarter == 0) TRACE(t, i, 1);  // S_t(i) ready
+      uint32_t sr[64];
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) tmem_ld_x32(t_s + c, *reinterpret_cast<uint32_t(*)[32]>(&sr[c]));
+      tmem_wait_ld();
+      if (lane == 0 && quarter == 0) TRACE(t, i, 2);  // scores in registers
+
+      const int kv0 = (s_lo + i) * 64;
+      const int kv_valid = p.Tk - kv0;
+      float sc = p.scale_log2;
+      if (p.kv_bias != nullptr) {  // rare (context masks): fold scale and bias into the scores first
+        const float* bias = p.kv_bias + static_cast<long long>(job.b) * p.Tk + kv0;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          const float bv = (c < kv_valid) ? __ldg(bias + c) * kLog2e : 0.f;
+          sr[c] = __float_as_uint(fmaf(__uint_as_float(sr[c]), sc, bv));
+        }
+        sc = 1.0f;
+      }
+      if (kv_valid < 64) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (c >= kv_valid) sr[c] = __float_as_uint(kMasked);
+      }
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mx[u] = fmaxf(mx[u], __uint_as_float(sr[c + u]));
+      }
+      const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sc;  // sc > 0
+      const float m_new = (m_tile > m + kTau) ? fmaxf(ceilf(m_tile), -1048576.0f) : m;  // integer stabiliser, moved lazily
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = (m_new == m) ? 1.0f : fast_exp2(m - m_use);  // m = -inf -> 0
+      if (i > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {  // O is free once PV_t(i-1) is done
+        mbar_wait(&hdr->pv_done[t], (i - 1) & 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int c = 0; c < kDh; c += 32) {
+          uint32_t o[32];
+          tmem_ld_x32(t_o + c, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+          tmem_st_x32(t_o + c, o);
+        }
+      }
+      if (lane == 0 && quarter == 0) TRACE(t, i, 3);  // maximum known
+      // P = 2^(s*sc - m): kEmu of every 8 column pairs on the FMA pipe (degree-3 polynomial), the rest on MUFU
+      constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
+      const uint64_t sc2 = pack_f32x2(sc, sc);
+      const uint64_t negm2 = pack_f32x2(-m_use, -m_use);
+      const uint64_t c2 = pack_f32x2(kMagic - m_use, kMagic - m_use);  // exact: m_use is an integer below 2^22
+      const uint64_t neg1 = pack_f32x2(-1.0f, -1.0f);
+      const uint64_t k0 = pack_f32x2(0.99992807f, 0.99992807f), k1 = pack_f32x2(0.69326099f, 0.69326099f);
+      const uint64_t k2 = pack_f32x2(0.24261114f, 0.24261114f), k3 = pack_f32x2(0.05517167f, 0.05517167f);
+      uint64_t rs2[2] = {0ull, 0ull};
+      uint32_t pk[32];
+#pragma unroll
+      for (int pi = 0; pi < 32; ++pi) {
+        const int c = 2 * pi;
+        const uint64_t s2 = pack_f32x2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));
+        float e0, e1;
+        if ((pi & 7) < kEmu) {
+          float x0, x1, p0, p1;
+          unpack_f32x2(fma_f32x2(s2, sc2, c2), x0, x1);  // kMagic + round(x)
+          x0 = fmaxf(x0, kMagic - 126.0f), x1 = fmaxf(x1, kMagic - 126.0f);
+          const uint64_t f = fma_f32x2(s2, sc2, fma_f32x2(pack_f32x2(x0, x1), neg1, c2));  // x - round(x)
+          unpack_f32x2(fma_f32x2(fma_f32x2(fma_f32x2(k3, f, k2), f, k1), f, k0), p0, p1);
+          e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(x0) << 23));
+          e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(x1) << 23));
+        } else {
+          float x0, x1;
+          unpack_f32x2(fma_f32x2(s2, sc2, negm2), x0, x1);
+          e0 = fast_exp2(x0), e1 = fast_exp2(x1);
+        }
+        rs2[pi & 1] = add_f32x2(rs2[pi & 1], pack_f32x2(e0, e1));
+        pk[pi] = pack_bf16x2(e0, e1);
+      }
+      tmem_st_x32(t_s, pk);  // P_t(i): packed bf16 over the first 32 columns of this buffer
+      tmem_wait_st();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&hdr->p_full[t][i & 1]);
+      if (lane == 0 && quarter == 0) TRACE(t, i, 4);  // P signalled
+      float r0, r1, r2, r3;
+      unpack_f32x2(rs2[0], r0, r1);
+      unpack_f32x2(rs2[1], r2, r3);
+      l = l * alpha + ((r0 + r1) + (r2 + r3));
+      m = m_new;
+    }
+    // ---- epilogue ----
+    if (lane == 0 && quarter == 0) TRACE(3, 0, 3 + t);  // softmax of the last step done
+    if (n_steps > 0) {
+      mbar_wait(&hdr->pv_done[t], (n_steps - 1) & 1);
+      tc_fence_after_sync();
+    }
+    if (lane == 0 && quarter == 0 && t == 0) TRACE(3, 0, 5);  // last PV done
+    const int row = job.q0 + t * 128 + r;
+    if (job.slot < 0) {
+      const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
+      __nv_bfloat16* orow = attn_out_row(p, job.b, row, job.h, kDh);
+#pragma unroll
+      for (int c = 0; c < kDh; c += 32) {
+        uint32_t o[32];
+        tmem_ld_x32(t_o + c, o);
+        tmem_wait_ld();
+        if (row < p.Tq) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[8 * k + 0]) * inv_l, __uint_as_float(o[8 * k + 1]) * inv_l);
+            w.y = pack_bf16x2(__uint_as_float(o[8 * k + 2]) * inv_l, __uint_as_float(o[8 * k + 3]) * inv_l);
+            w.z = pack_bf16x2(__uint_as_float(o[8 * k + 4]) * inv_l, __uint_as_float(o[8 * k + 5]) * inv_l);
+            w.w = pack_bf16x2(__uint_as_float(o[8 * k + 6]) * inv_l, __uint_as_float(o[8 * k + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c + 8 * k) = w;
+          }
+        }
+      }
+    } else {
+      const long long prow = static_cast<long long>(job.slot) * 256 + t * 128 + r;
+      float* wo = p.ws_o + prow * kDh;
+      if (row < p.Tq) *reinterpret_cast<float2*>(p.ws_ml + prow * 2) = make_float2(m, l);
+#pragma unroll
+      for (int c = 0; c < kDh; c += 32) {
+        uint32_t o[32];
+        tmem_ld_x32(t_o + c, o);
+        tmem_wait_ld();
+        if (row < p.Tq) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<uint4*>(wo + c + 4 * k) = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x == 0) TRACE(3, 0, 6);  // output stored by every warp
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
 // One warp per query row of a split job: O = sum_i 2^(m_i - M) O_i / sum_i 2^(m_i - M) l_i.
 template <int kDh>
 __global__ void __launch_bounds__(256) attention_combine_kernel(const AttnParams p, int n_left) {
@@ -465,11 +821,13 @@ static int launch_pair(const void* Q, long long ldq, const void* K, long long ld
                        cudaStream_t stream) {
   constexpr size_t kTileBytes = static_cast<size_t>(kDh / 64) * 128 * 128;
   constexpr size_t smem = 1024 + kPairHeader + 6 * kTileBytes;
-  auto kernel = attention_pair_kernel<kDh>;
-  static bool configured = false;
-  if (!configured) {
-    LTXB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = true;
+  // LTXB_ATTN_S64=0: the single-buffered 128-key-step kernel (kept for A/B runs)
+  static const bool s64 = [] { const char* e = getenv("LTXB_ATTN_S64"); return e == nullptr || atoi(e) != 0; }();
+  auto kernel = s64 ? attention_pair64_kernel<kDh> : attention_pair_kernel<kDh>;
+  static PerDeviceOnce configured;  // per instantiation and device
+  if (configured.first()) {
+    LTXB_CUDA(cudaFuncSetAttribute(attention_pair64_kernel<kDh>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    LTXB_CUDA(cudaFuncSetAttribute(attention_pair_kernel<kDh>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   }
   const int sms = num_sms();
   LTXB_CHECK_SUPPORTED(sms > 0, "ltxb_attention_fwd: no device");

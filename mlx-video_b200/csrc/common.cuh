@@ -40,7 +40,22 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box);
 
-int num_sms();
+int num_sms();  // of the CURRENT device (cached per device index)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE property of a kernel: one flag per (kernel
+// instantiation, device), so a process that moves between GPUs configures each of them once.
+constexpr int kMaxDeviceSlots = 16;
+struct PerDeviceOnce {
+  bool done[kMaxDeviceSlots] = {};
+  // true the first time it is called on the current device (devices beyond the table: every time)
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDeviceSlots) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
 
 // Launch with programmatic stream serialization (PDL) so the kernel may begin while its predecessor in the
 // stream drains; all kernels of this library call pdl_wait() before touching global memory.  LTXB_PDL=0 disables.

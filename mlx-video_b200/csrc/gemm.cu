@@ -584,10 +584,9 @@ template <int kCtas, int kEpi>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, int grid, size_t smem,
                        cudaStream_t stream) {
   auto kernel = gemm_bf16_kernel<kCtas, kEpi>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static PerDeviceOnce configured;  // per instantiation and device
+  if (configured.first()) {
     LTXB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    configured = true;
   }
   LTXB_CUDA(launch_kernel(kernel, dim3(grid), dim3(kGemmThreads), smem, stream, kCtas, ta, tw, p));
   return LTXB_OK;

@@ -113,7 +113,7 @@ class LTXModel:
 
     def __init__(self, config: LTXModelConfig, device: Union[str, torch.device, None] = None,
                  dedupe_timesteps: bool = True, timestep_capacity: int = 128, cache_context: bool = False,
-                 cuda_graphs: bool = False) -> None:
+                 cuda_graphs: bool = False, context_cache_slots: int = 2) -> None:
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
         if device is None or torch.device(device).type != "cuda":
@@ -130,7 +130,10 @@ class LTXModel:
         # coming in (constant across a denoise loop; the reference recomputes them every step — off by default so
         # the default forward executes the reference's work).  cuda_graphs: replay one captured graph per input
         # signature instead of ~800 launches per forward.
+        # context_cache_slots: how many DIFFERENT contexts keep their projections at once per modality (2 = the cond /
+        # uncond prompts the two-pass CFG loops alternate between, generate.py:1258-1283); least recently used goes first.
         self.cache_context, self._context_caches, self._context_keys = cache_context, {}, {}
+        self.context_cache_slots = max(1, int(context_cache_slots))
         self._graphs = {} if cuda_graphs else None
         self.workspace = Workspace()
         self.seq_parallel = None  # set by parallel.UlyssesGroup.attach()
@@ -310,11 +313,21 @@ class LTXModel:
         from .checkpoint import checkpoint_files, load_transformer_weights, read_quantization_meta, sanitize_state_dict
 
         model = cls(config, device=device)
-        if weights_override is not None:
-            model.load_weights(sanitize_state_dict(dict(weights_override)), strict=strict)
-            return model
         expected = set(model.parameters())
         expected |= {k[: -len("weight")] + suffix for k in expected if k.endswith(".weight") for suffix in ("scales", "biases")}
+        if weights_override is not None:
+            # ltx.py:828-842: overrides go through the same key filter as file tensors, so a unified audio+video
+            # state dict (the LoRA flow: apply_lora_to_weights -> from_pretrained(weights_override=merged)) loads into
+            # a video-only or audio-only config; only MISSING parameters raise
+            given = {k: v for k, v in sanitize_state_dict(dict(weights_override)).items() if k in expected}
+            meta = None
+            if any(k.endswith(".scales") for k in given) and model_path is not None:
+                try:
+                    meta = read_quantization_meta(checkpoint_files(model_path)[0])
+                except (OSError, ValueError, IndexError):
+                    meta = None
+            model.load_weights(given, strict=strict, quant_meta=meta)
+            return model
         weights = load_transformer_weights(model_path, config, expected=expected)
         meta = read_quantization_meta(checkpoint_files(model_path)[0]) if any(k.endswith(".scales") for k in weights) else None
         try:
@@ -340,6 +353,9 @@ class LTXModel:
             return ts.reshape(B * T), None, (B, T)
         values, index, count = ops.timestep_groups(ts.reshape(-1), self.timestep_capacity)
         self._group_counts.append(count)
+        if len(self._group_counts) > 64 and not torch.cuda.is_current_stream_capturing():
+            # long-lived processes that never call check_timestep_groups(): fold the history into one device scalar
+            self._group_counts = [torch.stack(self._group_counts).max().reshape(1)]
         return values, index, (1, self.timestep_capacity)
 
     def check_timestep_groups(self) -> None:
@@ -427,13 +443,34 @@ class LTXModel:
     def _tensor_key(t: Tensor):
         return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, t._version)
 
+    def _select_cache(self, pre: str, key) -> Tuple[int, ContextCache, bool]:
+        """The cache slot that holds (or will hold) the projections of the context named ``key``:
+        -> (slot index, cache, hit).  A miss re-targets the least recently used slot (its buffers keep their
+        addresses, only ``valid`` drops) — so ``cache.key`` always names what the buffers hold or are about to be
+        filled with, on the eager path and under graph replay alike."""
+        slots: List[ContextCache] = self._context_caches.setdefault(pre, [])
+        for c in slots:
+            if c.key == key:
+                c.stamp = self._cache_clock = getattr(self, "_cache_clock", 0) + 1
+                return slots.index(c), c, c.valid
+        if len(slots) < self.context_cache_slots:
+            slots.append(ContextCache())
+            c = slots[-1]
+        else:
+            c = min(slots, key=lambda s_: s_.stamp)
+        c.retarget(key)
+        c.stamp = self._cache_clock = getattr(self, "_cache_clock", 0) + 1
+        return slots.index(c), c, False
+
     def _context_cache_for(self, pre: str, context: Tensor) -> ContextCache:
-        cache = self._context_caches.get(pre)
-        if cache is None:
-            cache = self._context_caches[pre] = ContextCache()
         # under graph replay the forward sees a static copy of the context; the caller's tensor names the cache
-        cache.retarget(self._context_keys.get(pre) or self._tensor_key(context))
-        return cache
+        return self._select_cache(pre, self._context_keys.get(pre) or self._tensor_key(context))[1]
+
+    def invalidate_context(self) -> None:
+        """A new denoise loop starts: whatever prompt comes next is projected afresh (buffers and graphs are kept)."""
+        for slots in self._context_caches.values():
+            for c in slots:
+                c.key, c.valid = None, False
 
     def clear_caches(self) -> None:
         self._context_caches.clear()
@@ -464,15 +501,15 @@ class LTXModel:
         for t in flat:
             if t is not None and not t.is_cuda:
                 raise LtxbError("LTXModel inputs must be CUDA tensors; there is no CPU fallback on this path")
-        hits = []
+        used = []  # (prefix, slot index, cache, hit) of the context caches this call goes through
         for pre, m in (("", video), ("audio_", audio)):
-            hit = False
             if self.cache_context and m is not None:
                 self._context_keys[pre] = self._tensor_key(m.context)
-                c = self._context_caches.get(pre)
-                hit = c is not None and c.valid and c.key == self._context_keys[pre]
-            hits.append(hit)
-        key = (video is None, audio is None, tuple(sig(t) for t in flat), tuple(hits), self.seq_parallel is not None)
+                slot, c, hit = self._select_cache(pre, self._context_keys[pre])
+                used.append((pre, slot, c, hit))
+        enabled = tuple(None if m is None else bool(m.enabled) for m in (video, audio))
+        key = (video is None, audio is None, tuple(sig(t) for t in flat), tuple((pre, slot, hit) for pre, slot, _, hit in used),
+               self.seq_parallel is not None, enabled)
         try:
             entry = self._graphs.get(key)
             if entry is None:
@@ -484,11 +521,10 @@ class LTXModel:
                     return Modality(c(m.latent), c(m.timesteps), c(m.positions), c(m.context), m.enabled, c(m.context_mask),
                                     None if pe is None else (c(pe[0]), c(pe[1])))
                 sv, sa = static(video), static(audio)
-                valid_before = {pre: c.valid for pre, c in self._context_caches.items()}
                 self._forward(sv, sa)  # eager warm-up: sizes the workspaces, configures the kernels
                 torch.cuda.synchronize()
-                for pre, c in self._context_caches.items():  # capture the same variant (fill vs reuse) as this key
-                    c.valid = valid_before.get(pre, False) and c.valid
+                for _, _, c, hit in used:  # capture the same variant (fill vs reuse) as this key names
+                    c.valid = hit
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     out = self._forward(sv, sa)
@@ -498,7 +534,7 @@ class LTXModel:
                 if dst is not None:
                     dst.copy_(src)
             graph.replay()
-            for c in self._context_caches.values():
+            for _, _, c, _ in used:  # c.key was set by _select_cache: key and contents move together
                 c.valid = c.context is not None
         finally:
             self._context_keys.clear()
@@ -516,8 +552,10 @@ class LTXModel:
         ax = self._process_output(self.audio_scale_shift_table, self.audio_proj_out, aa, adt) if aa is not None else None
         if sp is not None:
             vx, ax = sp.gather_outputs(vx, ax)
-        for c in self._context_caches.values():  # every block has now filled its K/V entry
-            c.valid = c.context is not None
+        for pre, m in (("", video), ("audio_", audio)):  # every block has now filled its K/V entry
+            if self.cache_context and m is not None:
+                c = self._context_cache_for(pre, m.context)
+                c.valid = c.context is not None
         return vx, ax
 
     # ------------------------------------------------------------------ accounting

@@ -82,6 +82,7 @@ class ContextCache:
 
     def __init__(self) -> None:
         self.key = None
+        self.stamp = 0  # last use (LTXModel keeps a few of these and re-targets the least recently used)
         self.context: Optional[Tensor] = None  # projected caption, bf16 (B, Tc, D)
         self.kv: Dict[object, Tensor] = {}
         self.valid = False

@@ -1,6 +1,7 @@
 """Attention timing at the LTX-2 shapes vs torch SDPA (library yardstick)."""
 import json
 import math
+import os
 import sys
 
 import torch
@@ -33,5 +34,5 @@ for (B, T, Tk, H, dh) in [(1, 1280, 1280, 32, 128), (1, 1280, 1024, 32, 128), (2
     fl = 4.0 * B * H * T * Tk * dh
     ms = time_fn(lambda: ops.attention(q, k, v, o, B, T, Tk, H, dh, 1 / math.sqrt(dh)))
     q4, k4, v4 = (t.view(B, -1, H, dh).transpose(1, 2) for t in (q, k, v))
-    ms_t = time_fn(lambda: torch.nn.functional.scaled_dot_product_attention(q4, k4, v4))
+    ms_t = float("inf") if os.environ.get("ATTN_SWEEP_NO_SDPA") else time_fn(lambda: torch.nn.functional.scaled_dot_product_attention(q4, k4, v4))
     print(json.dumps({"B": B, "T": T, "Tk": Tk, "H": H, "dh": dh, "ltxb_us": round(ms * 1e3, 1), "ltxb_tflops": round(fl / ms / 1e9), "sdpa_tflops": round(fl / ms_t / 1e9)}), flush=True)

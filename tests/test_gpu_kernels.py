@@ -120,6 +120,47 @@ def test_attention(B, Tq, Tk, H, dh, bias):
     assert float((out.float() - 1).abs().max()) <= 8e-3
 
 
+def _attention_ref_fp32(q, k, v, B, Tq, Tk, H, dh):
+    """Plain PyTorch fp32 reference of attention.py:13-53, one (batch, head) at a time so the (Tq, Tk) score matrix of
+    the 14 080-token config (793 MB in fp32) is the largest temporary."""
+    D = H * dh
+    out = torch.empty(B * Tq, D, device=q.device, dtype=torch.float32)
+    q4, k4, v4 = q.view(B, Tq, H, dh), k.reshape(B, Tk, H, dh), v.reshape(B, Tk, H, dh)
+    for b in range(B):
+        for h in range(H):
+            s = (q4[b, :, h].float() @ k4[b, :, h].float().T) / math.sqrt(dh)
+            out.view(B, Tq, H, dh)[b, :, h] = torch.softmax(s, -1) @ v4[b, :, h].float()
+            del s
+    return out
+
+
+# BASELINE.json configs[2..4]: dev pipeline B=2 x 5184 tokens (CFG batch) self- and text-cross-attention, the 14 080-token
+# long config, and the audio<->video cross-attentions of the joint model (5184 video x 68 audio tokens, 64-wide heads).
+# These are the shapes bench.py --workload dev|av|long times: job decode past one wave, key split of the ragged wave,
+# single-64-key last tiles (68 = 64 + 4, 5184 = 40 * 128 + 64).
+@pytest.mark.parametrize("B,Tq,Tk,H,dh", [(2, 5184, 5184, 32, 128), (1, 14080, 14080, 32, 128), (2, 5184, 1024, 32, 128),
+                                           (1, 5184, 68, 32, 64), (1, 68, 5184, 32, 64), (1, 1280, 1024, 32, 128),
+                                           (1, 3520, 3520, 32, 128), (1, 648, 5184, 4, 128)])
+def test_attention_baseline_config_shapes(B, Tq, Tk, H, dh):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device=DEV).manual_seed(11)
+    D = H * dh
+    q = torch.randn(B * Tq, D, device=DEV, generator=g).bfloat16()
+    kv = torch.randn(B * Tk, 2 * D, device=DEV, generator=g).bfloat16()
+    k, v = kv[:, :D], kv[:, D:]
+    out = torch.empty(B * Tq, D, device=DEV, dtype=torch.bfloat16)
+    ops.attention(q, k, v, out, B, Tq, Tk, H, dh, 1.0 / math.sqrt(dh))
+    ref = _attention_ref_fp32(q, k, v, B, Tq, Tk, H, dh)
+    err = rel_l2(out.float(), ref)
+    assert torch.isfinite(out.float()).all() and err <= 8e-3, f"attention B={B} Tq={Tq} Tk={Tk} dh={dh}: rel_l2 {err:.3e}"
+    # per-row check as well: no single query row may be off (a wrong key range in ONE job would hide in the global norm)
+    row_err = (out.float() - ref).norm(dim=1) / ref.norm(dim=1).clamp_min(1e-20)
+    assert float(row_err.max()) <= 5e-2, f"worst row rel_l2 {float(row_err.max()):.3e} at row {int(row_err.argmax())}"
+    out2 = torch.empty_like(out)
+    ops.attention(q, k, v, out2, B, Tq, Tk, H, dh, 1.0 / math.sqrt(dh))
+    assert torch.equal(out, out2), "attention is not deterministic"
+
+
 def test_rmsnorm_layernorm_modulate():
     g = torch.Generator(device=DEV).manual_seed(1)
     for R, D in [(1280, 4096), (68, 2048), (37, 512), (5, 1032)]:

@@ -125,6 +125,96 @@ def test_production_width_block_vs_oracle():
     print(f"production block rel_l2={r:.3e}")
 
 
+def _rand_block_args(g, T, Tc, D, grid, heads, audio=False):
+    """Seeded TransformerArgs of one production-width stream for oracle and GPU (same values)."""
+    x = torch.randn(1, T, D, generator=g)
+    ctx = torch.randn(1, Tc, D, generator=g).to(torch.bfloat16).float()
+    ts = 0.1 * torch.randn(1, 1, 6 * D, generator=g)
+    pos = torch.from_numpy(O.create_audio_position_grid(1, T) if audio else O.create_position_grid(1, *grid))
+    max_pos = [20] if audio else [20, 2048, 2048]
+    pe = O.precompute_freqs_cis(pos, D, 10000.0, max_pos, True, heads, O.LTXRopeType.SPLIT, True)
+    return x, ctx, ts, pos, pe
+
+
+def test_production_width_block_dev_config_vs_oracle():
+    """BASELINE configs[2] (dev pipeline): ONE block at production width on 768x768x65 -> 24x24x9 = 5184 video tokens
+    and 1024 text tokens, vs the fp32 oracle on the same (bf16-rounded) weights."""
+    cfg = O.OracleConfig(num_layers=1)
+    tensors = bf16_round(O.init_params(cfg, seed=0))
+    g = torch.Generator().manual_seed(2)
+    T, Tc, D = 5184, 1024, 4096
+    x, ctx, ts, pos, pe = _rand_block_args(g, T, Tc, D, (9, 24, 24), 32)
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    oracle = O.OracleLTXModel(cfg, tensors)
+    with torch.no_grad():
+        want, _ = oracle.block(0, O.TransformerArgs(x, ctx, None, ts.expand(1, T, 6 * D), None, pe, None, None, None, True), None)
+    model = build(cfg, tensors)
+    args = M.TransformerArgs(x=x.to(DEV), context=ctx.to(DEV, torch.bfloat16), context_mask=None, timesteps=ts.to(DEV),
+                             embedded_timestep=torch.zeros(1, 1, D, device=DEV), positional_embeddings=(pe[0].to(DEV), pe[1].to(DEV)))
+    got, _ = model.transformer_blocks[0](video=args, audio=None)
+    assert_close(got.x, want.x, "dev-config block")
+    r = assert_close(got.x.cpu() - x, want.x - x, "dev-config block update")
+    print(f"dev-config block update rel_l2={r:.3e}")
+
+
+def test_production_width_av_block_vs_oracle():
+    """BASELINE configs[3] (joint audio+video): ONE block at production width, 5184 video + 68 audio tokens, 1024 text
+    tokens per modality — audio<->video cross-attention in both directions — vs the fp32 oracle."""
+    cfg = O.OracleConfig(num_layers=1, model_type=O.LTXModelType.AudioVideo)
+    tensors = bf16_round(O.init_params(cfg, seed=0))
+    g = torch.Generator().manual_seed(3)
+    T, Ta, Tc, D, Da = 5184, 68, 1024, cfg.inner_dim, cfg.audio_inner_dim
+    Hv, Ha = cfg.num_attention_heads, cfg.audio_num_attention_heads
+    vx, vctx, vts, vpos, vpe = _rand_block_args(g, T, Tc, D, (9, 24, 24), Hv)
+    ax, actx, ats, apos, ape = _rand_block_args(g, Ta, Tc, Da, None, Ha, audio=True)
+    cross_max = [max(cfg.positional_embedding_max_pos[0], cfg.audio_positional_embedding_max_pos[0])]
+    xdim = cfg.audio_cross_attention_dim
+    vcpe = O.precompute_freqs_cis(vpos[:, 0:1], xdim, 10000.0, cross_max, True, Hv, O.LTXRopeType.SPLIT, True)
+    acpe = O.precompute_freqs_cis(apos[:, 0:1], xdim, 10000.0, cross_max, True, Ha, O.LTXRopeType.SPLIT, True)
+    vss, vgt = 0.1 * torch.randn(1, 1, 4 * D, generator=g), 0.1 * torch.randn(1, 1, D, generator=g)
+    ass, agt = 0.1 * torch.randn(1, 1, 4 * Da, generator=g), 0.1 * torch.randn(1, 1, Da, generator=g)
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    oracle = O.OracleLTXModel(cfg, tensors)
+    with torch.no_grad():
+        wv, wa = oracle.block(0,
+                              O.TransformerArgs(vx, vctx, None, vts.expand(1, T, 6 * D), None, vpe, vcpe, vss.expand(1, T, 4 * D), vgt.expand(1, T, D), True),
+                              O.TransformerArgs(ax, actx, None, ats.expand(1, Ta, 6 * Da), None, ape, acpe, ass.expand(1, Ta, 4 * Da), agt.expand(1, Ta, Da), True))
+    model = build(cfg, tensors)
+    d = lambda t, dt=torch.float32: t.to(DEV, dt)  # noqa: E731
+    va = M.TransformerArgs(x=d(vx), context=d(vctx, torch.bfloat16), context_mask=None, timesteps=d(vts), embedded_timestep=torch.zeros(1, 1, D, device=DEV),
+                           positional_embeddings=(d(vpe[0]), d(vpe[1])), cross_positional_embeddings=(d(vcpe[0]), d(vcpe[1])),
+                           cross_scale_shift_timestep=d(vss), cross_gate_timestep=d(vgt))
+    aa = M.TransformerArgs(x=d(ax), context=d(actx, torch.bfloat16), context_mask=None, timesteps=d(ats), embedded_timestep=torch.zeros(1, 1, Da, device=DEV),
+                           positional_embeddings=(d(ape[0]), d(ape[1])), cross_positional_embeddings=(d(acpe[0]), d(acpe[1])),
+                           cross_scale_shift_timestep=d(ass), cross_gate_timestep=d(agt))
+    gv, ga = model.transformer_blocks[0](video=va, audio=aa)
+    assert_close(gv.x, wv.x, "AV block video stream")
+    assert_close(ga.x, wa.x, "AV block audio stream")
+    rv = assert_close(gv.x.cpu() - vx, wv.x - vx, "AV block video update")
+    ra = assert_close(ga.x.cpu() - ax, wa.x - ax, "AV block audio update")
+    print(f"AV block update rel_l2 video={rv:.3e} audio={ra:.3e}")
+
+
+def test_eight_block_production_width_model_vs_oracle():
+    """Depth at production width (scripts/deep_parity.py as a test): 8 blocks of D = 4096, 32 x 128 heads, 320 video
+    tokens, 128 text tokens — GPU bf16 vs the fp32 oracle on the host, same bf16-rounded weights (8.6 GB of fp32)."""
+    L, T, Tc = 8, 320, 128
+    cfg = O.OracleConfig(num_layers=L)
+    tensors = bf16_round(O.init_params(cfg, seed=0))
+    g = torch.Generator().manual_seed(1)
+    video = O.Modality(torch.randn(1, T, 128, generator=g), torch.full((1, T), 0.725), torch.from_numpy(O.create_position_grid(1, 5, 8, 8)),
+                       torch.randn(1, Tc, 3840, generator=g))
+    model = build(cfg, tensors)
+    got, _ = model(video=to_dev(video), audio=None)
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    with torch.no_grad():
+        want, _ = O.OracleLTXModel(cfg, tensors)(video, None)
+    r = assert_close(got, want, "8-block production-width model")
+    print(f"8-block production-width model rel_l2={r:.3e}")
+    del model, tensors
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("mt,L,B,grid,Tc,Ta", [
     (O.LTXModelType.VideoOnly, 4, 1, (4, 8, 10), 40, 0),     # T=320, ragged vs the 128-row tiles
     (O.LTXModelType.VideoOnly, 2, 2, (3, 7, 9), 72, 0),      # B=2 (cfg_batch), T=189, Tc not a tile multiple
@@ -324,7 +414,7 @@ def test_cuda_graph_and_context_cache_are_exact():
         for name, model in variants.items():
             got_v, got_a = model(video=v, audio=a)
             assert torch.equal(got_v, want_v) and torch.equal(got_a, want_a), f"{name} differs at step {step}"
-    assert variants["cache"]._context_caches[""].valid and len(variants["graph+cache"]._graphs) == 2  # fill + reuse graphs
+    assert variants["cache"]._context_caches[""][0].valid and len(variants["graph+cache"]._graphs) == 2  # fill + reuse graphs
     # a new prompt: same shapes, different tensor -> caches must be refilled
     ctx_v, ctx_a = torch.randn(1, Tc, 256, generator=g).to(DEV), torch.randn(1, Tc, 256, generator=g).to(DEV)
     v, a = inputs(200, 0.9)
@@ -337,6 +427,36 @@ def test_cuda_graph_and_context_cache_are_exact():
     want_v, _ = plain(video=v, audio=a)
     got_v, _ = variants["graph+cache"](video=v, audio=a)
     assert torch.equal(got_v, want_v)
+
+
+@pytest.mark.parametrize("slots", [1, 2])
+def test_graph_cache_alternating_contexts(slots):
+    """The two-pass CFG loops (generate.py:1258-1283) alternate the cond / uncond prompt every step: contexts A, B, A, B
+    of the same shape.  Under graph replay + context cache every call must still see ITS context's text K/V — with one
+    slot (every call refills) and with two (both prompts stay resident) — bit for bit equal to the plain model."""
+    cfg = O.small_config(O.LTXModelType.VideoOnly, num_layers=2)
+    tensors = O.init_params(cfg, seed=41)
+    g = torch.Generator().manual_seed(42)
+    T, Tc = 96, 24
+    pos = torch.from_numpy(O.create_position_grid(1, 2, 6, 8)).to(DEV)
+    ctx = [torch.randn(1, Tc, 256, generator=g).to(DEV) for _ in range(3)]
+    plain = build(cfg, tensors)
+    models = {"graph+cache": build(cfg, tensors, cuda_graphs=True, cache_context=True, context_cache_slots=slots),
+              "cache": build(cfg, tensors, cache_context=True, context_cache_slots=slots)}
+    for step, which in enumerate([0, 1, 0, 1, 0, 2, 1, 2, 0]):
+        lat = torch.randn(1, T, 128, generator=g).to(DEV)
+        m = M.Modality(lat, torch.full((1, T), 1.0 - 0.1 * step, device=DEV), pos, ctx[which])
+        want, _ = plain(video=m)
+        for name, model in models.items():
+            got, _ = model(video=m)
+            assert torch.equal(got, want), f"{name} (slots={slots}) served the wrong context at call {step} (context {which})"
+    # a disabled modality must not replay a graph captured with it enabled (graph key carries Modality.enabled)
+    m_on = M.Modality(lat, torch.full((1, T), 0.5, device=DEV), pos, ctx[0], True)
+    m_off = M.Modality(lat, torch.full((1, T), 0.5, device=DEV), pos, ctx[0], False)
+    for m in (m_on, m_off, m_on):
+        want, _ = plain(video=m)
+        got, _ = models["graph+cache"](video=m)
+        assert torch.equal(got, want)
 
 
 def test_full_size_model_properties():
