@@ -429,7 +429,10 @@ struct Pair64Header {
   uint64_t v_full[2], v_empty[2];
   uint64_t s_full[2][2];  // S_t(s) complete in buffer s&1          (MMA -> softmax t)
   uint64_t p_full[2][2];  // P_t(s) written over buffer s&1         (softmax t -> MMA); one arrival per warp
-  uint64_t pv_done[2];    // O_t += P_t(s) V(s) complete, per step  (MMA -> softmax t)
+  // O_t += P_t(s) V(s) complete (MMA -> softmax t), one barrier per score buffer: a softmax thread only knows that
+  // PV_t(s-2) has completed when it holds S_t(s), so with a single barrier per tile a parity wait could not tell
+  // "PV(s-2) done" from "PV(s) done" (two phases apart); per buffer the uncertainty is one phase
+  uint64_t pv_done[2][2];
   uint32_t tmem_base;
 };
 static_assert(sizeof(Pair64Header) <= kPairHeader, "header overflow");
@@ -470,9 +473,9 @@ attention_pair64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         mbar_init(&hdr->k_full[i], 1);
         mbar_init(&hdr->k_empty[i], 1);
         mbar_init(&hdr->v_full[i], 1);
-        mbar_init(&hdr->v_empty[i], 1);
-        mbar_init(&hdr->pv_done[i], 1);
+        mbar_init(&hdr->v_empty[i], 2);  // one commit from each PV issuer
         for (int j = 0; j < 2; ++j) {
+          mbar_init(&hdr->pv_done[i][j], 1);
           mbar_init(&hdr->s_full[i][j], 1);
           mbar_init(&hdr->p_full[i][j], 4);
         }
@@ -518,84 +521,74 @@ attention_pair64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             tma_load_3d(sV + st * kTileBytes + j * kBlockBytes, &tmap_v, &hdr->v_full[st], job.h * kDh + 64 * j, row, job.b);
         }
       }
-    } else if (warp == 1) {
-      // ===================== MMA issuer =====================
-      if (lane == 0) {
+    } else {
+      // ===================== MMA issuers: warp 1 = scores of both tiles, warp 2 / 3 = PV of tile 0 / 1 =====================
+      // Three issuing warps on three different schedulers instead of one: a single issuing thread needed ~2500 cycles for
+      // the ~350 instructions of one 64-key step (waits, polls, 24 MMAs) next to two busy softmax warps on its scheduler
+      // — twice the 1280 cycles the tensor pipe needs for them (scripts/umma_bench.cu: 48 cycles per 128x64x16 SS MMA,
+      // 64 per 128x128x16 TS MMA, with or without softmax-like background load) — so the pipe starved and the softmax
+      // waited ~1000 cycles per step for its scores (profiles/r2/attention_s64_notes.md).  Each warp runs its control
+      // flow warp-uniformly (descriptor arithmetic in uniform registers, ~3 issue slots per MMA) and one elected lane
+      // issues.  Descriptors are {lo, hi} words: only the 14-bit start-address field of lo changes between MMAs.
+      // Ordering that the single in-order issuer used to give for free: S_t(i) overwrites the buffer of P_t(i-2), so the
+      // score warp waits for PV_t(i-2) to COMPLETE (pv_done) before it issues S(i); that is a full softmax ahead of need.
+      const bool issuer = elect_one();
+      constexpr uint32_t kHiK = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B, version 1, 128B swizzle
+      constexpr uint32_t kTile16 = kTileBytes >> 4, kBlock16 = kBlockBytes >> 4;
+      if (warp == 1) {
         const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
-        const uint32_t idesc_o = make_idesc_bf16(128, kDh, 0, 1);  // B = V is MN-major (dh contiguous)
-        // S_t(i) = Q_t . K[64 key rows of step i]^T into buffer i&1 (the K stage of tile i>>1 must be full)
-        auto issue_s = [&](int t, int i) {
-          const uint32_t q_addr = smem_u32(sQ + t * kTileBytes);
-          const uint32_t k_addr = smem_u32(sK + ((i >> 1) & 1) * kTileBytes) + (i & 1) * (64 * 128);  // rows 64.. of every block
-          const uint32_t d = tmem_base + (t * 2 + (i & 1)) * 64;
-#pragma unroll
-          for (int kk = 0; kk < kDh / 16; ++kk) {
-            const uint32_t off = (kk >> 2) * kBlockBytes + (kk & 3) * 32;
-            umma_bf16_ss<1>(d, make_smem_desc_sw128(q_addr + off, 16, 1024), make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_s,
-                            kk != 0 ? 1u : 0u);
-          }
-          umma_commit(&hdr->s_full[t][i & 1]);
-        };
-        // O_t += P_t(i) . V[64 key rows of step i]  (P read from TMEM buffer i&1; the V stage of tile i>>1 must be full)
-        auto issue_pv = [&](int t, int i) {
-          const uint32_t v_addr = smem_u32(sV + ((i >> 1) & 1) * kTileBytes);
-          const uint32_t p_tmem = tmem_base + (t * 2 + (i & 1)) * 64;
-#pragma unroll
-          for (int kq = 0; kq < 4; ++kq) {  // 16 keys per MMA = 8 packed TMEM columns of P; V: 16 key rows = 2048 B
-            const int kk = 4 * (i & 1) + kq;
-            umma_bf16_ts(tmem_base + kColO + t * kDh, p_tmem + kq * 8, make_smem_desc_sw128(v_addr + kk * 2048, kBlockBytes, 1024),
-                         idesc_o, (i | kq) != 0 ? 1u : 0u);
-          }
-          umma_commit(&hdr->pv_done[t]);
-        };
+        const uint32_t q_lo = ((smem_u32(sQ) & 0x3FFFFu) >> 4) | (1u << 16);  // K-major operands: LBO field = 1 (unused)
+        const uint32_t k_lo = ((smem_u32(sK) & 0x3FFFFu) >> 4) | (1u << 16);
         mbar_wait(&hdr->q_full, 0);
-        mbar_wait(&hdr->k_full[0], 0);
-        tc_fence_after_sync();
-        issue_s(0, 0);
-        issue_s(1, 0);
         for (int i = 0; i < n_steps; ++i) {
           const int lt = i >> 1;
-          const bool more = i + 1 < n_steps;
-          if (more) {
-            if (i & 1) {  // step i+1 opens the next key tile
-              mbar_wait(&hdr->k_full[(lt + 1) & 1], ((lt + 1) >> 1) & 1);
-              tc_fence_after_sync();
-            }
-            // S_t(i+1) goes into the buffer P_t(i-1) lived in: PV_t(i-1) was issued one iteration ago and the tensor
-            // pipe runs MMAs in issue order, so no wait is needed — the scores are a step ahead of their softmax
-            issue_s(0, i + 1);
-            issue_s(1, i + 1);
-            if ((i & 1) == 0) umma_commit(&hdr->k_empty[lt & 1]);  // both halves of K tile lt have been contracted
-            TRACE(2, i, 3);
+          if ((i & 1) == 0) {  // step i opens key tile lt
+            mbar_wait(&hdr->k_full[lt & 1], (lt >> 1) & 1);
           }
-          if ((i & 1) == 0) {  // first step of a key tile: its V must have landed before the first PV
-            mbar_wait(&hdr->v_full[lt & 1], (lt >> 1) & 1);
-            tc_fence_after_sync();
+          if (i >= 2) {  // the buffers S(i) goes to still hold P(i-2) until PV(i-2) has read them
+            mbar_wait(&hdr->pv_done[0][i & 1], ((i - 2) >> 1) & 1);
+            mbar_wait(&hdr->pv_done[1][i & 1], ((i - 2) >> 1) & 1);
           }
-          // PV of the two query tiles in the order their P arrives
-          const uint32_t par = (i >> 1) & 1;
-          bool d0 = false, d1 = false;
-          const long long t0 = clock64();
-          uint32_t spins = 0;
-          while (!(d0 && d1)) {
-            if (!d0 && mbar_try_wait(&hdr->p_full[0][i & 1], par)) {
-              tc_fence_after_sync();
-              issue_pv(0, i);
-              TRACE(2, i, 0);
-              d0 = true;
+          tc_fence_after_sync();
+          // S_t(i) = Q_t . K[64 key rows of step i]^T into buffer i&1, both query tiles, MMAs interleaved
+          const uint32_t ka = k_lo + (lt & 1) * kTile16 + (i & 1) * ((64 * 128) >> 4);  // rows 64.. of every block
+          const uint32_t d0 = tmem_base + (i & 1) * 64, d1 = tmem_base + (2 + (i & 1)) * 64;
+          if (issuer) {
+#pragma unroll
+            for (int kk = 0; kk < kDh / 16; ++kk) {
+              const uint32_t off = (kk >> 2) * kBlock16 + (kk & 3) * 2;
+              umma_bf16_ss<1>(d0, desc_from_words(q_lo + off, kHiK), desc_from_words(ka + off, kHiK), idesc_s, kk != 0 ? 1u : 0u);
+              umma_bf16_ss<1>(d1, desc_from_words(q_lo + kTile16 + off, kHiK), desc_from_words(ka + off, kHiK), idesc_s, kk != 0 ? 1u : 0u);
             }
-            if (!d1 && mbar_try_wait(&hdr->p_full[1][i & 1], par)) {
-              tc_fence_after_sync();
-              issue_pv(1, i);
-              TRACE(2, i, 4);
-              d1 = true;
-            }
-            if ((++spins & 0x3ff) == 0 && clock64() - t0 > LTXB_WATCHDOG_CYCLES) {
-              printf("ltxb: attention issuer watchdog: block %d step %d waits for P (%d %d)\n", (int)blockIdx.x, i, (int)d0, (int)d1);
-              __trap();
-            }
+            umma_commit(&hdr->s_full[0][i & 1]);
+            umma_commit(&hdr->s_full[1][i & 1]);
+            if ((i & 1) == 1 || i + 1 == n_steps) umma_commit(&hdr->k_empty[lt & 1]);  // K tile lt fully contracted
           }
-          if (!more || (i & 1) == 1) umma_commit(&hdr->v_empty[lt & 1]);  // V tile lt is done
+          __syncwarp();
+          if (lane == 0) TRACE(2, i, 3);
+        }
+      } else {
+        const int t = warp - 2;  // query tile of this PV issuer
+        const uint32_t idesc_o = make_idesc_bf16(128, kDh, 0, 1);  // B = V is MN-major (dh contiguous)
+        const uint32_t v_lo = ((smem_u32(sV) & 0x3FFFFu) >> 4) | ((kBlockBytes >> 4) << 16);  // MN-major: LBO = next 64-column block
+        const uint32_t t_o = tmem_base + kColO + t * kDh;
+        for (int i = 0; i < n_steps; ++i) {
+          const int lt = i >> 1;
+          if ((i & 1) == 0) mbar_wait(&hdr->v_full[lt & 1], (lt >> 1) & 1);  // first step of a key tile: its V must have landed
+          mbar_wait(&hdr->p_full[t][i & 1], (i >> 1) & 1);
+          tc_fence_after_sync();
+          // O_t += P_t(i) . V[64 key rows of step i]  (P read from TMEM buffer i&1)
+          const uint32_t va = v_lo + (lt & 1) * kTile16 + (i & 1) * (4 * 2048 >> 4);
+          const uint32_t p_tmem = tmem_base + (t * 2 + (i & 1)) * 64;
+          if (issuer) {
+#pragma unroll
+            for (int kq = 0; kq < 4; ++kq)  // 16 keys per MMA = 8 packed TMEM columns of P; V: 16 key rows = 2048 B
+              umma_bf16_ts(t_o, p_tmem + kq * 8, desc_from_words(va + kq * (2048 >> 4), kHiK), idesc_o, (i | kq) != 0 ? 1u : 0u);
+            umma_commit(&hdr->pv_done[t][i & 1]);
+            if ((i & 1) == 1 || i + 1 == n_steps) umma_commit(&hdr->v_empty[lt & 1]);  // this tile's share of V tile lt is done
+          }
+          __syncwarp();
+          if (lane == 0) TRACE(2, i, t * 4);
         }
       }
     }
@@ -649,7 +642,7 @@ attention_pair64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = (m_new == m) ? 1.0f : fast_exp2(m - m_use);  // m = -inf -> 0
       if (i > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {  // O is free once PV_t(i-1) is done
-        mbar_wait(&hdr->pv_done[t], (i - 1) & 1);
+        mbar_wait(&hdr->pv_done[t][(i - 1) & 1], ((i - 1) >> 1) & 1);
         tc_fence_after_sync();
 #pragma unroll
         for (int c = 0; c < kDh; c += 32) {
@@ -708,7 +701,7 @@ attention_pair64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     // ---- epilogue ----
     if (lane == 0 && quarter == 0) TRACE(3, 0, 3 + t);  // softmax of the last step done
     if (n_steps > 0) {
-      mbar_wait(&hdr->pv_done[t], (n_steps - 1) & 1);
+      mbar_wait(&hdr->pv_done[t][(n_steps - 1) & 1], ((n_steps - 1) >> 1) & 1);  // MMAs complete in issue order: all PV_t are done
       tc_fence_after_sync();
     }
     if (lane == 0 && quarter == 0 && t == 0) TRACE(3, 0, 5);  // last PV done

@@ -61,6 +61,10 @@ struct GemmParams {
   int sk_splits;       // k-range pieces per such tile
   float* sk_partials;  // [clusters][ctas][kBlockM * block_n] fp32 parked partial accumulators
   int* sk_counters;    // [sk_rem][ctas] arrivals per cut tile; zero outside a launch
+  // contiguous stream-K (small M, weight-streaming regime): cluster c owns k-block units [c*U/C, (c+1)*U/C) of the
+  // tile-major unit list (U = tiles * k-blocks), boundaries rounded to sk_gran k-blocks
+  int sk_contig;
+  int sk_gran;
 };
 
 // Tiles are dealt to clusters round-robin, all clusters marching through K in lockstep (tiles that share an A
@@ -74,8 +78,24 @@ struct WorkItem {
 };
 struct WorkIter {
   int num_kb, num_tiles, stride, tile, split_tile, split_kb0, split_kb1;
+  long long u, u_end;  // contiguous mode: next unit / end of this cluster's range (unit = tile * num_kb + kb)
+  bool contig;
+  // start of cluster c's unit range in contiguous mode
+  static __device__ __forceinline__ long long range_start(long long units, int clusters, int c, int gran) {
+    if (c >= clusters) return units;
+    const long long b = units * c / clusters;
+    return b - b % gran;
+  }
   __device__ WorkIter(const GemmParams& p, int cluster_id, int num_clusters, int num_kb_)
-      : num_kb(num_kb_), num_tiles(p.num_m_tiles * p.num_n_tiles), stride(num_clusters), split_tile(-1) {
+      : num_kb(num_kb_), num_tiles(p.num_m_tiles * p.num_n_tiles), stride(num_clusters), split_tile(-1), u(0), u_end(0),
+        contig(p.sk_contig != 0) {
+    if (contig) {
+      const long long units = static_cast<long long>(num_tiles) * num_kb_;
+      u = range_start(units, num_clusters, cluster_id, p.sk_gran);
+      u_end = range_start(units, num_clusters, cluster_id + 1, p.sk_gran);
+      tile = 0;
+      return;
+    }
     int first = 0;
     if (p.sk_splits > 1) {
       first = p.sk_rem;
@@ -89,6 +109,14 @@ struct WorkIter {
     tile = first + cluster_id;
   }
   __device__ __forceinline__ bool next(WorkItem& w) {
+    if (contig) {
+      if (u >= u_end) return false;
+      w.tile = static_cast<int>(u / num_kb);
+      w.kb0 = static_cast<int>(u - static_cast<long long>(w.tile) * num_kb);
+      w.kb1 = static_cast<int>(min(static_cast<long long>(num_kb), w.kb0 + (u_end - u)));
+      u += w.kb1 - w.kb0;
+      return true;
+    }
     if (split_tile >= 0) {
       w.tile = split_tile, w.kb0 = split_kb0, w.kb1 = split_kb1;
       split_tile = -1;
@@ -358,9 +386,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         return reinterpret_cast<float4*>(slot + static_cast<size_t>(c / 32) * (kBlockM * 32)) + row_in_cta;
       };
       int* counter = p.sk_counters + w.tile * kCtas + static_cast<int>(cta_rank);
-      int others = 0;  // owner: number of parked partials to add (clusters cluster_id+1 .. cluster_id+others)
+      int others = 0;  // owner: number of parked partials to add, held by clusters contrib(0) .. contrib(others-1) in k order
+      // lockstep split: piece o+1 of tile t sits on cluster t + (o+1)*sk_rem; contiguous: on the next clusters in line
+      const int contrib_stride = p.sk_contig ? 1 : p.sk_rem;
       if (owner) {
-        others = p.sk_splits - 1;
+        if (p.sk_contig) {
+          const long long units = static_cast<long long>(num_tiles) * num_kb;
+          const long long tile_end = static_cast<long long>(w.tile + 1) * num_kb;
+          for (int c = cluster_id + 1; c < num_clusters && WorkIter::range_start(units, num_clusters, c, p.sk_gran) < tile_end; ++c) ++others;
+        } else {
+          others = p.sk_splits - 1;
+        }
         if (epi_leader) {
           const long long t0 = clock64();
           while (*reinterpret_cast<volatile int*>(counter) < others) {
@@ -446,7 +482,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int o = 0; o < 2; ++o) {
             if (o < batch) {
-              const float4* src = chunk_of(cluster_id + (o + 1) * p.sk_rem, c);
+              const float4* src = chunk_of(cluster_id + (o + 1) * contrib_stride, c);
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 if (i * 4 < width) ld[o][i] = __ldcg(src + i * kF4Stride);
@@ -476,7 +512,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
           for (int o = 2; o < others; ++o) {
-            const float4* src = chunk_of(cluster_id + (o + 1) * p.sk_rem, c);
+            const float4* src = chunk_of(cluster_id + (o + 1) * contrib_stride, c);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               if (i * 4 < width) {

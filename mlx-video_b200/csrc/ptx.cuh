@@ -193,6 +193,23 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   d |= static_cast<uint64_t>(2) << 61;                           // [61,64) layout = SWIZZLE_128B
   return d;
 }
+// The same descriptor from its two 32-bit words (lo: start address >> 4 | LBO >> 4 << 16; hi: SBO >> 4 | version | layout):
+// kernels that issue many MMAs keep `hi` constant and only add to the address field of `lo`.
+__device__ __forceinline__ uint64_t desc_from_words(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+// One lane of a converged warp (the others skip): keeps the surrounding control flow warp-uniform.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // Instruction descriptor for kind::f16 with bf16 operands and fp32 accumulation.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
   return (1u << 4)                                    // c_format  = F32

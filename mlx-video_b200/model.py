@@ -453,7 +453,10 @@ class LTXModel:
             if c.key == key:
                 c.stamp = self._cache_clock = getattr(self, "_cache_clock", 0) + 1
                 return slots.index(c), c, c.valid
-        if len(slots) < self.context_cache_slots:
+        free = [c for c in slots if c.key is None]  # invalidated (a finished denoise loop): reuse before growing
+        if free:
+            c = free[0]
+        elif len(slots) < self.context_cache_slots:
             slots.append(ContextCache())
             c = slots[-1]
         else:
