@@ -441,17 +441,18 @@ def run_workload(name: str, wl: dict, args, ctx: dict, models: dict, steps: int,
 
     # ---------------- per-kernel timing (CUDA events around every launch, same stream) for the roofline leg
     graphs, model._graphs = model._graphs, None  # eager for this leg: the brackets sit between the launches
+    fill_prof = ops.profile(True)
+    torch.cuda._sleep(int(3e7))  # give the host a head start so launch latency is not inside the brackets
+    step(0)  # the first step of a loop: a steady step's work + the once-per-loop context projections
+    torch.cuda.synchronize()
+    ops.profile(False)
     launches_step0 = ops.launches
     prof = ops.profile(True)
-    torch.cuda._sleep(int(3e7))  # give the host a head start so launch latency is not inside the brackets
+    torch.cuda._sleep(int(3e7))
     step(1)  # a steady step of the loop (text K/V of this loop's prompt already projected when the cache is on)
     torch.cuda.synchronize()
     ops.profile(False)
     launches_per_step = ops.launches - launches_step0
-    fill_prof = ops.profile(True)
-    step(0)  # the first step of a loop: the same work + the once-per-loop context projections
-    torch.cuda.synchronize()
-    ops.profile(False)
     model._graphs = graphs
     table = {}
     for kname, work, a, bb in prof:

@@ -62,7 +62,9 @@ int64_t ltxb_kernel_launches(void);
  * tcgen05/TMEM tensor-core kernel fed by TMA; persistent over output tiles.
  * Requirements: K % 64 == 0, N % 16 == 0, lda/ldw/ldo multiples of 8, 16-byte aligned pointers.
  * block_n: N extent of one output tile (multiple of 16, 32..256) or 0 = choose for wave efficiency.
- * cta_pair: 1 = cta_group::2 (two SMs share one 256-row tile), 0 = single CTA, -1 = choose.
+ * cta_pair: 1 = cta_group::2 (two SMs share one 256-row tile), 0 = single CTA, -1 = choose; 2 / 3 = force the
+ *   contiguous stream-K schedule (every SM an equal, contiguous share of the (tile, k-block) list; what -1 picks for
+ *   M <= 640 when the tile count leaves a ragged wave) with single-CTA / pair tiles.
  * ---------------------------------------------------------------------------------------------- */
 enum {
   LTXB_EPI_BIAS_BF16 = 0,

@@ -656,6 +656,7 @@ extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   LTXB_CHECK_SUPPORTED(lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0 && (lda >= K || epi->a_group_cols > 0) && ldw >= K && ldo >= N,
                        "ltxb_gemm_bf16: leading dimensions must be multiples of 8 and cover the row");
   LTXB_CHECK_ARG(epi->mode >= 0 && epi->mode < LTXB_EPI_COUNT, "ltxb_gemm_bf16: bad epilogue mode %d", epi->mode);
+  LTXB_CHECK_ARG(cta_pair >= -1 && cta_pair <= 3, "ltxb_gemm_bf16: cta_pair=%d not in [-1, 3]", cta_pair);
   LTXB_CHECK_ARG(block_n == 0 || (block_n >= 32 && block_n <= 256 && block_n % 16 == 0),
                  "ltxb_gemm_bf16: block_n=%d must be 0 or a multiple of 16 in [32,256]", block_n);
   if (epi->bias) LTXB_CHECK_ARG(aligned16(epi->bias), "ltxb_gemm_bf16: bias must be 16-byte aligned");
@@ -677,16 +678,44 @@ extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   static const int env_bn = [] { const char* e = getenv("LTXB_GEMM_BN"); return e ? atoi(e) : 0; }();
   if (cta_pair < 0) cta_pair = env_pair;
   if (block_n == 0) block_n = env_bn;
+  // cta_pair 2 / 3: force the contiguous stream-K schedule with single-CTA / pair tiles (tests, sweeps)
+  int force_contig = 0;
+  if (cta_pair == 2 || cta_pair == 3) {
+    force_contig = 1;
+    cta_pair -= 2;
+  }
   const TileChoice tc = choose_tile(M, N, sms, block_n, cta_pair);
   if (tc.block_n == 0) return set_error(LTXB_ERR_UNSUPPORTED, "ltxb_gemm_bf16: no tile for M=%d N=%d", M, N);
   static const int env_sk = [] { const char* e = getenv("LTXB_GEMM_STREAMK"); return e ? atoi(e) : 1; }();
+  // measured (profiles/r2/gemm_small_m.md): at M = 160 the contiguous schedule is 2-8 us SLOWER per launch than the lockstep
+  // split (every cluster pays a contributor park AND an owner fix-up), so it is opt-in: LTXB_GEMM_SK_CONTIG=-1 lets the
+  // library pick it for M <= 640, 1 forces it, cta_pair 2 / 3 select it per call
+  static const int env_contig = [] { const char* e = getenv("LTXB_GEMM_SK_CONTIG"); return e ? atoi(e) : 0; }();
   int dev = 0;
   cudaGetDevice(&dev);
   const SkWorkspace ws = (dev >= 0 && dev < kMaxDevices) ? g_sk_ws[dev] : SkWorkspace{};
   SkChoice sk{false, 0, 0, 0, 0};
-  if (env_sk && ws.partials != nullptr) sk = choose_split_k(M, N, K, sms, block_n, cta_pair, tc);
-  const int ctas = sk.use ? sk.ctas : tc.ctas;
-  const int bn = sk.use ? sk.block_n : tc.block_n;
+  // Contiguous stream-K for SMALL M (the weight-streaming regime of a sequence-parallel shard: M = 160 rows per rank at
+  // 1280 tokens on 8 GPUs): one m-tile, so no tile shares a W panel with another and the only thing that matters is that
+  // EVERY SM streams an equal slice of W.  The unit list (tile-major, k-minor) is cut into one contiguous range per
+  // cluster; at most the first item of a range is a contributor piece and the last an owner piece (see the kernel).
+  bool contig = false;
+  int c_ctas = 0, c_bn = 0;
+  if (ws.partials != nullptr && env_sk && (force_contig || (env_contig != 0 && block_n == 0 && cta_pair < 0))) {
+    c_ctas = force_contig ? (cta_pair == 1 ? 2 : 1) : (M <= kBlockM ? 1 : 2);
+    c_bn = block_n > 0 ? block_n : (N >= 256 ? 256 : ((N + 15) / 16) * 16);
+    const int slots = sms / c_ctas;
+    const long long tiles = 1ll * ((M + kBlockM * c_ctas - 1) / (kBlockM * c_ctas)) * ((N + c_bn - 1) / c_bn);
+    const long long waves = (tiles + slots - 1) / slots;
+    const int num_kb = K / kBlockK;
+    const double fill = static_cast<double>(tiles) / static_cast<double>(waves * slots);
+    const bool small_m = M <= 2 * kBlockM * 2 + kBlockM;  // <= 640 rows: at most 3 pair m-tiles
+    contig = force_contig || env_contig == 1 || (small_m && fill < 0.93 && num_kb >= 16 && tiles * c_ctas <= kSkCounterInts);
+    if (c_bn < 32 || (c_ctas == 2 && (c_bn % 16 != 0 || (c_bn / 2) % 8 != 0)) || tiles * num_kb < 8) contig = false;
+  }
+  if (!contig && env_sk && ws.partials != nullptr) sk = choose_split_k(M, N, K, sms, block_n, cta_pair, tc);
+  const int ctas = contig ? c_ctas : (sk.use ? sk.ctas : tc.ctas);
+  const int bn = contig ? c_bn : (sk.use ? sk.block_n : tc.block_n);
   if (ctas == 2) LTXB_CHECK_SUPPORTED(bn % 16 == 0 && (bn / 2) % 8 == 0, "pair mode needs block_n %% 16 == 0");
 
   GemmParams p{};
@@ -736,7 +765,16 @@ extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   }
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   int clusters = std::min(num_tiles, sms / ctas);
-  if (sk.use) {
+  if (contig) {
+    p.sk_contig = 1;
+    p.sk_gran = (K / kBlockK) % 4 == 0 ? 4 : 1;  // range boundaries on multiples of 4 k-blocks: no 1-block pieces
+    // every cluster must own a NON-EMPTY range (the owner of a cut tile counts the clusters that follow it as its
+    // contributors): at least sk_gran units each
+    const long long units = static_cast<long long>(num_tiles) * (K / kBlockK);
+    clusters = static_cast<int>(std::min<long long>(sms / ctas, units / p.sk_gran));
+    p.sk_partials = ws.partials;
+    p.sk_counters = ws.counters;
+  } else if (sk.use) {
     clusters = std::min(sms / ctas, std::max(num_tiles, sk.rem * sk.splits));
     p.sk_rem = sk.rem;
     p.sk_splits = sk.splits;

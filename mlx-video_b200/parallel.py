@@ -136,7 +136,12 @@ class UlyssesGroup:
             hit = self._rope_cache.get(key)
             if hit is None or hit[0] is not pe[0] or hit[1] is not pe[1]:
                 hit = (pe[0], pe[1], (pe[0][:, :, sl].contiguous(), pe[1][:, :, sl].contiguous()))
-                self._rope_cache = {key: hit}  # one live table at a time (constant across a denoise loop)
+                # captured CUDA graphs hold the ADDRESSES of these slices: a slice must outlive every graph that was captured
+                # with it, so entries are only dropped oldest-first beyond a handful of live tables (two stages x two
+                # modalities in the reference pipelines)
+                if len(self._rope_cache) >= 8:
+                    self._rope_cache.pop(next(iter(self._rope_cache)))
+                self._rope_cache[key] = hit
             pe = hit[2]
         return replace(m, latent=m.latent[:, sl].contiguous(), timesteps=ts.contiguous(), positions=m.positions[:, :, sl].contiguous(),
                        positional_embeddings=pe)

@@ -83,6 +83,35 @@ def test_gemm_split_k_matches_data_parallel_and_is_reproducible():
     assert all(torch.equal(outs[0], o) for o in outs[1:])
 
 
+# Sequence-parallel shards: M = T / ranks rows per GPU (1280 / 8 = 160, 1280 / 4 = 320, 5184 / 8 = 648, 68 audio tokens)
+# against the full LTX-2 weight matrices — the weight-streaming regime where the contiguous stream-K schedule applies.
+SMALL_M_SHAPES = [(160, 4096, 4096), (160, 12288, 4096), (160, 16384, 4096), (160, 4096, 16384), (320, 4096, 4096),
+                  (320, 16384, 4096), (640, 12288, 4096), (68, 2048, 2048), (128, 4096, 4096), (1, 4096, 1024), (200, 272, 1024)]
+
+
+@pytest.mark.parametrize("M,N,K", SMALL_M_SHAPES)
+def test_gemm_contiguous_stream_k(M, N, K):
+    """cta_pair 2 / 3 force the contiguous stream-K schedule (single-CTA / pair tiles); -1 lets the library choose it.
+    All must agree with the fp32 reference and with each other to summation order, and be bit-reproducible."""
+    auto = gemm_case(M, N, K, _lib.EPI_BIAS_F32)
+    for pair in (2, 3):
+        a = gemm_case(M, N, K, _lib.EPI_BIAS_F32, pair=pair)
+        b = gemm_case(M, N, K, _lib.EPI_BIAS_F32, pair=pair)
+        assert torch.equal(a, b), f"contiguous stream-K (cta_pair={pair}) differs between two runs"
+        assert rel_l2(a, auto) < 2e-5
+    assert torch.equal(auto, gemm_case(M, N, K, _lib.EPI_BIAS_F32))
+
+
+@pytest.mark.parametrize("mode", [_lib.EPI_BIAS_BF16, _lib.EPI_GELU_BF16, _lib.EPI_RESID_GATE_F32])
+def test_gemm_contiguous_stream_k_epilogues(mode):
+    for M, N, K in [(160, 4096, 4096), (160, 16384, 4096), (160, 4096, 16384), (648, 4096, 4096)]:
+        for pair in (-1, 2, 3):
+            gemm_case(M, N, K, mode, pair=pair)
+    # back-to-back launches reuse the parked-partial slots and the arrival counters
+    outs = [gemm_case(160, 4096, 16384, _lib.EPI_GELU_BF16, pair=3, seed=5) for _ in range(6)]
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+
+
 def test_gemm_rejects_bad_shapes():
     a = torch.zeros(64, 96, device=DEV, dtype=torch.bfloat16)
     w = torch.zeros(64, 96, device=DEV, dtype=torch.bfloat16)
