@@ -178,6 +178,16 @@ int ltxb_qknorm_rope_scatter_peers(const void* x, int64_t ldx, void* const* grou
                                    int32_t B, int32_t T, int32_t H, int32_t dh, const float* weight, float eps,
                                    const float* cos_tab, const float* sin_tab, int32_t B_pe, void* stream);
 
+/* q | k | v of the fused QKV buffer in ONE launch (three column segments seg_stride elements apart): q and k get their
+ * full-width RMSNorm (qk_weight f32 [2, H*dh]: q_norm row 0, k_norm row 1; attention.py:96-97,129-130) and split RoPE
+ * (rope.py:109-172), v is copied; head group g of segment s is stored to group_bases[g] + s * slot_stride (elements),
+ * rows ldo apart — the receive buffer layout [rows][q | k | v][heads of this rank].  Replaces three
+ * ltxb_qknorm_rope_scatter_peers launches per block of the sequence-parallel forward. */
+int ltxb_qkv_norm_rope_scatter_peers(const void* qkv, int64_t ldx, int64_t seg_stride, void* const* group_bases,
+                                     int32_t n_groups, int64_t ldo, int64_t slot_stride, int32_t T, int32_t H, int32_t dh,
+                                     const float* qk_weight, float eps, const float* cos_tab, const float* sin_tab,
+                                     int32_t B_pe, void* stream);
+
 /* Cross-GPU barrier on NVLink peer memory (new).  flag_ptrs: host array, flag_ptrs[i] = rank i's
  * int32[n_peers] flag array mapped into this process (zero-initialised once); epoch_counter: one int32 in LOCAL
  * device memory, zero-initialised once, advanced by the kernel (so a captured CUDA graph can replay the barrier).
@@ -304,6 +314,40 @@ int ltxb_latent_layout(const float* x, float* out, const float* scale, const flo
 int ltxb_euler_step(float* x, const float* v_pos, const float* v_neg, float cfg_scale, const float* sigma_tok,
                     float sigma, float sigma_next, const float* mask, const float* clean, int64_t n_tok,
                     int32_t C, float* x0_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row N4, second half: the LTX-2 video VAE decoder (video_vae/decoder.py:94-450) and tiled decoding (tiling.py:279-520).
+ *     Activations: f32, channels-last [N, D, H, W, C]; every CausalConv3d is ltxb_gemm_bf16 over the rows built here.
+ * ---------------------------------------------------------------------------------------------- */
+/* CausalConv3d operand (convolution.py:120-166, kernel 3, stride 1): rows [m0, m0 + rows) of the [N*D*H*W, 27*C] bf16
+ * matrix whose row m holds the 27 taps of output position m — temporal padding by frame replication (causal != 0: two
+ * copies of the first frame; else first + last), reflect padding in H and W (convolution.py:13-40).  pre_op != 0 applies
+ * the chain in front of a ResNet convolution to every tap while it is gathered (decoder.py:140-180, 357-359, 425-440):
+ *     silu( x / sqrt(mean_c(x^2) + eps) * (1 + table_scale[c] + emb_scale[n, c]) + table_shift[c] + emb_shift[n, c] )
+ * (tables / embeddings may be NULL: pixel norm + SiLU only).  HBM: 27 x (4C read (L2-resident after the first tap) +
+ * 2C written) bytes per position. */
+int ltxb_vae_gather_rows(const float* x, void* out, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C, int32_t causal,
+                         int64_t m0, int64_t rows, const float* table_scale, const float* table_shift, const float* emb_scale,
+                         const float* emb_shift, int64_t emb_ld, float eps, int32_t pre_op, void* stream);
+/* DepthToSpaceUpsample, stride (2,2,2), residual, first frame dropped (sampling.py:143-197): y = the convolution's
+ * output [N, D, H, W, 4C], x = its input [N, D, H, W, C] -> out [N, 2D-1, 2H, 2W, C/2]:
+ *     out[n, 2d+st-1, 2h+sh, 2w+sw, c] = y[n,d,h,w, ((c*2+st)*2+sh)*2+sw] + x[n,d,h,w, (((c % (C/8))*2+st)*2+sh)*2+sw] */
+int ltxb_vae_depth_to_space(const float* y, const float* x, float* out, int64_t N, int32_t D, int32_t H, int32_t W, int32_t C,
+                            void* stream);
+/* decoder.py:380-384: channels-first latents (N, C, S) [+ noise] -> channels-last (N, S, C):
+ *     out = (noise * noise_scale + (1 - noise_scale) * sample) * std[c] + mean[c]        (noise NULL = zeros) */
+int ltxb_vae_prepare_latent(const float* sample, const float* noise, float noise_scale, const float* stdv, const float* mean,
+                            float* out, int64_t N, int32_t C, int64_t S, void* stream);
+/* ops.py:47-80 (patch 4): z channels-last [N, F, H, W, 48] -> video channels-first (N, 3, F, 4H, 4W),
+ *     video[n, c, f, 4h+pq, 4w+pr] = z[n, f, h, w, (c*4+pr)*4+pq] */
+int ltxb_vae_unpatchify(const float* z, float* video, int64_t N, int32_t F, int32_t H, int32_t W, void* stream);
+/* Tiled decoding (tiling.py:404-470): the (at, ah, aw) corner of a decoded tile (N, 3, Ft, Ht, Wt) is accumulated into
+ * output (N, 3, F, H, W) at (t0, h0, w0) with the separable trapezoid mask mt[t] * mh[h] * mw[w]; weights (N, 1, F, H, W)
+ * accumulates the mask.  ltxb_vae_blend_normalize: output /= max(weights, 1e-8) (tiling.py:506-508), plane = F*H*W. */
+int ltxb_vae_blend_tile(const float* tile, int64_t N, int32_t Ft, int32_t Ht, int32_t Wt, int32_t at, int32_t ah, int32_t aw,
+                        const float* mt, const float* mh, const float* mw, float* output, float* weights, int32_t F, int32_t H,
+                        int32_t W, int32_t t0, int32_t h0, int32_t w0, void* stream);
+int ltxb_vae_blend_normalize(float* output, const float* weights, int64_t N, int64_t plane, void* stream);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,7 @@ SIGNATURES = {
     "ltxb_qknorm_rope_segments": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _f32, _vp, _vp, _i32, _vp]),
     "ltxb_qknorm_rope_scatter": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _i32, _vp]),
     "ltxb_qknorm_rope_scatter_peers": (C.c_int, [_vp, _i64, C.POINTER(_vp), _i32, _i64, _i32, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _i32, _vp]),
+    "ltxb_qkv_norm_rope_scatter_peers": (C.c_int, [_vp, _i64, _i64, C.POINTER(_vp), _i32, _i64, _i64, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _i32, _vp]),
     "ltxb_peer_barrier": (C.c_int, [C.POINTER(_vp), _i32, _i32, _vp, _vp]),
     "ltxb_peer_broadcast": (C.c_int, [_vp, _i64, C.POINTER(_vp), _i32, _vp]),
     "ltxb_attention_fwd_peers": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, C.POINTER(_vp), _i32, _i32, _i64, _i32, _i32, _i32, _i32, _f32, _vp]),
@@ -76,6 +77,12 @@ SIGNATURES = {
     "ltxb_groupnorm_silu": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _i32, _vp, _i64, _vp]),
     "ltxb_pixel_shuffle2": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "ltxb_latent_layout": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _i32, _vp]),
+    "ltxb_vae_gather_rows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _f32, _i32, _vp]),
+    "ltxb_vae_depth_to_space": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "ltxb_vae_prepare_latent": (C.c_int, [_vp, _vp, _f32, _vp, _vp, _vp, _i64, _i32, _i64, _vp]),
+    "ltxb_vae_unpatchify": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "ltxb_vae_blend_tile": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "ltxb_vae_blend_normalize": (C.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "ltxb_euler_step": (C.c_int, [_vp, _vp, _vp, _f32, _vp, _f32, _f32, _vp, _vp, _i64, _i32, _vp, _vp]),
 }
 

@@ -270,15 +270,18 @@ qknorm_rope_kernel(const __nv_bfloat16* x, long long ldx, __nv_bfloat16* out, lo
                    int heads_per_group, long long group_stride, const PeerBases peers, int T, int H, int dh,
                    const float* __restrict__ weight,
                    float eps, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, int B_pe,
-                   long long seg_x_stride, long long seg_w_stride, const float* __restrict__ weight2) {
+                   long long seg_x_stride, long long seg_w_stride, const float* __restrict__ weight2, int n_norm_seg,
+                   long long seg_o_stride) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[32];
   const long long row = blockIdx.x;
   // segment blockIdx.y: an independent [rows, H*dh] column slice of the same buffer with its own norm weight
-  // (q and k of the fused QKV buffer; the text K of every block in the stacked K/V buffer)
+  // (q and k of the fused QKV buffer; the text K of every block in the stacked K/V buffer).  Segments >= n_norm_seg
+  // are copied without norm / rotation (V on its way into the peers' receive buffers, same launch as q and k).
   x += blockIdx.y * seg_x_stride;
   if (out != nullptr) out += blockIdx.y * seg_x_stride;
+  if (static_cast<int>(blockIdx.y) >= n_norm_seg) weight = nullptr;
   if (weight != nullptr) weight += blockIdx.y * seg_w_stride;
   if (weight2 != nullptr) weight2 += blockIdx.y * seg_w_stride;
   const int half = dh / 2;
@@ -340,7 +343,7 @@ qknorm_rope_kernel(const __nv_bfloat16* x, long long ldx, __nv_bfloat16* out, lo
     // ... and with peer bases the group IS the destination GPU: the store goes straight over NVLink into that
     // rank's receive buffer (no send buffer, no separate all-to-all)
     const int grp = h / heads_per_group;
-    __nv_bfloat16* gbase = (out == nullptr) ? reinterpret_cast<__nv_bfloat16*>(peers.p[grp]) : out + grp * group_stride;
+    __nv_bfloat16* gbase = (out == nullptr) ? reinterpret_cast<__nv_bfloat16*>(peers.p[grp]) + blockIdx.y * seg_o_stride : out + grp * group_stride;
     __nv_bfloat16* o1 = gbase + row * ldo + (h % heads_per_group) * dh + off;
     store8_bf16(o1, a[j]);
     store8_bf16(o1 + half, b[j]);
@@ -755,7 +758,7 @@ static int qknorm_rope_launch(const void* x, int64_t ldx, void* out, const PeerB
                               int32_t heads_per_group, int64_t group_stride, int32_t B, int32_t T, int32_t H, int32_t dh,
                               const float* weight, float eps, const float* cos_tab, const float* sin_tab, int32_t B_pe,
                               void* stream, int32_t n_seg = 1, int64_t seg_x_stride = 0, int64_t seg_w_stride = 0,
-                              const float* weight2 = nullptr);
+                              const float* weight2 = nullptr, int32_t n_norm_seg = 1 << 30, int64_t seg_o_stride = 0);
 
 extern "C" int ltxb_qknorm_rope_scatter(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t heads_per_group,
                                         int64_t group_stride, int32_t B, int32_t T, int32_t H, int32_t dh,
@@ -780,10 +783,28 @@ extern "C" int ltxb_qknorm_rope_scatter_peers(const void* x, int64_t ldx, void* 
   return qknorm_rope_launch(x, ldx, nullptr, peers, ldo, H / n_groups, 0, B, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe, stream);
 }
 
+extern "C" int ltxb_qkv_norm_rope_scatter_peers(const void* qkv, int64_t ldx, int64_t seg_stride, void* const* group_bases,
+                                                int32_t n_groups, int64_t ldo, int64_t slot_stride, int32_t T, int32_t H, int32_t dh,
+                                                const float* qk_weight, float eps, const float* cos_tab, const float* sin_tab,
+                                                int32_t B_pe, void* stream) {
+  LTXB_CHECK_ARG(group_bases && n_groups >= 1 && n_groups <= 8 && H % n_groups == 0,
+                 "ltxb_qkv_norm_rope_scatter_peers: 1..8 groups dividing H=%d", H);
+  LTXB_CHECK_ARG(qk_weight && seg_stride % 8 == 0 && slot_stride % 8 == 0, "ltxb_qkv_norm_rope_scatter_peers: null weight / misaligned strides");
+  PeerBases peers{};
+  for (int i = 0; i < n_groups; ++i) {
+    LTXB_CHECK_ARG(group_bases[i] && aligned16(group_bases[i]), "ltxb_qkv_norm_rope_scatter_peers: null / misaligned base %d", i);
+    peers.p[i] = group_bases[i];
+  }
+  // three column segments of the fused QKV buffer in ONE launch: q and k normalised (weights [2, H*dh]) and rotated, v copied
+  return qknorm_rope_launch(qkv, ldx, nullptr, peers, ldo, H / n_groups, 0, 1, T, H, dh, qk_weight, eps, cos_tab, sin_tab, B_pe, stream, 3,
+                            seg_stride, static_cast<int64_t>(H) * dh, nullptr, 2, slot_stride);
+}
+
 static int qknorm_rope_launch(const void* x, int64_t ldx, void* out, const PeerBases& peers, int64_t ldo,
                               int32_t heads_per_group, int64_t group_stride, int32_t B, int32_t T, int32_t H, int32_t dh,
                               const float* weight, float eps, const float* cos_tab, const float* sin_tab, int32_t B_pe,
-                              void* stream, int32_t n_seg, int64_t seg_x_stride, int64_t seg_w_stride, const float* weight2) {
+                              void* stream, int32_t n_seg, int64_t seg_x_stride, int64_t seg_w_stride, const float* weight2,
+                              int32_t n_norm_seg, int64_t seg_o_stride) {
   LTXB_CHECK_ARG(x, "ltxb_qknorm_rope: null pointer");
   LTXB_CHECK_ARG(n_seg >= 1 && n_seg <= 65535 && seg_x_stride % 8 == 0 && seg_w_stride % 4 == 0 && (weight2 == nullptr || aligned16(weight2)),
                  "ltxb_qknorm_rope: bad segments n=%d", n_seg);
@@ -806,7 +827,8 @@ static int qknorm_rope_launch(const void* x, int64_t ldx, void* out, const PeerB
   __nv_bfloat16* oi = reinterpret_cast<__nv_bfloat16*>(out);
 #define LTXB_LAUNCH_QK(P)                                                                                             \
   LTXB_CUDA(launch_kernel(qknorm_rope_kernel<P>, dim3(B * T, n_seg), dim3(nthr), 0, st, 1, xi, ldx, oi, ldo, heads_per_group, \
-                          group_stride, peers, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe, seg_x_stride, seg_w_stride, weight2))
+                          group_stride, peers, T, H, dh, weight, eps, cos_tab, sin_tab, B_pe, seg_x_stride, seg_w_stride, weight2, n_norm_seg,  \
+                          seg_o_stride))
   if (per == 1) LTXB_LAUNCH_QK(1);
   else if (per == 2) LTXB_LAUNCH_QK(2);
   else if (per == 4) LTXB_LAUNCH_QK(4);

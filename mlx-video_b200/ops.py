@@ -320,6 +320,79 @@ def dequant_affine(packed: torch.Tensor, scales: torch.Tensor, biases: torch.Ten
     return out
 
 
+def vae_gather_rows(x: torch.Tensor, out: torch.Tensor, causal: bool, m0: int, rows: int, pre_op: bool = False,
+                    table_scale: Optional[torch.Tensor] = None, table_shift: Optional[torch.Tensor] = None,
+                    emb_scale: Optional[torch.Tensor] = None, emb_shift: Optional[torch.Tensor] = None, emb_ld: int = 0,
+                    eps: float = 1e-8) -> torch.Tensor:
+    """Rows [m0, m0+rows) of the CausalConv3d operand of x f32 channels-last (N, D, H, W, C) -> out bf16 [rows, 27*C] (ltxb.h N4)."""
+    _prep(x)
+    N, D, H, W, Cc = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
+    assert out.shape[0] >= rows and out.shape[1] == 27 * Cc
+    for t in (table_scale, table_shift, emb_scale, emb_shift):
+        assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.stride(-1) == 1)
+    _call("ltxb_vae_gather_rows", 0.0, x.data_ptr(), out.data_ptr(), N, D, H, W, Cc, int(causal), m0, rows, _ptr(table_scale),
+          _ptr(table_shift), _ptr(emb_scale), _ptr(emb_shift), emb_ld, eps, int(pre_op), _stream())
+    return out
+
+
+def vae_depth_to_space(y: torch.Tensor, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """y f32 (N, D, H, W, 4C) conv output + x (N, D, H, W, C) conv input -> out (N, 2D-1, 2H, 2W, C/2) (ltxb.h N4)."""
+    _prep(y)
+    N, D, H, W, Cc = x.shape
+    assert y.shape == (N, D, H, W, 4 * Cc) and out.shape == (N, 2 * D - 1, 2 * H, 2 * W, Cc // 2)
+    for t in (y, x, out):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    _call("ltxb_vae_depth_to_space", 0.0, y.data_ptr(), x.data_ptr(), out.data_ptr(), N, D, H, W, Cc, _stream())
+    return out
+
+
+def vae_prepare_latent(sample: torch.Tensor, noise: Optional[torch.Tensor], noise_scale: float, std: torch.Tensor, mean: torch.Tensor,
+                       out: torch.Tensor) -> torch.Tensor:
+    """sample f32 channels-first (N, C, F, H, W) [+ noise] -> out channels-last (N, F, H, W, C), de-normalised (ltxb.h N4)."""
+    _prep(sample)
+    N, Cc = sample.shape[:2]
+    S = sample.numel() // (N * Cc)
+    for t in (sample, noise, std, mean, out):
+        assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
+    assert out.numel() == sample.numel() and out.shape[-1] == Cc
+    _call("ltxb_vae_prepare_latent", 0.0, sample.data_ptr(), _ptr(noise), noise_scale, std.data_ptr(), mean.data_ptr(), out.data_ptr(),
+          N, Cc, S, _stream())
+    return out
+
+
+def vae_unpatchify(z: torch.Tensor, video: torch.Tensor) -> torch.Tensor:
+    """z f32 channels-last (N, F, H, W, 48) -> video channels-first (N, 3, F, 4H, 4W)."""
+    _prep(z)
+    N, F_, H, W, Cc = z.shape
+    assert Cc == 48 and video.shape == (N, 3, F_, 4 * H, 4 * W) and z.is_contiguous() and video.is_contiguous()
+    assert z.dtype == torch.float32 and video.dtype == torch.float32
+    _call("ltxb_vae_unpatchify", 0.0, z.data_ptr(), video.data_ptr(), N, F_, H, W, _stream())
+    return video
+
+
+def vae_blend_tile(tile: torch.Tensor, at: int, ah: int, aw: int, mt: torch.Tensor, mh: torch.Tensor, mw: torch.Tensor,
+                   output: torch.Tensor, weights: torch.Tensor, t0: int, h0: int, w0: int) -> None:
+    """output (N,3,F,H,W) += tile[..., :at, :ah, :aw] * mt x mh x mw at (t0, h0, w0); weights (N,1,F,H,W) += mask."""
+    _prep(tile)
+    N, _, Ft, Ht, Wt = tile.shape
+    _, _, F_, H, W = output.shape
+    for t in (tile, mt, mh, mw, output, weights):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    assert mt.numel() >= at and mh.numel() >= ah and mw.numel() >= aw and weights.shape == (N, 1, F_, H, W)
+    _call("ltxb_vae_blend_tile", 0.0, tile.data_ptr(), N, Ft, Ht, Wt, at, ah, aw, mt.data_ptr(), mh.data_ptr(), mw.data_ptr(),
+          output.data_ptr(), weights.data_ptr(), F_, H, W, t0, h0, w0, _stream())
+
+
+def vae_blend_normalize(output: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+    _prep(output)
+    N = output.shape[0]
+    plane = output.numel() // (N * 3)
+    assert output.dtype == torch.float32 and weights.dtype == torch.float32 and weights.numel() == N * plane
+    _call("ltxb_vae_blend_normalize", 0.0, output.data_ptr(), weights.data_ptr(), N, plane, _stream())
+    return output
+
+
 def qknorm_rope(
     x: torch.Tensor,
     B: int,
@@ -500,6 +573,22 @@ def qknorm_rope_scatter_peers(x: torch.Tensor, group_bases, B: int, T: int, H: i
         b_pe = cos.shape[0]
     _call("ltxb_qknorm_rope_scatter_peers", 0.0, x.data_ptr(), _ld(x), _ptr_array(group_bases), len(group_bases), ldo, B, T, H, dh,
           _ptr(weight), eps, _ptr(cos), _ptr(sin), b_pe, _stream())
+
+
+def qkv_norm_rope_scatter_peers(qkv: torch.Tensor, inner: int, group_bases, T: int, H: int, dh: int, ldo: int, slot_stride: int,
+                                qk_weight: torch.Tensor, eps: float, cos: Optional[torch.Tensor] = None,
+                                sin: Optional[torch.Tensor] = None) -> None:
+    """q | k | v column segments of the fused QKV buffer (bf16 [T, 3*inner]) in one launch: q, k normalised with
+    ``qk_weight`` (f32 [2, inner]) and rotated, v copied; head group g of segment s goes to ``group_bases[g] + s*slot_stride``."""
+    _prep(qkv)
+    assert qkv.dtype == torch.bfloat16 and qkv.shape[-1] == 3 * inner and inner == H * dh
+    assert qk_weight.dtype == torch.float32 and qk_weight.is_contiguous() and tuple(qk_weight.shape) == (2, inner)
+    b_pe = 1
+    if cos is not None:
+        assert cos.is_contiguous() and sin.is_contiguous() and cos.shape[1:] == (H, T, dh // 2)
+        b_pe = cos.shape[0]
+    _call("ltxb_qkv_norm_rope_scatter_peers", 0.0, qkv.data_ptr(), _ld(qkv), inner, _ptr_array(group_bases), len(group_bases), ldo, slot_stride,
+          T, H, dh, qk_weight.data_ptr(), eps, _ptr(cos), _ptr(sin), b_pe, _stream())
 
 
 def attention_peers(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o_bases, rows_per_peer: int, ldo: int, Tq: int, Tk: int,

@@ -208,10 +208,15 @@ class UlyssesGroup:
         back, back_ptrs = self.peers.buffer("o", (P, Tl, w), BF16)         # chunk j: head group j, my tokens
         cos, sin = (None, None) if pe is None else pe
         chunk = Tl * 3 * w * 2  # bytes of one rank's chunk in a qkv receive buffer
-        for slot, (lo, norm) in enumerate(((0, attn.q_norm), (inner, attn.k_norm), (2 * inner, None))):
-            bases = [recv_ptrs[j] + me * chunk + slot * w * 2 for j in range(P)]
-            ops.qknorm_rope_scatter_peers(qkv[:, lo:lo + inner], bases, 1, Tl, H, dh, 3 * w, None if norm is None else norm.weight,
-                                          0.0 if norm is None else norm.eps, None if norm is None else cos, None if norm is None else sin)
+        fused_qkv = attn.q_norm.weight.data_ptr() == attn.qk_norm_weight[0].data_ptr() and attn.k_norm.weight.data_ptr() == attn.qk_norm_weight[1].data_ptr()
+        if fused_qkv:  # q | k | v in one launch (three column segments of the fused QKV buffer)
+            bases = [recv_ptrs[j] + me * chunk for j in range(P)]
+            ops.qkv_norm_rope_scatter_peers(qkv, inner, bases, Tl, H, dh, 3 * w, w, attn.qk_norm_weight, attn.q_norm.eps, cos, sin)
+        else:
+            for slot, (lo, norm) in enumerate(((0, attn.q_norm), (inner, attn.k_norm), (2 * inner, None))):
+                bases = [recv_ptrs[j] + me * chunk + slot * w * 2 for j in range(P)]
+                ops.qknorm_rope_scatter_peers(qkv[:, lo:lo + inner], bases, 1, Tl, H, dh, 3 * w, None if norm is None else norm.weight,
+                                              0.0 if norm is None else norm.eps, None if norm is None else cos, None if norm is None else sin)
         self.peers.barrier()  # every rank's q/k/v have landed here
         full = recv.view(T, 3 * w)
         o_bases = [back_ptrs[i] + me * Tl * w * 2 for i in range(P)]

@@ -64,6 +64,14 @@ class array:
     def __len__(self):
         return self._t.shape[0]
 
+    def __setitem__(self, idx, value):
+        # mlx arrays support slice assignment (``a[..., lo:hi] = b``; used by video_vae/tiling.py:429-434)
+        if isinstance(idx, tuple):
+            idx = tuple(_unwrap(i) for i in idx)
+        else:
+            idx = _unwrap(idx)
+        self._t[idx] = _unwrap(value)
+
     def __getitem__(self, idx):
         if isinstance(idx, tuple):
             idx = tuple(_unwrap(i) for i in idx)

@@ -1,0 +1,185 @@
+"""GPU: the LTX-2 video VAE decoder product path (mlx-video_b200/vae_decoder.py, csrc/vae.cu; SURVEY 8f row N4, second
+half) through the C ABI — every kernel against the oracle's piece (oracle/vae_decoder_oracle.py), the whole decoder against
+the outputs of the reference's OWN LTX2VideoDecoder (tests/golden/vae_decoder.npz), tiled decoding against the reference's own
+decode_with_tiling (tests/golden/vae_tiling.npz).  Tolerance: bf16 convolution operands with fp32 accumulation and fp32
+activations — rel-L2 <= 1e-2, cosine >= 0.999 end to end (the BASELINE bar); rearrangements bit-exact."""
+import pathlib
+
+import numpy as np
+import pytest
+import torch
+
+import mlx_video_b200  # noqa: F401
+import vae_decoder_oracle as V
+from conftest import cosine, rel_l2
+from make_golden_vae import CASES, SEED, case_inputs
+from make_golden_vae_tiling import CASES as TCASES, SAMPLE, case_latents, fake_decoder_torch
+from mlx_video_b200 import _lib, ops
+from mlx_video_b200 import vae_decoder as VD
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cl(x):  # channels-first (B, C, D, H, W) -> channels-last contiguous on the device
+    return x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("C,D,H,W", [(128, 3, 4, 5), (1024, 2, 2, 2), (256, 4, 3, 2), (512, 1, 2, 3)])
+def test_gather_rows_plain_is_exact(C, D, H, W, causal):
+    """Replicate-in-time / reflect-in-space operand fetch: bit-exact against padding + unfold of the bf16-rounded input."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, C, D, H, W, generator=g)
+    xp = torch.cat([x[:, :, :1].repeat(1, 1, 2, 1, 1), x], 2) if causal else torch.cat([x[:, :, :1], x, x[:, :, -1:]], 2)
+    xp = torch.nn.functional.pad(xp, (1, 1, 1, 1, 0, 0), mode="reflect").to(torch.bfloat16)
+    want = xp.unfold(2, 3, 1).unfold(3, 3, 1).unfold(4, 3, 1)  # (B, C, D, H, W, kz, ky, kx)
+    want = want.permute(0, 2, 3, 4, 5, 6, 7, 1).reshape(2 * D * H * W, 27 * C)
+    M = 2 * D * H * W
+    out = torch.empty(M, 27 * C, dtype=torch.bfloat16, device=DEV)
+    ops.vae_gather_rows(cl(x), out, causal, 0, M)
+    assert torch.equal(out.cpu(), want)
+    # chunked: rows [m0, m0 + rows) land at the start of the buffer
+    part = torch.empty(7, 27 * C, dtype=torch.bfloat16, device=DEV)
+    ops.vae_gather_rows(cl(x), part, causal, 5, 7)
+    assert torch.equal(part.cpu(), want[5:12])
+
+
+def test_gather_rows_fused_preop_vs_oracle():
+    """pixel norm -> (1 + scale) x + shift -> SiLU applied while gathering == the oracle's chain followed by the padding."""
+    g = torch.Generator().manual_seed(4)
+    B, C, D, H, W = 2, 256, 3, 3, 4
+    x = torch.randn(B, C, D, H, W, generator=g) * 2
+    table = 0.1 * torch.randn(4, C, generator=g)
+    emb = 0.1 * torch.randn(B, 4 * C, generator=g)
+    ada = table[None, :, :, None, None, None] + emb.reshape(B, 4, C, 1, 1, 1)
+    h = torch.nn.functional.silu(V.pixel_norm(x) * (1 + ada[:, 3]) + ada[:, 2])
+    hp = torch.cat([h[:, :, :1], h, h[:, :, -1:]], 2)
+    hp = torch.nn.functional.pad(hp, (1, 1, 1, 1, 0, 0), mode="reflect")
+    want = hp.unfold(2, 3, 1).unfold(3, 3, 1).unfold(4, 3, 1).permute(0, 2, 3, 4, 5, 6, 7, 1).reshape(B * D * H * W, 27 * C)
+    out = torch.empty(B * D * H * W, 27 * C, dtype=torch.bfloat16, device=DEV)
+    t, e = table.to(DEV), emb.to(DEV)
+    ops.vae_gather_rows(cl(x), out, False, 0, out.shape[0], pre_op=True, table_shift=t[2], table_scale=t[3], emb_shift=e[:, 2 * C:3 * C],
+                        emb_scale=e[:, 3 * C:], emb_ld=4 * C)
+    assert rel_l2(out.float(), want) <= 3e-3  # bf16 rounding of the gathered values
+    ops.vae_gather_rows(cl(x), out, False, 0, out.shape[0], pre_op=True)  # no modulation: pixel norm + SiLU only
+    hp = torch.nn.functional.silu(V.pixel_norm(x))
+    hp = torch.nn.functional.pad(torch.cat([hp[:, :, :1], hp, hp[:, :, -1:]], 2), (1, 1, 1, 1, 0, 0), mode="reflect")
+    want = hp.unfold(2, 3, 1).unfold(3, 3, 1).unfold(4, 3, 1).permute(0, 2, 3, 4, 5, 6, 7, 1).reshape(B * D * H * W, 27 * C)
+    assert rel_l2(out.float(), want) <= 3e-3
+
+
+def test_rearrangement_kernels_are_exact():
+    g = torch.Generator().manual_seed(5)
+    B, C, D, H, W = 2, 64, 3, 2, 3
+    x, y = torch.randn(B, C, D, H, W, generator=g), torch.randn(B, 4 * C, D, H, W, generator=g)
+    want = V.depth_to_space(y)[:, :, 1:] + V.depth_to_space(x).repeat(1, 4, 1, 1, 1)[:, :, 1:]  # sampling.py:143-197
+    out = torch.empty(B, 2 * D - 1, 2 * H, 2 * W, C // 2, device=DEV)
+    ops.vae_depth_to_space(cl(y), cl(x), out)
+    assert torch.equal(out.cpu().permute(0, 4, 1, 2, 3), want)
+    z = torch.randn(B, 48, D, H, W, generator=g)
+    video = torch.empty(B, 3, D, 4 * H, 4 * W, device=DEV)
+    ops.vae_unpatchify(cl(z), video)
+    assert torch.equal(video.cpu(), V.unpatchify(z, 4))
+    s, n = torch.randn(B, 128, D, H, W, generator=g), torch.randn(B, 128, D, H, W, generator=g)
+    std, mean = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g)
+    o = torch.empty(B, D, H, W, 128, device=DEV)
+    ops.vae_prepare_latent(s.to(DEV), n.to(DEV), 0.025, std.to(DEV), mean.to(DEV), o)
+    want = (n * 0.025 + (1 - 0.025) * s) * std.reshape(1, -1, 1, 1, 1) + mean.reshape(1, -1, 1, 1, 1)
+    assert float((o.cpu().permute(0, 4, 1, 2, 3) - want).abs().max()) <= 1e-6
+
+
+@pytest.fixture(scope="module")
+def decoder():
+    params = V.init_decoder_params(SEED)
+    model = VD.LTX2VideoDecoder(device=DEV)
+    model.load_weights(params, strict=True)
+    return model, params
+
+
+def test_resnet_block_and_upsample_vs_oracle(decoder):
+    """One timestep-conditioned ResNet block at 512 channels and the 512 -> 256 depth-to-space stage against the oracle."""
+    model, params = decoder
+    g = torch.Generator().manual_seed(6)
+    B, c, D, H, W = 1, 512, 3, 4, 3
+    x = torch.randn(B, c, D, H, W, generator=g)
+    ts = V.timestep_embedder(params, "up_blocks.2.time_embedder", torch.tensor([50.0]))
+    bf = lambda t: t.to(torch.bfloat16).float()  # noqa: E731  (the GPU stores conv weights in bf16)
+    p2 = {k: (bf(v) if v.dim() == 5 else v) for k, v in params.items()}
+    want = V.resnet_block(p2, "up_blocks.2.res_blocks.1", x, False, ts)
+    name = "up_blocks.2.res_blocks.1"
+    tab, emb = model._p[name + ".scale_shift_table"], ts.to(DEV).contiguous()
+    xc, h = cl(x), torch.empty(B, D, H, W, c, device=DEV)
+    model._conv(name + ".conv1.conv.conv", xc, False, h, pre=dict(table_shift=tab[0], table_scale=tab[1], emb_shift=emb[:, :c], emb_scale=emb[:, c:2 * c], emb_ld=4 * c))
+    model._conv(name + ".conv2.conv.conv", h, False, xc, pre=dict(table_shift=tab[2], table_scale=tab[3], emb_shift=emb[:, 2 * c:3 * c], emb_scale=emb[:, 3 * c:], emb_ld=4 * c), resid=xc)
+    got = xc.cpu().permute(0, 4, 1, 2, 3)
+    assert rel_l2(got - x, want - x) <= 1e-2, f"resnet block update rel_l2 {rel_l2(got - x, want - x):.3e}"
+    want_up = V.depth_to_space_upsample(p2, "up_blocks.3", x, True)
+    yc = torch.empty(B, D, H, W, 4 * c, device=DEV)
+    model._conv("up_blocks.3.conv.conv", cl(x), True, yc)
+    up = torch.empty(B, 2 * D - 1, 2 * H, 2 * W, c // 2, device=DEV)
+    ops.vae_depth_to_space(yc, cl(x), up)
+    assert rel_l2(up.cpu().permute(0, 4, 1, 2, 3), want_up) <= 5e-3
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_decoder_against_reference_golden(golden, decoder, case):
+    """The whole decoder vs the output of the reference's own LTX2VideoDecoder (full width, 545 M seeded parameters)."""
+    model, _ = decoder
+    g = golden("vae_decoder")
+    c = CASES[case]
+    x = case_inputs(case)
+    torch.manual_seed(1234)
+    noise = torch.randn(x.shape)
+    model.decode_noise_scale = c["noise_scale"]
+    ts = None if c["timestep"] is None else torch.full((x.shape[0],), c["timestep"], device=DEV)
+    got = model(x.to(DEV), causal=c["causal"], timestep=ts, noise=noise.to(DEV))
+    B, _, F_, H, W = x.shape
+    assert tuple(got.shape) == (B, 3, 8 * (F_ - 1) + 1, 32 * H, 32 * W) and got.dtype == torch.float32
+    sf, sh, sw = c["sample"]
+    want = torch.from_numpy(g[f"{case}/output"])
+    r, cs = rel_l2(got[:, :, ::sf, ::sh, ::sw], want), cosine(got[:, :, ::sf, ::sh, ::sw], want)
+    print(f"vae decoder {case}: rel_l2 {r:.3e} cosine {cs:.6f}")
+    assert torch.isfinite(got).all() and r <= 1e-2 and cs >= 0.999, f"{case}: rel_l2={r:.3e} cos={cs:.6f}"
+    model.decode_noise_scale = 0.025
+
+
+def test_decoder_chunked_rows_and_errors(decoder):
+    """The materialised operand is produced in row chunks: a tiny chunk size must give the same video; CPU tensors raise."""
+    model, _ = decoder
+    x = case_inputs("plain").to(DEV)
+    model.decode_noise_scale = 0.0
+    full = model(x)
+    old = model.max_rows_per_chunk
+    try:
+        type(model).max_rows_per_chunk = 200
+        chunked = model(x)
+    finally:
+        type(model).max_rows_per_chunk = old
+    model.decode_noise_scale = 0.025
+    assert torch.equal(full, chunked)
+    with pytest.raises(_lib.LtxbError):
+        model(x.cpu())
+    with pytest.raises(ValueError):
+        model(torch.zeros(1, 64, 2, 2, 2, device=DEV))
+    with pytest.raises(ValueError):  # strict load: every parameter must be present (decoder.py:625-640)
+        VD.LTX2VideoDecoder(device=DEV).load_weights({"conv_in.conv.conv.weight": torch.zeros(1024, 3, 3, 3, 128)}, strict=True)
+
+
+@pytest.mark.parametrize("case", sorted(TCASES))
+def test_decode_with_tiling_against_reference(case):
+    """Tile split, trapezoid masks, weighted accumulation, normalisation and the streaming callback against the reference's
+    own decode_with_tiling (run over the shim with the same stand-in decoder)."""
+    g = np.load(pathlib.Path(__file__).parent / "golden" / "vae_tiling.npz", allow_pickle=True)
+    c = TCASES[case]
+    cfg = VD.TilingConfig(None if c["spatial"] is None else VD.SpatialTilingConfig(*c["spatial"]),
+                          None if c["temporal"] is None else VD.TemporalTilingConfig(*c["temporal"]))
+
+    def decoder_fn(tile, causal=False, timestep=None, debug=False, chunked_conv=False):
+        return fake_decoder_torch(tile.cpu()).to(DEV)  # test stand-in for the network (the blend is what is under test)
+
+    emitted = []
+    got = VD.decode_with_tiling(decoder_fn, case_latents(case).to(DEV), cfg, on_frames_ready=lambda fr, start: emitted.append([int(start), fr.shape[2]]))
+    want = torch.from_numpy(g[f"{case}/output"])
+    assert float((got.cpu()[:, :, :, ::SAMPLE[0], ::SAMPLE[1]] - want).abs().max()) <= 2e-5
+    assert emitted == g[f"{case}/emitted"].tolist()
