@@ -254,6 +254,19 @@ int ltxb_attention_fwd_peers(const void* Q, int64_t ldq, const void* K, int64_t 
                              void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, int64_t ldo, int32_t Tq,
                              int32_t Tk, int32_t H, int32_t dh, float scale, void* stream);
 
+/* Attention over a SLICE of the keys, left un-normalised, and the merge of such slices (new: video->audio attention with
+ * the video rows sharded across ranks, SURVEY.md 8e — queries = the replicated audio stream, keys / values = this rank's
+ * video rows; transformer.py:326-339 computes it over all keys at once).  ltxb_attention_partial writes, for every
+ * (batch, head, query row), O~ = sum_j 2^(s_j - m) v_j (f32 [dh]), the stabiliser m (log2 domain) and l = sum_j 2^(s_j - m)
+ * into `part`: [B*H*Tq][dh] floats followed by [B*H*Tq][2] (ltxb_attention_partial_floats floats in all, Tq <= 256).
+ * ltxb_attention_merge combines n_parts such blocks (part i at parts + i*part_stride floats — e.g. the all-gathered blocks
+ * of the ranks) by log-sum-exp:  O = sum_i 2^(m_i - M) O~_i / sum_i 2^(m_i - M) l_i  -> bf16 O [B*Tq, H*dh]. */
+int64_t ltxb_attention_partial_floats(int32_t B, int32_t Tq, int32_t H, int32_t dh);
+int ltxb_attention_partial(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, float* part,
+                           int32_t B, int32_t Tq, int32_t Tk, int32_t H, int32_t dh, float scale, void* stream);
+int ltxb_attention_merge(const float* parts, int64_t part_stride, int32_t n_parts, void* O, int64_t ldo, int32_t B, int32_t Tq,
+                         int32_t H, int32_t dh, void* stream);
+
 /* N3  LoRA merged into a non-quantised bf16 weight, the path the reference takes for such checkpoints
  *     (lora.py:93-129 via generate.py:2997-3007):  w[r,c] = bf16( w[r,c] + bf16(delta[r,c] * strength) )
  *     delta f32 [R,C] = B (out, rank) . A (rank, in), produced by ltxb_gemm_bf16 (LTXB_EPI_BIAS_F32, no bias) with

@@ -61,6 +61,9 @@ SIGNATURES = {
     "ltxb_peer_barrier": (C.c_int, [C.POINTER(_vp), _i32, _i32, _vp, _vp]),
     "ltxb_peer_broadcast": (C.c_int, [_vp, _i64, C.POINTER(_vp), _i32, _vp]),
     "ltxb_attention_fwd_peers": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, C.POINTER(_vp), _i32, _i32, _i64, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "ltxb_attention_partial_floats": (C.c_int64, [_i32, _i32, _i32, _i32]),
+    "ltxb_attention_partial": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "ltxb_attention_merge": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "ltxb_timestep_embed": (C.c_int, [_vp, _i32, _f32, _i32, _vp, _i64, _vp]),
     "ltxb_timestep_groups": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "ltxb_rope_table": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(_f32), _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),

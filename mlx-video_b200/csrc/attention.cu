@@ -359,6 +359,41 @@ extern "C" int ltxb_attention_fwd_peers(const void* Q, int64_t ldq, const void* 
   return attention_impl(Q, ldq, K, ldk, V, ldv, o_peers[0], ldo, 1, Tq, Tk, H, dh, scale, nullptr, o_peers, n_peers, rows_per_peer, stream);
 }
 
+extern "C" int64_t ltxb_attention_partial_floats(int32_t B, int32_t Tq, int32_t H, int32_t dh) {
+  const long long n_qp = (Tq + 255) / 256;
+  const long long rows = static_cast<long long>(B) * H * n_qp * (n_qp == 1 ? Tq : 256);
+  return ((rows * (dh + 2) + 3) / 4) * 4;
+}
+
+extern "C" int ltxb_attention_partial(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, float* part,
+                                      int32_t B, int32_t Tq, int32_t Tk, int32_t H, int32_t dh, float scale, void* stream) {
+  LTXB_CHECK_ARG(Q && K && V && part, "ltxb_attention_partial: null pointer");
+  LTXB_CHECK_ARG(B > 0 && Tq > 0 && Tk > 0 && H > 0, "ltxb_attention_partial: bad shape B=%d Tq=%d Tk=%d H=%d", B, Tq, Tk, H);
+  LTXB_CHECK_SUPPORTED(dh == 64 || dh == 128, "ltxb_attention_partial: head dim %d not in {64,128}", dh);
+  LTXB_CHECK_ARG(aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(part), "ltxb_attention_partial: pointers must be 16-byte aligned");
+  LTXB_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldq >= H * dh && ldk >= H * dh && ldv >= H * dh,
+                 "ltxb_attention_partial: leading dims must be multiples of 8 covering H*dh");
+  AttnParams p{};
+  p.B = B, p.Tq = Tq, p.Tk = Tk, p.H = H;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  const long long n_qp = (Tq + 255) / 256;
+  const long long rows = static_cast<long long>(B) * H * n_qp * (n_qp == 1 ? Tq : 256);
+  LTXB_CHECK_SUPPORTED((rows * dh) % 4 == 0, "ltxb_attention_partial: partial O block must stay 16-byte aligned");
+  return launch_attention_partial(Q, ldq, K, ldk, V, ldv, p, dh, part, part + rows * dh, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ltxb_attention_merge(const float* parts, int64_t part_stride, int32_t n_parts, void* O, int64_t ldo, int32_t B, int32_t Tq,
+                                    int32_t H, int32_t dh, void* stream) {
+  LTXB_CHECK_ARG(parts && O && n_parts >= 1 && B > 0 && Tq > 0 && H > 0, "ltxb_attention_merge: bad argument");
+  LTXB_CHECK_SUPPORTED(dh == 64 || dh == 128, "ltxb_attention_merge: head dim %d not in {64,128}", dh);
+  LTXB_CHECK_ARG(aligned16(parts) && aligned16(O) && ldo % 8 == 0 && ldo >= H * dh, "ltxb_attention_merge: misaligned operands");
+  AttnParams p{};
+  p.B = B, p.Tq = Tq, p.Tk = 0, p.H = H;
+  p.O = reinterpret_cast<__nv_bfloat16*>(O);
+  p.ldo = ldo;
+  return launch_attention_merge(p, dh, parts, part_stride, n_parts, reinterpret_cast<cudaStream_t>(stream));
+}
+
 static int attention_impl(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
                           int64_t ldo, int32_t B, int32_t Tq, int32_t Tk, int32_t H, int32_t dh, float scale,
                           const float* kv_bias, void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, void* stream) {

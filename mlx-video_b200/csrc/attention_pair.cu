@@ -378,7 +378,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         }
       }
     } else {
-      const long long prow = static_cast<long long>(job.slot) * 256 + t * 128 + r;
+      const long long prow = static_cast<long long>(job.slot) * p.part_rows + t * 128 + r;
       float* wo = p.ws_o + prow * kDh;
       if (row < p.Tq) *reinterpret_cast<float2*>(p.ws_ml + prow * 2) = make_float2(m, l);
 #pragma unroll
@@ -729,7 +729,7 @@ attention_pair64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
       }
     } else {
-      const long long prow = static_cast<long long>(job.slot) * 256 + t * 128 + r;
+      const long long prow = static_cast<long long>(job.slot) * p.part_rows + t * 128 + r;
       float* wo = p.ws_o + prow * kDh;
       if (row < p.Tq) *reinterpret_cast<float2*>(p.ws_ml + prow * 2) = make_float2(m, l);
 #pragma unroll
@@ -764,26 +764,25 @@ __global__ void __launch_bounds__(256) attention_combine_kernel(const AttnParams
   constexpr int kPer = kDh / 32;  // columns per lane
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int jl = gw >> 8, rr = gw & 255;
+  const int jl = gw / p.part_rows, rr = gw - jl * p.part_rows;
   if (jl >= n_left) return;
   const int jb = p.n_full + jl;
   const int bh = jb / p.n_qp;
   const int row = (jb - bh * p.n_qp) * 256 + rr;
   if (row >= p.Tq) return;
   const int b = bh / p.H, h = bh - b * p.H;
-  const long long prow0 = static_cast<long long>(jl) * p.n_split * 256 + rr;
+  const long long prow0 = static_cast<long long>(jl) * p.cmb_job_stride + rr;
   float M = -INFINITY;
-  for (int i = 0; i < p.n_split; ++i) M = fmaxf(M, p.ws_ml[(prow0 + i * 256ll) * 2]);
+  for (int i = 0; i < p.n_split; ++i) M = fmaxf(M, p.ws_ml[i * p.cmb_part_ml + prow0 * 2]);
   float acc[kPer];
 #pragma unroll
   for (int u = 0; u < kPer; ++u) acc[u] = 0.f;
   float L = 0.f;
   for (int i = 0; i < p.n_split; ++i) {
-    const long long pr = prow0 + i * 256ll;
-    const float2 ml = *reinterpret_cast<const float2*>(p.ws_ml + pr * 2);
+    const float2 ml = *reinterpret_cast<const float2*>(p.ws_ml + i * p.cmb_part_ml + prow0 * 2);
     const float w = (ml.x == -INFINITY) ? 0.f : fast_exp2(ml.x - M);
     L += w * ml.y;
-    const float* src = p.ws_o + pr * kDh + lane * kPer;
+    const float* src = p.ws_o + i * p.cmb_part_o + prow0 * kDh + lane * kPer;
     if constexpr (kPer == 4) {
       const float4 v = *reinterpret_cast<const float4*>(src);
       acc[0] += w * v.x, acc[1] += w * v.y, acc[2] += w * v.z, acc[3] += w * v.w;
@@ -845,6 +844,10 @@ static int launch_pair(const void* Q, long long ldq, const void* K, long long ld
     p.n_split = n_split;
     p.ws_o = g_attn_ws[dev].base;
     p.ws_ml = p.ws_o + static_cast<long long>(n_split) * n_left * 256 * kDh;
+    p.part_rows = 256;
+    p.cmb_job_stride = static_cast<long long>(n_split) * 256;
+    p.cmb_part_o = 256ll * kDh;
+    p.cmb_part_ml = 512;
   } else {
     p.n_full = static_cast<int>(jobs);
     p.n_split = 1;
@@ -867,6 +870,64 @@ static int launch_pair(const void* Q, long long ldq, const void* K, long long ld
   LTXB_CUDA(launch_kernel(kernel, dim3(grid), dim3(kPairThreads), smem, stream, 1, tq, tk, tv, p));
   if (n_split > 1)
     LTXB_CUDA(launch_kernel(attention_combine_kernel<kDh>, dim3(n_left * 256 / 8), dim3(256), 0, stream, 1, p, n_left));
+  return LTXB_OK;
+}
+
+template <int kDh>
+static int launch_partial(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, AttnParams p,
+                          float* part_o, float* part_ml, cudaStream_t stream) {
+  constexpr size_t kTileBytes = static_cast<size_t>(kDh / 64) * 128 * 128;
+  constexpr size_t smem = 1024 + kPairHeader + 6 * kTileBytes;
+  auto kernel = attention_pair64_kernel<kDh>;
+  static PerDeviceOnce configured;
+  if (configured.first()) LTXB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  p.n_qp = (p.Tq + 255) / 256;
+  const long long jobs = static_cast<long long>(p.B) * p.H * p.n_qp;
+  LTXB_CHECK_SUPPORTED(jobs < (1ll << 30), "ltxb_attention_partial: too many (batch, head, query tile) jobs");
+  p.n_full = 0;  // every CTA is a "piece" (slot = job) covering the whole key range: unnormalised output
+  p.n_split = 1;
+  p.ws_o = part_o;
+  p.ws_ml = part_ml;
+  p.part_rows = p.n_qp == 1 ? p.Tq : 256;  // compact when a job holds fewer than 256 query rows
+  CUtensorMap tq, tk, tv;
+  const uint32_t box[3] = {64, 128, 1};
+  auto enc = [&](CUtensorMap* m, const void* base, long long ld, int T) {
+    const uint64_t dims[3] = {static_cast<uint64_t>(p.H) * kDh, static_cast<uint64_t>(T), static_cast<uint64_t>(p.B)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * static_cast<uint64_t>(T)};
+    return encode_tmap_bf16(m, base, 3, dims, strides, box);
+  };
+  int rc;
+  if ((rc = enc(&tq, Q, ldq, p.Tq))) return rc;
+  if ((rc = enc(&tk, K, ldk, p.Tk))) return rc;
+  if ((rc = enc(&tv, V, ldv, p.Tk))) return rc;
+  LTXB_CUDA(launch_kernel(kernel, dim3(static_cast<unsigned>(jobs)), dim3(kPairThreads), smem, stream, 1, tq, tk, tv, p));
+  return LTXB_OK;
+}
+
+int launch_attention_partial(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, AttnParams p,
+                             int dh, float* part_o, float* part_ml, cudaStream_t stream) {
+  if (dh == 128) return launch_partial<128>(Q, ldq, K, ldk, V, ldv, p, part_o, part_ml, stream);
+  return launch_partial<64>(Q, ldq, K, ldk, V, ldv, p, part_o, part_ml, stream);
+}
+
+int launch_attention_merge(AttnParams p, int dh, const float* parts, long long part_stride, int n_parts, cudaStream_t stream) {
+  p.n_qp = (p.Tq + 255) / 256;
+  const long long jobs = static_cast<long long>(p.B) * p.H * p.n_qp;
+  p.n_full = 0;
+  p.n_split = n_parts;
+  p.part_rows = p.n_qp == 1 ? p.Tq : 256;
+  const long long rows = jobs * p.part_rows;
+  // part i: [rows][dh] floats at parts + i*part_stride, then [rows][2]
+  LTXB_CHECK_ARG(part_stride >= rows * (dh + 2) && part_stride % 4 == 0, "ltxb_attention_merge: part stride %lld too small / misaligned for %lld rows",
+                 part_stride, rows);
+  p.ws_o = const_cast<float*>(parts);
+  p.ws_ml = const_cast<float*>(parts) + rows * dh;
+  p.cmb_job_stride = p.part_rows;
+  p.cmb_part_o = part_stride;
+  p.cmb_part_ml = part_stride;
+  const int warps = static_cast<int>(jobs * p.part_rows);
+  if (dh == 128) LTXB_CUDA(launch_kernel(attention_combine_kernel<128>, dim3((warps + 7) / 8), dim3(256), 0, stream, 1, p, static_cast<int>(jobs)));
+  else LTXB_CUDA(launch_kernel(attention_combine_kernel<64>, dim3((warps + 7) / 8), dim3(256), 0, stream, 1, p, static_cast<int>(jobs)));
   return LTXB_OK;
 }
 

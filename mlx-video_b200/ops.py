@@ -482,6 +482,29 @@ def attention(
     return out
 
 
+def attention_partial_floats(B: int, Tq: int, H: int, dh: int) -> int:
+    return int(lib.ltxb_attention_partial_floats(B, Tq, H, dh))
+
+
+def attention_partial(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, part: torch.Tensor, B: int, Tq: int, Tk: int, H: int, dh: int,
+                      scale: float) -> torch.Tensor:
+    """Un-normalised attention over the given keys: part (f32, attention_partial_floats elements) <- [B*H*Tq][dh] | [B*H*Tq][2]."""
+    _prep(q)
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16 and part.dtype == torch.float32 and part.is_contiguous()
+    assert part.numel() >= attention_partial_floats(B, Tq, H, dh)
+    _call("ltxb_attention_partial", 4.0 * B * H * Tq * Tk * dh, q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), part.data_ptr(),
+          B, Tq, Tk, H, dh, scale, _stream())
+    return part
+
+
+def attention_merge(parts: torch.Tensor, out: torch.Tensor, B: int, Tq: int, H: int, dh: int) -> torch.Tensor:
+    """parts f32 [n_parts, block] (contiguous; block >= attention_partial_floats) -> out bf16 [B*Tq, H*dh] (log-sum-exp merge)."""
+    _prep(parts)
+    assert parts.dtype == torch.float32 and parts.dim() == 2 and parts.is_contiguous() and out.dtype == torch.bfloat16
+    _call("ltxb_attention_merge", 0.0, parts.data_ptr(), parts.shape[1], parts.shape[0], out.data_ptr(), _ld(out), B, Tq, H, dh, _stream())
+    return out
+
+
 def euler_step(
     x: torch.Tensor,
     v_pos: torch.Tensor,

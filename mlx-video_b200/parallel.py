@@ -226,20 +226,39 @@ class UlyssesGroup:
 
     def video_to_audio(self, attn, ws: Workspace, a_in: Tensor, v_in: Tensor, Ba: int, Ta: int, Tl: int, ax: Tensor, a, v,
                        gate: Tensor, gate_table: Tensor, row_div: int, row_index: Optional[Tensor]) -> None:
-        """v2a (transformer.py:326-339) with video rows sharded: project K/V on local rows, all-gather them,
-        attend redundantly on every rank (audio is replicated, so every rank computes the same update)."""
+        """v2a (transformer.py:326-339) with the video rows sharded: queries = the replicated audio stream, keys / values =
+        THIS rank's video rows.  Every rank attends over its own key slice and leaves the result un-normalised
+        (``ltxb_attention_partial``: O~, stabiliser, row sum — 264 bytes per (head, audio row)); the P slices are
+        all-gathered (0.57 MB per rank and block at 68 audio tokens, instead of 42 MB of projected video K/V at 5184 tokens)
+        and merged by log-sum-exp (``ltxb_attention_merge``) on every rank, which keeps the replicated audio stream
+        identical everywhere.  LTXB_V2A_LSE=0: the round-1 path (all-gather the projected K/V, attend redundantly)."""
+        import math
+        import os
+
         from . import ops
 
-        inner, dev = attn.inner_dim, a_in.device
+        inner, dev, H, dh = attn.inner_dim, a_in.device, attn.heads, attn.dim_head
         q, k, vv = attn.project(ws, "av.v2a", a_in, Ba, Ta, v_in, Tl, a.cross_positional_embeddings, v.cross_positional_embeddings)
-        kv_local = ws.get("av.v2a.kv", (Ba * Tl, 2 * inner), BF16, dev)  # the buffer k / vv are views of
-        if self.peers is not None:
-            parts = self.peers.all_gather("av.v2a.kv_all", kv_local)
+        if os.environ.get("LTXB_V2A_LSE", "1") != "0" and Ta <= 256:
+            n = ops.attention_partial_floats(Ba, Ta, H, dh)
+            part = ws.get("av.v2a.part", (n,), torch.float32, dev)
+            ops.attention_partial(q, k, vv, part, Ba, Ta, Tl, H, dh, 1.0 / math.sqrt(dh))
+            if self.peers is not None:
+                parts = self.peers.all_gather("av.v2a.parts", part)
+            else:
+                parts = ws.get("av.v2a.parts", (self.size, n), torch.float32, dev)
+                dist.all_gather_into_tensor(parts, part, group=self.group)
+            o = ws.get("av.v2a.o", (Ba * Ta, inner), BF16, dev)
+            ops.attention_merge(parts.view(self.size, n), o, Ba, Ta, H, dh)
         else:
-            parts = ws.get("av.v2a.kv_all", (self.size, Ba * Tl, 2 * inner), BF16, dev)
-            dist.all_gather_into_tensor(parts, kv_local, group=self.group)
-        full = parts.view(self.size * Tl, 2 * inner)
-        o = attn.sdpa(ws, "av.v2a", q, full[:, :inner], full[:, inner:], Ba, Ta, self.size * Tl, None)
+            kv_local = ws.get("av.v2a.kv", (Ba * Tl, 2 * inner), BF16, dev)  # the buffer k / vv are views of
+            if self.peers is not None:
+                parts = self.peers.all_gather("av.v2a.kv_all", kv_local)
+            else:
+                parts = ws.get("av.v2a.kv_all", (self.size, Ba * Tl, 2 * inner), BF16, dev)
+                dist.all_gather_into_tensor(parts, kv_local, group=self.group)
+            full = parts.view(self.size * Tl, 2 * inner)
+            o = attn.sdpa(ws, "av.v2a", q, full[:, :inner], full[:, inner:], Ba, Ta, self.size * Tl, None)
         ops.gemm(o, attn.to_out.weight, attn.to_out.bias, ax, _lib.EPI_RESID_GATE_F32, resid=ax, gate=gate,
                  gate_table=gate_table, gate_row_div=row_div, gate_row_index=row_index)
 

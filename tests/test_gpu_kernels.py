@@ -190,6 +190,33 @@ def test_attention_baseline_config_shapes(B, Tq, Tk, H, dh):
     assert torch.equal(out, out2), "attention is not deterministic"
 
 
+@pytest.mark.parametrize("B,Tq,Tk,H,dh,parts", [(1, 68, 5184, 32, 64, 8), (1, 68, 1296, 32, 64, 4), (2, 37, 300, 4, 128, 3), (1, 130, 648, 8, 64, 2)])
+def test_attention_partial_and_merge(B, Tq, Tk, H, dh, parts):
+    """Video->audio attention under sequence parallelism: un-normalised attention over key SLICES (ltxb_attention_partial)
+    merged by log-sum-exp (ltxb_attention_merge) == attention over all keys (attention.py:13-53)."""
+    g = torch.Generator(device=DEV).manual_seed(13)
+    D = H * dh
+    q = torch.randn(B * Tq, D, device=DEV, generator=g).bfloat16()
+    k = (torch.randn(B, Tk, D, device=DEV, generator=g) * 1.5).bfloat16()
+    v = torch.randn(B, Tk, D, device=DEV, generator=g).bfloat16()
+    n = ops.attention_partial_floats(B, Tq, H, dh)
+    blocks = torch.zeros(parts, n, device=DEV)
+    Tl = Tk // parts
+    for i in range(parts):
+        ks, vs = k[:, i * Tl:(i + 1) * Tl].reshape(B * Tl, D).contiguous(), v[:, i * Tl:(i + 1) * Tl].reshape(B * Tl, D).contiguous()
+        ops.attention_partial(q, ks, vs, blocks[i], B, Tq, Tl, H, dh, 1.0 / math.sqrt(dh))
+    out = torch.empty(B * Tq, D, device=DEV, dtype=torch.bfloat16)
+    ops.attention_merge(blocks, out, B, Tq, H, dh)
+    used = Tl * parts
+    ref = _attention_ref_fp32(q, k[:, :used].reshape(B * used, D), v[:, :used].reshape(B * used, D), B, Tq, used, H, dh)
+    err = rel_l2(out.float(), ref)
+    assert torch.isfinite(out.float()).all() and err <= 8e-3, f"partial+merge rel_l2 {err:.3e}"
+    # one part == plain attention, to the bf16 rounding of the output
+    whole = torch.empty_like(out)
+    ops.attention(q, k[:, :used].reshape(B * used, D), v[:, :used].reshape(B * used, D), whole, B, Tq, used, H, dh, 1.0 / math.sqrt(dh))
+    assert rel_l2(out.float(), whole.float()) <= 8e-3
+
+
 def test_rmsnorm_layernorm_modulate():
     g = torch.Generator(device=DEV).manual_seed(1)
     for R, D in [(1280, 4096), (68, 2048), (37, 512), (5, 1032)]:
