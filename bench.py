@@ -241,16 +241,24 @@ def parity_check(M, par, audio: bool, use_cfg: bool, dev, world: int, rank: int)
         sharded = M.LTXModel(pcfg, device=dev)
         sharded.load_weights(tensors)
         par.attach(sharded)
+        def rel(a, b):
+            return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
         if par.cfg is not None:
             mine, _ = sharded(*mods(ctx_p if par.cfg.is_cond else ctx_n))
             got = list(par.cfg.exchange(mine))
-            same = all(torch.equal(g_, r_[0]) for g_, r_ in zip(got, refs))
+            pairs = [(g_, r_[0]) for g_, r_ in zip(got, refs)]
         else:
             gv, ga = sharded(*mods(ctx_p))
-            same = torch.equal(gv, refs[0][0]) and (not audio or torch.equal(ga, refs[0][1]))
-        flag = torch.tensor([1 if same else 0], device=dev, dtype=torch.int32)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        out["bit_identical"] = bool(int(flag.item()))
+            pairs = [(gv, refs[0][0])] + ([(ga, refs[0][1])] if audio else [])
+        same = all(torch.equal(g_, r_) for g_, r_ in pairs)
+        worst = max(rel(g_, r_) for g_, r_ in pairs)
+        stats = torch.tensor([1.0 if same else 0.0, -worst], device=dev, dtype=torch.float64)
+        dist.all_reduce(stats, op=dist.ReduceOp.MIN)
+        # bit identity holds when the shards happen to take the same tile / key-split schedule as the whole problem; what is
+        # required is agreement to summation order: rel-L2 <= 5e-3 against the un-sharded model on the same GPU
+        out["bit_identical"] = bool(stats[0].item() > 0.5)
+        out["rel_l2_vs_single_gpu"] = float(-stats[1].item())
         out["layout"] = par.describe()
     if rank == 0:
         torch.set_num_threads(os.cpu_count() or 1)
@@ -262,7 +270,7 @@ def parity_check(M, par, audio: bool, use_cfg: bool, dev, world: int, rank: int)
         if audio:
             ga = refs[0][1].cpu().double()
             out["audio_rel_l2_vs_oracle"] = float((ga - wa.double()).norm() / wa.double().norm())
-        out["ok"] = bool(out["rel_l2_vs_oracle"] <= 1e-2 and out["cosine_vs_oracle"] >= 0.999 and out.get("bit_identical", True))
+        out["ok"] = bool(out["rel_l2_vs_oracle"] <= 1e-2 and out["cosine_vs_oracle"] >= 0.999 and out.get("rel_l2_vs_single_gpu", 0.0) <= 5e-3)
     del single
     torch.cuda.empty_cache()
     return out
