@@ -34,9 +34,20 @@ constexpr int kGemmThreads = 384;  // warp 0 TMA, warp 1 MMA, warps 2,3 idle, wa
 // (setmaxnreg): 128 * 104 + 256 * 200 <= 64 K
 constexpr int kRegsIssue = 104, kRegsEpilogue = 200;
 constexpr int kEpiThreads = 256;
-constexpr int kSmemHeader = 1024;  // barriers + tmem pointer live in front of the tile ring
+constexpr int kSmemHeader = 2048;  // barriers, tmem pointer and the tile's bias slice live in front of the tile ring
 constexpr int kTmemCols = 512;
 constexpr uint32_t kAccStride = 256;  // TMEM column stride between the two accumulators
+
+// LTXB_GEMM_TRACE: CTA 0 records clock64() at its life-cycle events into the first bytes of the split-K partial
+// workspace (long long [16]); scripts/gemm_trace.py prints them.
+#ifdef LTXB_GEMM_TRACE
+#define GTRACE(ev)                                                                                           \
+  do {                                                                                                       \
+    if (blockIdx.x == 0 && p.sk_partials != nullptr) reinterpret_cast<long long*>(p.sk_partials)[(ev)] = clock64(); \
+  } while (0)
+#else
+#define GTRACE(ev) do {} while (0)
+#endif
 
 struct GemmParams {
   int M, N, K;
@@ -135,6 +146,10 @@ struct GemmSmemHeader {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
+  // bias[n0, n0 + bn) of the tile being stored: fetched ONCE per tile by the epilogue warps while the main loop still runs,
+  // instead of one dependent global round trip per 32-column chunk and warp (the epilogue of a tile is a latency chain:
+  // LTXB_GEMM_TRACE showed ~3 k cycles per chunk, 12 k per 256-column tile, fully exposed when a CTA owns a single tile)
+  alignas(16) float bias[256];
 };
 static_assert(sizeof(GemmSmemHeader) <= kSmemHeader, "header overflow");
 
@@ -143,15 +158,15 @@ __device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 
 // Apply the fused epilogue to `n` (16 or 32) consecutive accumulator columns of one output row.
 template <int kEpi, int kCols>
 __device__ __forceinline__ void epilogue_store(const GemmParams& p, const uint32_t* acc, long long row, int col,
-                                               long long grow) {
+                                               long long grow, const float* sbias) {
   float v[kCols];
 #pragma unroll
   for (int i = 0; i < kCols; ++i) v[i] = __uint_as_float(acc[i]);
   if (p.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+    const float4* b4 = reinterpret_cast<const float4*>(sbias);  // shared memory: this chunk's slice of the staged bias
 #pragma unroll
     for (int i = 0; i < kCols / 4; ++i) {
-      const float4 b = __ldg(b4 + i);
+      const float4 b = b4[i];
       v[4 * i + 0] += b.x;
       v[4 * i + 1] += b.y;
       v[4 * i + 2] += b.z;
@@ -226,6 +241,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) GTRACE(0);  // kernel entry
   const uint32_t cta_rank = (kCtas == 2) ? cluster_ctarank() : 0u;
   const bool is_leader = (cta_rank == 0);
   const int num_clusters = gridDim.x / kCtas;
@@ -263,8 +279,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if constexpr (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&hdr->tmem_base);
+  if (threadIdx.x == 0) GTRACE(1);  // barriers + TMEM + cluster sync done
   pdl_launch_dependents();
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
+  if (threadIdx.x == 0) GTRACE(2);  // predecessor complete
 
   if (warp < 4) {
   reg_dealloc<kRegsIssue>();
@@ -320,6 +338,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&hdr->full[stage], phase);
+          if (kb == w.kb0) GTRACE(3);  // first operands of this item landed
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(tiles + static_cast<size_t>(stage) * stage_bytes);
           const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
@@ -333,6 +352,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
         }
         if constexpr (kCtas == 1) umma_commit(&hdr->tmem_full[acc]); else umma_commit_pair(&hdr->tmem_full[acc], 3);
+        GTRACE(4);  // all MMAs of this item issued
         if (++acc == 2) acc = 0, acc_phase ^= 1;
       }
     }
@@ -385,6 +405,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         float* slot = p.sk_partials + (static_cast<size_t>(cluster) * kCtas + cta_rank) * slot_elems;
         return reinterpret_cast<float4*>(slot + static_cast<size_t>(c / 32) * (kBlockM * 32)) + row_in_cta;
       };
+      if (p.bias != nullptr && !(partial && !owner)) {  // contributors store raw partials: no bias
+        epilogue_bar_sync();  // the previous tile's chunks have all read their bias
+        const int t = threadIdx.x - 128;
+        if (t < bn) hdr->bias[t] = (n0 + t < p.N) ? __ldg(p.bias + n0 + t) : 0.f;
+        epilogue_bar_sync();
+      }
       int* counter = p.sk_counters + w.tile * kCtas + static_cast<int>(cta_rank);
       int others = 0;  // owner: number of parked partials to add, held by clusters contrib(0) .. contrib(others-1) in k order
       // lockstep split: piece o+1 of tile t sits on cluster t + (o+1)*sk_rem; contiguous: on the next clusters in line
@@ -406,11 +432,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
           *counter = 0;  // every contributor has arrived; ready for the next launch
+          GTRACE(9);  // owner: all partials parked
         }
         epilogue_bar_sync();
         __threadfence();
       }
       mbar_wait(&hdr->tmem_full[acc], acc_phase);
+      if (epi_leader) GTRACE(5);  // accumulator complete
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccStride;
       auto finish_chunk = [&](const float* v, int c, int width) {
@@ -418,9 +446,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (!row_ok) return;
         const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
         if (width == 32 && col + 32 <= p.N) {
-          epilogue_store<kEpi, 32>(p, r, row, col, grow);
+          epilogue_store<kEpi, 32>(p, r, row, col, grow, hdr->bias + c);
         } else if (col + 16 <= p.N) {
-          epilogue_store<kEpi, 16>(p, r, row, col, grow);
+          epilogue_store<kEpi, 16>(p, r, row, col, grow, hdr->bias + c);
         }
       };
       if (c_begin >= c_end && !(partial && !owner)) release_acc();  // nothing to read for this warp (narrow tile)
@@ -435,9 +463,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (last) release_acc();
             if (row_ok) {
               if (col + 32 <= p.N) {
-                epilogue_store<kEpi, 32>(p, r, row, col, grow);
+                epilogue_store<kEpi, 32>(p, r, row, col, grow, hdr->bias + c);
               } else if (col + 16 <= p.N) {
-                epilogue_store<kEpi, 16>(p, r, row, col, grow);
+                epilogue_store<kEpi, 16>(p, r, row, col, grow, hdr->bias + c);
               }
             }
           } else {  // 16-column tail of a BN that is not a multiple of 32
@@ -445,7 +473,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tmem_ld_x16(t_row + c, r);
             tmem_wait_ld();
             release_acc();
-            if (row_ok && col + 16 <= p.N) epilogue_store<kEpi, 16>(p, r, row, col, grow);
+            if (row_ok && col + 16 <= p.N) epilogue_store<kEpi, 16>(p, r, row, col, grow, hdr->bias + c);
           }
         }
       } else if (!owner) {
@@ -474,13 +502,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (epi_leader) atomicAdd(counter, 1);
       } else {
         // ---- owner: own accumulator (TMEM) + the parked partials of pieces 1.. in k order.  The loads of up to
-        // three partials for a 32-column chunk are issued together (the fix-up is a latency-bound L2 read).
+        // kFixBatch partials for a 32-column chunk are issued together: the fix-up is a chain of L2 round trips (measured
+        // with LTXB_GEMM_TRACE at M = 160, N = K = 4096: 20 k cycles of fix-up behind a 19 k-cycle main loop when three
+        // partials took two trips per chunk), so every trip saved is ~1.5 k cycles per chunk.
         for (int c = c_begin; c < c_end; c += 32) {
           const int width = (c + 32 <= bn) ? 32 : 16;
-          float4 ld[2][8];
-          const int batch = min(others, 2);
+          constexpr int kFixBatch = 4;
+          float4 ld[kFixBatch][8];
+          const int batch = min(others, kFixBatch);
 #pragma unroll
-          for (int o = 0; o < 2; ++o) {
+          for (int o = 0; o < kFixBatch; ++o) {
             if (o < batch) {
               const float4* src = chunk_of(cluster_id + (o + 1) * contrib_stride, c);
 #pragma unroll
@@ -504,14 +535,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           if (c + 32 >= c_end) release_acc();
 #pragma unroll
-          for (int o = 0; o < 2; ++o) {
+          for (int o = 0; o < kFixBatch; ++o) {
             if (o < batch) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 if (i * 4 < width) v[4 * i] += ld[o][i].x, v[4 * i + 1] += ld[o][i].y, v[4 * i + 2] += ld[o][i].z, v[4 * i + 3] += ld[o][i].w;
             }
           }
-          for (int o = 2; o < others; ++o) {
+          for (int o = kFixBatch; o < others; ++o) {
             const float4* src = chunk_of(cluster_id + (o + 1) * contrib_stride, c);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -522,8 +553,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
           finish_chunk(v, c, width);
+          if (epi_leader && c == c_begin) GTRACE(10);  // owner: first chunk reduced and stored
         }
       }
+      if (epi_leader) GTRACE(6);  // epilogue of this item done (stores issued)
       if (++acc == 2) acc = 0, acc_phase ^= 1;
     }
   }
@@ -532,10 +565,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncwarp();
   tc_fence_before_sync();
   if constexpr (kCtas == 2) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x == 0) GTRACE(7);  // teardown sync passed
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc<kCtas>(tmem_base, kTmemCols);
   }
+  if (threadIdx.x == 32) GTRACE(8);  // TMEM released
 }
 
 // ------------------------------------------------------------------------------------------------
