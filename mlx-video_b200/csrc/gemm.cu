@@ -34,7 +34,7 @@ constexpr int kGemmThreads = 384;  // warp 0 TMA, warp 1 MMA, warps 2,3 idle, wa
 // (setmaxnreg): 128 * 104 + 256 * 200 <= 64 K
 constexpr int kRegsIssue = 104, kRegsEpilogue = 200;
 constexpr int kEpiThreads = 256;
-constexpr int kSmemHeader = 2048;  // barriers, tmem pointer and the tile's bias slice live in front of the tile ring
+constexpr int kSmemHeader = 1024;  // barriers + tmem pointer live in front of the tile ring
 constexpr int kTmemCols = 512;
 constexpr uint32_t kAccStride = 256;  // TMEM column stride between the two accumulators
 
@@ -146,10 +146,6 @@ struct GemmSmemHeader {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
-  // bias[n0, n0 + bn) of the tile being stored: fetched ONCE per tile by the epilogue warps while the main loop still runs,
-  // instead of one dependent global round trip per 32-column chunk and warp (the epilogue of a tile is a latency chain:
-  // LTXB_GEMM_TRACE showed ~3 k cycles per chunk, 12 k per 256-column tile, fully exposed when a CTA owns a single tile)
-  alignas(16) float bias[256];
 };
 static_assert(sizeof(GemmSmemHeader) <= kSmemHeader, "header overflow");
 
@@ -158,15 +154,18 @@ __device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 
 // Apply the fused epilogue to `n` (16 or 32) consecutive accumulator columns of one output row.
 template <int kEpi, int kCols>
 __device__ __forceinline__ void epilogue_store(const GemmParams& p, const uint32_t* acc, long long row, int col,
-                                               long long grow, const float* sbias) {
+                                               long long grow) {
   float v[kCols];
 #pragma unroll
   for (int i = 0; i < kCols; ++i) v[i] = __uint_as_float(acc[i]);
   if (p.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(sbias);  // shared memory: this chunk's slice of the staged bias
+    // (tried: the tile's bias slice staged in shared memory once per tile instead of one global round trip per chunk —
+    // the epilogue of a single tile got shorter, 12.3 k -> 8.9 k cycles, but the two extra named barriers per tile cost
+    // more in the multi-tile kernels: +0.35 ms per step in a same-box A/B, profiles/r2/gemm_small_m.md)
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
     for (int i = 0; i < kCols / 4; ++i) {
-      const float4 b = b4[i];
+      const float4 b = __ldg(b4 + i);
       v[4 * i + 0] += b.x;
       v[4 * i + 1] += b.y;
       v[4 * i + 2] += b.z;
@@ -405,12 +404,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         float* slot = p.sk_partials + (static_cast<size_t>(cluster) * kCtas + cta_rank) * slot_elems;
         return reinterpret_cast<float4*>(slot + static_cast<size_t>(c / 32) * (kBlockM * 32)) + row_in_cta;
       };
-      if (p.bias != nullptr && !(partial && !owner)) {  // contributors store raw partials: no bias
-        epilogue_bar_sync();  // the previous tile's chunks have all read their bias
-        const int t = threadIdx.x - 128;
-        if (t < bn) hdr->bias[t] = (n0 + t < p.N) ? __ldg(p.bias + n0 + t) : 0.f;
-        epilogue_bar_sync();
-      }
       int* counter = p.sk_counters + w.tile * kCtas + static_cast<int>(cta_rank);
       int others = 0;  // owner: number of parked partials to add, held by clusters contrib(0) .. contrib(others-1) in k order
       // lockstep split: piece o+1 of tile t sits on cluster t + (o+1)*sk_rem; contiguous: on the next clusters in line
@@ -446,9 +439,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (!row_ok) return;
         const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
         if (width == 32 && col + 32 <= p.N) {
-          epilogue_store<kEpi, 32>(p, r, row, col, grow, hdr->bias + c);
+          epilogue_store<kEpi, 32>(p, r, row, col, grow);
         } else if (col + 16 <= p.N) {
-          epilogue_store<kEpi, 16>(p, r, row, col, grow, hdr->bias + c);
+          epilogue_store<kEpi, 16>(p, r, row, col, grow);
         }
       };
       if (c_begin >= c_end && !(partial && !owner)) release_acc();  // nothing to read for this warp (narrow tile)
@@ -463,9 +456,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (last) release_acc();
             if (row_ok) {
               if (col + 32 <= p.N) {
-                epilogue_store<kEpi, 32>(p, r, row, col, grow, hdr->bias + c);
+                epilogue_store<kEpi, 32>(p, r, row, col, grow);
               } else if (col + 16 <= p.N) {
-                epilogue_store<kEpi, 16>(p, r, row, col, grow, hdr->bias + c);
+                epilogue_store<kEpi, 16>(p, r, row, col, grow);
               }
             }
           } else {  // 16-column tail of a BN that is not a multiple of 32
@@ -473,7 +466,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tmem_ld_x16(t_row + c, r);
             tmem_wait_ld();
             release_acc();
-            if (row_ok && col + 16 <= p.N) epilogue_store<kEpi, 16>(p, r, row, col, grow, hdr->bias + c);
+            if (row_ok && col + 16 <= p.N) epilogue_store<kEpi, 16>(p, r, row, col, grow);
           }
         }
       } else if (!owner) {
@@ -502,12 +495,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (epi_leader) atomicAdd(counter, 1);
       } else {
         // ---- owner: own accumulator (TMEM) + the parked partials of pieces 1.. in k order.  The loads of up to
-        // kFixBatch partials for a 32-column chunk are issued together: the fix-up is a chain of L2 round trips (measured
-        // with LTXB_GEMM_TRACE at M = 160, N = K = 4096: 20 k cycles of fix-up behind a 19 k-cycle main loop when three
-        // partials took two trips per chunk), so every trip saved is ~1.5 k cycles per chunk.
+        // kFixBatch partials for a 32-column chunk are issued together (the fix-up is a chain of L2 round trips; measured
+        // with LTXB_GEMM_TRACE at M = 160, N = K = 4096: 20 k cycles of fix-up behind a 19 k-cycle main loop.  Batching four
+        // instead of two did not shorten it — the row-per-lane stores, ~1 k LSU wavefronts per chunk and CTA, pace it).
         for (int c = c_begin; c < c_end; c += 32) {
           const int width = (c + 32 <= bn) ? 32 : 16;
-          constexpr int kFixBatch = 4;
+          constexpr int kFixBatch = 2;
           float4 ld[kFixBatch][8];
           const int batch = min(others, kFixBatch);
 #pragma unroll
