@@ -44,6 +44,8 @@ WORKLOADS = {
     # BASELINE configs[4]: distilled stage 2 of 1280x704x121 -> 40x22x16 = 14080 video tokens
     "long": dict(grid=(16, 22, 40), Tc=1024, cfg=1.0, desc="LTX-2 19B video-only DiT, 48 blocks, distilled stage-2, 1280x704x121 (40x22x16=14080 tokens), 1024 text tokens"),
     # BASELINE configs[3]: joint audio+video model, 768x768x65 + 68 audio latents (audio<->video cross-attention in every block)
+    # debug stand-in (not a BASELINE config): the GEMM rows ONE rank sees in the 8-GPU distilled run (1280 / 8 = 160 tokens)
+    "shard160": dict(grid=(1, 10, 16), Tc=1024, cfg=1.0, desc="debug: 160 video tokens on one GPU = the per-rank GEMM shapes of the 8-GPU distilled run"),
     "av": dict(grid=(9, 24, 24), Tc=1024, cfg=1.0, Ta=68, desc="LTX-2 19B audio+video DiT, 48 blocks, 768x768x65 (5184 video + 68 audio tokens), 1024 text tokens per modality"),
 }
 

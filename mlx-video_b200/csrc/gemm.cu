@@ -17,6 +17,7 @@
 //     count fills whole waves of 148 SMs (e.g. M=1280, N=4096: BN=144 in pair mode -> 145 tiles on 74
 //     pairs = 96 % wave efficiency instead of 54 % at BN=256).
 #include "common.cuh"
+#include "gemm_small_m.cuh"
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -605,7 +606,7 @@ static TileChoice choose_tile(int M, int N, int sms, int want_bn, int want_pair)
 // ---- stream-K workspace: registered by the host framework (the library never allocates) -----------
 constexpr int kMaxDevices = 16;
 constexpr long long kSkCounterInts = 1 << 16;                                  // arrivals: [tiles][ctas]
-constexpr long long kSkPartialBytes = 148ll * kBlockM * 256 * sizeof(float);  // [<=148 CTAs][128 x 256] fp32 parked partials
+constexpr long long kSkPartialBytes = 296ll * kBlockM * 256 * sizeof(float);  // [<=148 CTAs][128 x 256] fp32 parked partials (big tiles); [<=296 CTAs][128 x <=256] or [<=148][128 x <=512] (small-M kernel)
 struct SkWorkspace {
   int* counters = nullptr;
   float* partials = nullptr;
@@ -684,8 +685,8 @@ extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   LTXB_CHECK_SUPPORTED(lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0 && (lda >= K || epi->a_group_cols > 0) && ldw >= K && ldo >= N,
                        "ltxb_gemm_bf16: leading dimensions must be multiples of 8 and cover the row");
   LTXB_CHECK_ARG(epi->mode >= 0 && epi->mode < LTXB_EPI_COUNT, "ltxb_gemm_bf16: bad epilogue mode %d", epi->mode);
-  LTXB_CHECK_ARG(cta_pair >= -1 && cta_pair <= 3, "ltxb_gemm_bf16: cta_pair=%d not in [-1, 3]", cta_pair);
-  LTXB_CHECK_ARG(block_n == 0 || (block_n >= 32 && block_n <= 256 && block_n % 16 == 0),
+  LTXB_CHECK_ARG(cta_pair >= -1 && cta_pair <= 4, "ltxb_gemm_bf16: cta_pair=%d not in [-1, 4]", cta_pair);
+  LTXB_CHECK_ARG(cta_pair == 4 || block_n == 0 || (block_n >= 32 && block_n <= 256 && block_n % 16 == 0),
                  "ltxb_gemm_bf16: block_n=%d must be 0 or a multiple of 16 in [32,256]", block_n);
   if (epi->bias) LTXB_CHECK_ARG(aligned16(epi->bias), "ltxb_gemm_bf16: bias must be 16-byte aligned");
   if (epi->mode == LTXB_EPI_RESID_GATE_F32) {
@@ -704,6 +705,21 @@ extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   if (sms <= 0) return set_error(LTXB_ERR_NO_DEVICE, "ltxb_gemm_bf16: no CUDA device");
   static const int env_pair = [] { const char* e = getenv("LTXB_GEMM_PAIR"); return e ? atoi(e) : -1; }();
   static const int env_bn = [] { const char* e = getenv("LTXB_GEMM_BN"); return e ? atoi(e) : 0; }();
+  // Few rows (a sequence-parallel shard, the audio stream, AdaLN rows): the weight-streaming kernel with swapped operands
+  // (gemm_small_m.cu).  cta_pair 4 forces it (block_n then = number of k-range splits, 0 = choose); LTXB_GEMM_SMALL_M is the
+  // largest M the library sends there on its own (0 disables).
+  {
+    static const int env_small_m = [] { const char* e = getenv("LTXB_GEMM_SMALL_M"); return e ? atoi(e) : 256; }();
+    const bool forced = (cta_pair == 4);
+    if (forced) LTXB_CHECK_SUPPORTED(gemm_small_m_supported(M, N, K), "ltxb_gemm_bf16: the small-M kernel needs M <= 512 (M=%d N=%d K=%d)", M, N, K);
+    if (forced || (cta_pair < 0 && block_n == 0 && M <= env_small_m && N >= 128 && K >= 256 && gemm_small_m_supported(M, N, K) && env_pair < 0 && env_bn == 0)) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      const SkWorkspace ws = (dev >= 0 && dev < kMaxDevices) ? g_sk_ws[dev] : SkWorkspace{};
+      return launch_gemm_small_m(A, lda, W, ldw, out, ldo, M, N, K, epi, ws.partials, ws.partials ? kSkPartialBytes : 0, ws.counters,
+                                 forced ? block_n : 0, reinterpret_cast<cudaStream_t>(stream));
+    }
+  }
   if (cta_pair < 0) cta_pair = env_pair;
   if (block_n == 0) block_n = env_bn;
   // cta_pair 2 / 3: force the contiguous stream-K schedule with single-CTA / pair tiles (tests, sweeps)

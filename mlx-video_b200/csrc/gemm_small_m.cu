@@ -1,0 +1,490 @@
+// K1 for FEW rows: out = epilogue(A[M,K] . W[N,K]^T) with M <= 512 — the weight-streaming regime.
+//
+// Where it runs: the sequence-parallel shards of the LTX-2 DiT (1280 tokens on 8 GPUs = 160 rows per rank against the
+// full 4096 / 16384-wide weights), the audio stream (68 tokens per sample) and the AdaLN tables (one row per sample):
+// the same nn.Linear call sites as gemm.cu (attention.py:91-93,100,123-126,142; feed_forward.py:31,33; adaln.py:27,130-132).
+// A tile of the big kernel is 256 token rows x 256 weight rows: at M = 160 it spends the tensor time of 256 rows, holds only
+// 64 KB of weights in flight per SM and pays an 8 us prologue / fix-up / teardown (profiles/r2/gemm_small_m.md).
+//
+// Design (B200 / sm_100a) — the operands are SWAPPED:
+//   * the WEIGHT rows are the MMA's M dimension (TMEM lanes): one CTA pair (cta_group::2) owns 256 weight rows, 128 per
+//     CTA; the TOKENS are the MMA's N dimension (16 .. 256 columns, one or two MMAs per k-slice), so the tensor work and
+//     the TMEM footprint scale with the token count and nothing is padded to 128 rows;
+//   * each CTA of the pair stages its own 128 weight rows (16 KB per k-block, from HBM) and HALF of the token rows
+//     (from L2) — the pair MMA reads the B operand from both CTAs' shared memory, which halves the L2 -> SM traffic of
+//     re-reading the activations per weight tile;
+//   * one (weight tile, k-range) per CTA pair, no persistence: grid = tiles x splits pairs, all co-resident, two CTAs
+//     per SM when the token count fits 256 TMEM columns (2 x 4 stages x 16 KB of weights in flight per SM);
+//   * split-K is a reduce-scatter through L2: every pair parks the 8-token chunks it does not own, all pairs of a tile
+//     meet at a counter, and each adds the others' parts to the chunks it owns, in split order (run-to-run
+//     reproducible), then applies the fused epilogue;
+//   * in the epilogue a thread owns one OUTPUT COLUMN (its TMEM lane) and walks the tokens, so the 32 lanes of a warp
+//     store 32 consecutive columns of one row: coalesced 64 / 128-byte stores instead of one row per lane.
+#include "common.cuh"
+#include "gemm_small_m.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace ltxb {
+
+constexpr int kWsTileRows = 128;  // weight rows (= output columns) per CTA: the TMEM lanes
+constexpr int kWsBlockK = 64;     // 64 bf16 = one 128-byte swizzle span
+constexpr int kWsThreads = 320;   // warp 0 TMA producer, warp 1 MMA issuer + TMEM, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kWsMaxStages = 8;
+constexpr int kWsChunk = 8;  // tokens per reduce-scatter chunk
+constexpr int kWsHeader = 1024;
+constexpr uint32_t kWsWBytes = kWsTileRows * kWsBlockK * 2;
+constexpr int kWsDepartOffset = 1 << 15;  // counters: arrivals at [0, 32768), departures behind them
+
+struct WsParams {
+  int M, N, K;
+  int m_pad;      // token columns of the accumulator (multiple of 16; of 32 when n_mma == 2)
+  int n_mma;      // MMAs per k-slice: 1 (m_pad <= 256) or 2
+  int tmem_cols;  // power of two >= m_pad
+  int num_stages;
+  int splits;  // k-range pieces per weight tile
+  const float* bias;
+  void* out;
+  long long ldo;
+  const float* resid;
+  long long ldr;
+  const float* gate;
+  long long gate_ld;
+  int gate_row_div;
+  const int* gate_row_index;
+  const float* gate_table;
+  int a_group_cols;
+  float* partials;  // [grid][m_pad / 8][2][128] float4: parked chunks
+  int* counters;
+  long long* trace;  // LTXB_WS_DEBUG builds, debug & 8: [grid][4] globaltimer at PDL wait / accumulator / met / done (tail of the workspace)
+  int debug;  // LTXB_WS_DEBUG builds only: 1 = no token loads after the first k-block, 2 = no epilogue, 4 = no weight loads
+              // after the first k-block, 8 = every CTA records its life-cycle times (timing experiments; results are wrong)
+};
+#ifdef LTXB_WS_DEBUG
+__device__ __forceinline__ long long ws_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define WS_DBG(bit) ((p.debug & (bit)) != 0)
+#else
+#define WS_DBG(bit) false
+#endif
+
+struct WsSmemHeader {
+  uint64_t full[kWsMaxStages];
+  uint64_t empty[kWsMaxStages];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+};
+static_assert(sizeof(WsSmemHeader) <= kWsHeader, "header overflow");
+
+__device__ __forceinline__ void ws_epilogue_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// Fused epilogue for the 8 tokens [m0, m0 + 8) of output column n (one thread): the warp's 32 lanes hold 32 consecutive
+// columns, so every load / store below is one contiguous 64- or 128-byte piece per token.
+template <int kEpi>
+__device__ __forceinline__ void ws_finish_chunk(const WsParams& p, const float* acc, int m0, long long n, float bias_n,
+                                                float table_n) {
+  float v[kWsChunk];
+#pragma unroll
+  for (int i = 0; i < kWsChunk; ++i) v[i] = acc[i] + bias_n;
+  if constexpr (kEpi == LTXB_EPI_GELU_BF16) {
+#pragma unroll
+    for (int i = 0; i < kWsChunk; ++i) v[i] = gelu_tanh(v[i]);
+  } else if constexpr (kEpi == LTXB_EPI_SILU_BF16) {
+#pragma unroll
+    for (int i = 0; i < kWsChunk; ++i) v[i] = silu(v[i]);
+  }
+  if constexpr (kEpi == LTXB_EPI_BIAS_BF16 || kEpi == LTXB_EPI_GELU_BF16 || kEpi == LTXB_EPI_SILU_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + n;
+#pragma unroll
+    for (int i = 0; i < kWsChunk; ++i)
+      if (m0 + i < p.M) o[static_cast<long long>(m0 + i) * p.ldo] = __float2bfloat16_rn(v[i]);
+  } else if constexpr (kEpi == LTXB_EPI_BIAS_F32) {
+    float* o = reinterpret_cast<float*>(p.out) + n;
+#pragma unroll
+    for (int i = 0; i < kWsChunk; ++i)
+      if (m0 + i < p.M) o[static_cast<long long>(m0 + i) * p.ldo] = v[i];
+  } else {  // LTXB_EPI_RESID_GATE_F32; `out` normally IS `resid`: read the whole chunk before the first store
+    float r[kWsChunk], g[kWsChunk];
+#pragma unroll
+    for (int i = 0; i < kWsChunk; ++i) {
+      const int m = m0 + i;
+      r[i] = 0.f, g[i] = 1.f;
+      if (m < p.M) {
+        r[i] = p.resid[static_cast<long long>(m) * p.ldr + n];
+        if (p.gate != nullptr) {
+          const long long grow = p.gate_row_index != nullptr ? __ldg(p.gate_row_index + m) : m / p.gate_row_div;
+          g[i] = __ldg(p.gate + grow * p.gate_ld + n) + table_n;
+        }
+      }
+    }
+    float* o = reinterpret_cast<float*>(p.out) + n;
+#pragma unroll
+    for (int i = 0; i < kWsChunk; ++i)
+      if (m0 + i < p.M) o[static_cast<long long>(m0 + i) * p.ldo] = fmaf(v[i], g[i], r[i]);
+  }
+}
+
+template <int kEpi>
+__global__ void __launch_bounds__(kWsThreads, 2)
+gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const WsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  WsSmemHeader* hdr = reinterpret_cast<WsSmemHeader*>(smem);
+  uint8_t* tiles = smem + kWsHeader;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool is_leader = (cta_rank == 0);
+  const int pair_id = blockIdx.x >> 1;
+  const int tile = pair_id / p.splits;
+  const int split = pair_id - tile * p.splits;
+  const int num_kb = p.K / kWsBlockK;
+  const int kb0 = (num_kb * split) / p.splits;
+  const int kb1 = (num_kb * (split + 1)) / p.splits;
+  const int mma_n = p.m_pad / p.n_mma;  // tokens per MMA
+  const int box_rows = mma_n / 2;       // token rows this CTA stages per MMA
+  const uint32_t x_box_bytes = box_rows * kWsBlockK * 2;
+  const uint32_t stage_bytes = kWsWBytes + p.n_mma * x_box_bytes;
+  const int num_stages = p.num_stages;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < num_stages; ++s) {
+        mbar_init(&hdr->full[s], 1);
+        mbar_init(&hdr->empty[s], 1);
+      }
+      mbar_init(&hdr->tmem_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<2>(&hdr->tmem_base, p.tmem_cols);
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&hdr->tmem_base);
+  pdl_launch_dependents();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
+#ifdef LTXB_WS_DEBUG
+  const long long t_pdl = ws_globaltimer();
+  long long t_acc = t_pdl, t_met = 0;
+#endif
+
+  if (warp == 0) {
+    // ===================== TMA producer: this CTA's 128 weight rows + its half of the token rows =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const int n0 = tile * (2 * kWsTileRows) + static_cast<int>(cta_rank) * kWsTileRows;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&hdr->empty[stage], phase ^ 1);
+        uint8_t* sw = tiles + static_cast<size_t>(stage) * stage_bytes;
+        uint8_t* sx = sw + kWsWBytes;
+        const int ka = kb * kWsBlockK;
+        const bool skip_x = WS_DBG(1) && kb != kb0, skip_w = WS_DBG(4) && kb != kb0;
+        if (is_leader) mbar_arrive_expect_tx(&hdr->full[stage], (stage_bytes - (skip_x ? p.n_mma * x_box_bytes : 0) - (skip_w ? kWsWBytes : 0)) * 2);  // both CTAs report on the leader's barrier
+        const uint32_t bar = mapa_u32(smem_u32(&hdr->full[stage]), 0);
+        if (!skip_w) tma_load_2d_pair(sw, &tmap_w, bar, ka, n0);
+        for (int j = 0; j < p.n_mma && !skip_x; ++j) {
+          const int row0 = j * mma_n + static_cast<int>(cta_rank) * box_rows;
+          if (p.a_group_cols > 0) tma_load_3d_pair(sx + j * x_box_bytes, &tmap_x, bar, ka % p.a_group_cols, row0, ka / p.a_group_cols);
+          else tma_load_2d_pair(sx + j * x_box_bytes, &tmap_x, bar, ka, row0);
+        }
+        if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
+      }
+      // neither CTA of the pair may retire while commit arrivals for its barriers are still in flight
+      for (int s = 0; s < num_stages; ++s) {
+        mbar_wait(&hdr->empty[stage], phase ^ 1);
+        if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA): D[256 weight rows, tokens] += W_tile . X^T =====================
+    if (lane == 0 && is_leader) {
+      const uint32_t idesc = make_idesc_bf16(2 * kWsTileRows, mma_n, 0, 0);
+      uint32_t stage = 0, phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&hdr->full[stage], phase);
+        tc_fence_after_sync();
+        const uint32_t sa = smem_u32(tiles + static_cast<size_t>(stage) * stage_bytes);
+        const uint64_t wdesc = make_smem_desc_sw128(sa, 16, 1024);
+        for (int j = 0; j < p.n_mma; ++j) {
+          const uint64_t xdesc = make_smem_desc_sw128(sa + kWsWBytes + j * x_box_bytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kWsBlockK / 16; ++k)
+            umma_bf16_ss<2>(tmem_base + j * mma_n, wdesc + 2 * k, xdesc + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+        }
+        umma_commit_pair(&hdr->empty[stage], 3);
+        if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
+      }
+      umma_commit_pair(&hdr->tmem_full, 3);
+    }
+  } else {
+    // ===================== epilogue: thread = output column, walks the tokens =====================
+    // Eight warps, two per TMEM lane quarter: the epilogue is a long run of per-token address / convert / store
+    // instructions per thread, so it is paced by how many warps the four schedulers can interleave.
+    const int quarter = warp & 3;          // TMEM lanes [32 * quarter, +32) belong to this warp
+    const int half = (warp - 2) >> 2;      // which half of the token chunks this warp walks
+    const int lane_row = quarter * 32 + lane;
+    const long long n = static_cast<long long>(tile) * (2 * kWsTileRows) + cta_rank * kWsTileRows + lane_row;
+    const bool n_ok = n < p.N;
+    const float bias_n = (p.bias != nullptr && n_ok) ? __ldg(p.bias + n) : 0.f;
+    const float table_n = (p.gate_table != nullptr && n_ok) ? __ldg(p.gate_table + n) : 0.f;
+    const bool epi_leader = (warp == 2 && lane == 0);
+    const int chunks = p.m_pad / kWsChunk;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    mbar_wait(&hdr->tmem_full, 0);
+    tc_fence_after_sync();
+#ifdef LTXB_WS_DEBUG
+    t_acc = ws_globaltimer();
+#endif
+    if (WS_DBG(2)) {
+    } else if (p.splits == 1) {
+      const int groups = chunks / 2;  // 16-token groups (m_pad is a multiple of 16)
+      const int g0 = half == 0 ? 0 : (groups + 1) / 2, g1 = half == 0 ? (groups + 1) / 2 : groups;
+      for (int g = g0; g < g1; ++g) {
+        uint32_t r[16];
+        tmem_ld_x16(t_row + g * 16, r);
+        tmem_wait_ld();
+        if (n_ok) {
+          ws_finish_chunk<kEpi>(p, reinterpret_cast<const float*>(r), g * 16, n, bias_n, table_n);
+          ws_finish_chunk<kEpi>(p, reinterpret_cast<const float*>(r) + kWsChunk, g * 16 + kWsChunk, n, bias_n, table_n);
+        }
+      }
+    } else {
+      // ---- reduce-scatter over the `splits` pairs of this weight tile: split s owns chunks [own0, own1)
+      const int own0 = (chunks * split) / p.splits, own1 = (chunks * (split + 1)) / p.splits;
+      const size_t slot_f4 = static_cast<size_t>(p.m_pad / 4) * kWsTileRows;  // float4 per CTA slot
+      float4* my_slot = reinterpret_cast<float4*>(p.partials) + static_cast<size_t>(blockIdx.x) * slot_f4 + lane_row;
+      for (int c = 2 * half; c < chunks; c += 4) {  // 16-token groups, alternating between the two warps of a quarter
+        if (c >= own0 && c + 2 <= own1) continue;
+        uint32_t r[16];
+        tmem_ld_x16(t_row + c * kWsChunk, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int cc = c + h;
+          if (cc >= own0 && cc < own1) continue;
+          // slot layout [chunk][half 0..1][128 lanes] float4: a warp's 32 lanes touch 512 contiguous bytes
+          __stcg(my_slot + (cc * 2 + 0) * kWsTileRows, make_float4(__uint_as_float(r[8 * h]), __uint_as_float(r[8 * h + 1]), __uint_as_float(r[8 * h + 2]), __uint_as_float(r[8 * h + 3])));
+          __stcg(my_slot + (cc * 2 + 1) * kWsTileRows, make_float4(__uint_as_float(r[8 * h + 4]), __uint_as_float(r[8 * h + 5]), __uint_as_float(r[8 * h + 6]), __uint_as_float(r[8 * h + 7])));
+        }
+      }
+      // release / acquire through the leader: the CTA barrier orders every warp's parked chunks before the leader's fence
+      // (cumulativity), and the readers' loads after its acquire
+      ws_epilogue_bar();
+      int* arrive = p.counters + tile * 2 + static_cast<int>(cta_rank);
+      if (epi_leader) {
+        __threadfence();
+        atomicAdd(arrive, 1);
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile int*>(arrive) < p.splits) {
+          if (clock64() - t0 > LTXB_WATCHDOG_CYCLES) {
+            printf("ltxb: small-M split-K watchdog: tile %d split %d sees %d of %d arrivals\n", tile, split, *reinterpret_cast<volatile int*>(arrive), p.splits);
+            __trap();
+          }
+        }
+        __threadfence();
+      }
+      ws_epilogue_bar();
+#ifdef LTXB_WS_DEBUG
+      if (epi_leader) t_met = ws_globaltimer();
+#endif
+      const float4* tile_slots = reinterpret_cast<const float4*>(p.partials) + (static_cast<size_t>(tile) * p.splits * 2 + cta_rank) * slot_f4 + lane_row;
+      const int mid = own0 + (own1 - own0 + 1) / 2;
+      const int c_begin = half == 0 ? own0 : mid, c_end = half == 0 ? mid : own1;
+      // two chunks per pass, the parts of two other splits loaded together; parts are added in split order with the own
+      // accumulator at its own position, so the sum does not depend on arrival order
+      for (int c = c_begin; c < c_end; c += 2) {
+        const bool two = (c + 1 < c_end);
+        uint32_t r[2][8];
+        tmem_ld_x8(t_row + c * kWsChunk, r[0]);
+        if (two) tmem_ld_x8(t_row + (c + 1) * kWsChunk, r[1]);
+        float v[2][kWsChunk];
+#pragma unroll
+        for (int i = 0; i < kWsChunk; ++i) v[0][i] = 0.f, v[1][i] = 0.f;
+        bool own_pending = true;
+        int o = 0;
+        while (o < p.splits || own_pending) {
+          // next two OTHER splits in order
+          int oa = o;
+          if (oa == split) ++oa;
+          int ob = oa + 1;
+          if (ob == split) ++ob;
+          const bool has_a = oa < p.splits, has_b = ob < p.splits;
+          float4 ld[2][2][2];
+          if (has_a) {
+            const float4* src = tile_slots + static_cast<size_t>(oa) * 2 * slot_f4 + (c * 2) * kWsTileRows;
+            ld[0][0][0] = __ldcg(src), ld[0][0][1] = __ldcg(src + kWsTileRows);
+            if (two) ld[0][1][0] = __ldcg(src + 2 * kWsTileRows), ld[0][1][1] = __ldcg(src + 3 * kWsTileRows);
+          }
+          if (has_b) {
+            const float4* src = tile_slots + static_cast<size_t>(ob) * 2 * slot_f4 + (c * 2) * kWsTileRows;
+            ld[1][0][0] = __ldcg(src), ld[1][0][1] = __ldcg(src + kWsTileRows);
+            if (two) ld[1][1][0] = __ldcg(src + 2 * kWsTileRows), ld[1][1][1] = __ldcg(src + 3 * kWsTileRows);
+          }
+          auto add_own = [&]() {
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < kWsChunk; ++i) v[0][i] += __uint_as_float(r[0][i]), v[1][i] += two ? __uint_as_float(r[1][i]) : 0.f;
+            own_pending = false;
+          };
+          auto add_part = [&](int b) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              if (q == 1 && !two) break;
+              v[q][0] += ld[b][q][0].x, v[q][1] += ld[b][q][0].y, v[q][2] += ld[b][q][0].z, v[q][3] += ld[b][q][0].w;
+              v[q][4] += ld[b][q][1].x, v[q][5] += ld[b][q][1].y, v[q][6] += ld[b][q][1].z, v[q][7] += ld[b][q][1].w;
+            }
+          };
+          if (own_pending && (!has_a || split < oa)) add_own();
+          if (has_a) add_part(0);
+          if (own_pending && (!has_b || split < ob)) add_own();
+          if (has_b) add_part(1);
+          o = ob + 1;
+        }
+        if (n_ok) {
+          ws_finish_chunk<kEpi>(p, v[0], c * kWsChunk, n, bias_n, table_n);
+          if (two) ws_finish_chunk<kEpi>(p, v[1], (c + 1) * kWsChunk, n, bias_n, table_n);
+        }
+      }
+      // the last pair to leave re-arms the counters for the next launch
+      ws_epilogue_bar();
+      if (epi_leader) {
+        int* depart = p.counters + kWsDepartOffset + tile * 2 + static_cast<int>(cta_rank);
+        if (atomicAdd(depart, 1) == p.splits - 1) {
+          *arrive = 0;
+          *depart = 0;
+        }
+      }
+    }
+  }
+
+#ifdef LTXB_WS_DEBUG
+  if (WS_DBG(8) && threadIdx.x == 64 && p.trace != nullptr) {  // warp 2 lane 0 = the epilogue leader
+    long long* t = p.trace + static_cast<size_t>(blockIdx.x) * 4;
+    t[0] = t_pdl, t[1] = t_acc, t[2] = t_met, t[3] = ws_globaltimer();
+  }
+#endif
+  // teardown: nobody may leave while the peer can still read this CTA's shared memory / TMEM
+  __syncwarp();
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<2>(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int kEpi>
+static int launch_ws(const CUtensorMap& tx, const CUtensorMap& tw, const WsParams& p, int grid, size_t smem, cudaStream_t stream) {
+  auto kernel = gemm_small_m_kernel<kEpi>;
+  static PerDeviceOnce configured;
+  if (configured.first()) LTXB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  LTXB_CUDA(launch_kernel(kernel, dim3(grid), dim3(kWsThreads), smem, stream, 2, tx, tw, p));
+  return LTXB_OK;
+}
+
+bool gemm_small_m_supported(int M, int N, int K) { return M >= 1 && M <= 512 && N >= 16 && K >= kWsBlockK && K % kWsBlockK == 0; }
+
+int launch_gemm_small_m(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
+                        const ltxb_epilogue* epi, float* partials, long long partial_bytes, int* counters, int want_splits,
+                        cudaStream_t stream) {
+  const int sms = num_sms();
+  if (sms <= 0) return set_error(LTXB_ERR_NO_DEVICE, "ltxb_gemm_bf16: no CUDA device");
+  WsParams p{};
+  p.M = M, p.N = N, p.K = K;
+  p.n_mma = M > 256 ? 2 : 1;
+  p.m_pad = p.n_mma == 1 ? ((M + 15) / 16) * 16 : ((M + 31) / 32) * 32;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.m_pad) p.tmem_cols *= 2;
+  const size_t stage_bytes = kWsWBytes + static_cast<size_t>(p.m_pad / 2) * kWsBlockK * 2;
+  // two CTAs per SM when both the accumulators (<= 256 TMEM columns each) and >= 3 stages fit twice
+  int per_sm = p.tmem_cols <= 256 ? 2 : 1;
+  size_t budget = 113 * 1024 - 1024 - kWsHeader;
+  if (per_sm == 2 && budget / stage_bytes < 3) per_sm = 1;
+  if (per_sm == 1) budget = 232448 - 1024 - kWsHeader;
+  p.num_stages = static_cast<int>(std::min<size_t>(kWsMaxStages, budget / stage_bytes));
+  const size_t smem = 1024 + kWsHeader + p.num_stages * stage_bytes;
+  const int slots = (sms / 2) * per_sm;  // co-resident CTA pairs
+  const int tiles = (N + 2 * kWsTileRows - 1) / (2 * kWsTileRows);
+  const int num_kb = K / kWsBlockK;
+  static const int env_min_kb = [] { const char* e = getenv("LTXB_GEMM_SMALL_M_MIN_KB"); return e ? atoi(e) : 4; }();
+  static const int env_max_splits = [] { const char* e = getenv("LTXB_GEMM_SMALL_M_MAX_SPLITS"); return e ? atoi(e) : 16; }();
+  int splits = 1;
+  if (partials != nullptr && counters != nullptr && tiles * 2 <= kWsDepartOffset) {
+    splits = std::max(1, std::min({slots / tiles, num_kb / std::max(1, env_min_kb), env_max_splits}));
+    if (want_splits > 0) splits = std::min({want_splits, num_kb, std::max(1, slots / tiles)});
+    // every CTA of the grid parks into its own slot
+    while (splits > 1 && static_cast<long long>(tiles) * splits * 2 * p.m_pad * kWsTileRows * 4 > partial_bytes) --splits;
+  }
+  p.splits = splits;
+  p.bias = epi->bias;
+  p.out = out;
+  p.ldo = ldo;
+  p.resid = epi->resid;
+  p.ldr = epi->ldr;
+  p.gate = epi->gate;
+  p.gate_ld = epi->gate_ld;
+  p.gate_row_div = epi->gate_row_div > 0 ? epi->gate_row_div : 1;
+  p.gate_row_index = epi->gate_row_index;
+  p.gate_table = epi->gate_table;
+  p.partials = partials;
+  p.counters = counters;
+#ifdef LTXB_WS_DEBUG
+  {
+    const char* e = getenv("LTXB_WS_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+    if ((p.debug & 8) && partials != nullptr) p.trace = reinterpret_cast<long long*>(reinterpret_cast<char*>(partials) + partial_bytes) - 296 * 4 * 4;
+  }
+#endif
+
+  const uint32_t box_rows = static_cast<uint32_t>(p.m_pad / p.n_mma / 2);
+  CUtensorMap tx, tw;
+  if (epi->a_group_cols > 0) {
+    LTXB_CHECK_SUPPORTED(epi->a_group_cols % kWsBlockK == 0 && K % epi->a_group_cols == 0 && epi->a_group_stride % 8 == 0,
+                         "ltxb_gemm_bf16: a_group_cols=%d must divide K=%d and be a multiple of %d", epi->a_group_cols, K, kWsBlockK);
+    p.a_group_cols = epi->a_group_cols;
+    const uint64_t dims[3] = {static_cast<uint64_t>(epi->a_group_cols), static_cast<uint64_t>(M), static_cast<uint64_t>(K / epi->a_group_cols)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(lda) * 2, static_cast<uint64_t>(epi->a_group_stride) * 2};
+    const uint32_t box[3] = {kWsBlockK, box_rows, 1};
+    int rc = encode_tmap_bf16(&tx, A, 3, dims, strides, box);
+    if (rc) return rc;
+  } else {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
+    const uint32_t box[2] = {kWsBlockK, box_rows};
+    int rc = encode_tmap_bf16(&tx, A, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    const uint32_t box[2] = {kWsBlockK, kWsTileRows};
+    int rc = encode_tmap_bf16(&tw, W, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  const int grid = tiles * splits * 2;
+  switch (epi->mode) {
+    case LTXB_EPI_BIAS_BF16: return launch_ws<LTXB_EPI_BIAS_BF16>(tx, tw, p, grid, smem, stream);
+    case LTXB_EPI_GELU_BF16: return launch_ws<LTXB_EPI_GELU_BF16>(tx, tw, p, grid, smem, stream);
+    case LTXB_EPI_SILU_BF16: return launch_ws<LTXB_EPI_SILU_BF16>(tx, tw, p, grid, smem, stream);
+    case LTXB_EPI_BIAS_F32: return launch_ws<LTXB_EPI_BIAS_F32>(tx, tw, p, grid, smem, stream);
+    case LTXB_EPI_RESID_GATE_F32: return launch_ws<LTXB_EPI_RESID_GATE_F32>(tx, tw, p, grid, smem, stream);
+    default: return set_error(LTXB_ERR_BAD_ARG, "ltxb_gemm_bf16: unknown epilogue mode %d", epi->mode);
+  }
+}
+
+}  // namespace ltxb

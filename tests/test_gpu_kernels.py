@@ -112,6 +112,103 @@ def test_gemm_contiguous_stream_k_epilogues(mode):
     assert all(torch.equal(outs[0], o) for o in outs[1:])
 
 
+# The weight-streaming kernel for few rows (gemm_small_m.cu; cta_pair=4 forces it, block_n = number of k-range splits):
+# sequence-parallel shards, audio tokens, AdaLN rows, ragged N (not a multiple of the 256-row weight tile), two-MMA
+# token ranges (M > 256), K down to one k-block per split.
+WS_SHAPES = [(160, 4096, 4096), (160, 12288, 4096), (160, 16384, 4096), (160, 4096, 16384), (68, 2048, 2048), (136, 2048, 8192),
+             (1, 4096, 1024), (2, 36864, 4096), (16, 256, 64), (200, 272, 1024), (256, 4096, 4096), (255, 1040, 512),
+             (320, 4096, 4096), (320, 16384, 4096), (512, 4096, 4096), (257, 784, 256), (500, 12288, 4096)]
+
+
+@pytest.mark.parametrize("M,N,K", WS_SHAPES)
+def test_gemm_small_m_kernel(M, N, K):
+    """Forced (cta_pair=4) with the library's own split choice, with no split, and with 2 / 3 / 7 k-range splits: all agree
+    with the fp32 reference, with each other to summation order, and each is bit-reproducible run to run."""
+    auto = gemm_case(M, N, K, _lib.EPI_BIAS_F32, pair=4)
+    assert torch.equal(auto, gemm_case(M, N, K, _lib.EPI_BIAS_F32, pair=4))
+    for splits in (1, 2, 3, 7):
+        a = gemm_case(M, N, K, _lib.EPI_BIAS_F32, pair=4, bn=splits)
+        b = gemm_case(M, N, K, _lib.EPI_BIAS_F32, pair=4, bn=splits)
+        assert torch.equal(a, b), f"small-M kernel with {splits} splits differs between two runs"
+        assert rel_l2(a, auto) < 2e-5
+    if M <= 256:  # what the library picks on its own for few rows
+        assert torch.equal(auto, gemm_case(M, N, K, _lib.EPI_BIAS_F32))
+
+
+@pytest.mark.parametrize("mode", [_lib.EPI_BIAS_BF16, _lib.EPI_GELU_BF16, _lib.EPI_SILU_BF16, _lib.EPI_RESID_GATE_F32])
+def test_gemm_small_m_kernel_epilogues(mode):
+    for M, N, K in [(160, 4096, 4096), (160, 16384, 4096), (160, 4096, 16384), (68, 2048, 2048), (320, 4096, 4096), (3, 784, 512)]:
+        for splits in (0, 1, 4):
+            gemm_case(M, N, K, mode, pair=4, bn=splits)
+    # back-to-back launches reuse the parked chunks and the arrival / departure counters
+    outs = [gemm_case(160, 4096, 16384, mode, pair=4, seed=5) for _ in range(6)]
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+
+
+def test_gemm_small_m_kernel_group_major_rows_and_strides():
+    """The A operand as the Ulysses gather all-to-all delivers it ([K / g][M][g], read in place through a 3-D map), a
+    gate looked up through a row index, and outputs / residuals that are column slices of wider tensors."""
+    g = torch.Generator(device=DEV).manual_seed(11)
+    M, N, K, gc = 160, 4096, 4096, 512
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g)
+    a_grouped = a.view(M, K // gc, gc).permute(1, 0, 2).contiguous()
+    ref = a.float() @ w.float().T + bias
+    for pair in (4, -1):
+        out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+        ops.gemm(a_grouped, w, bias, out, mode=_lib.EPI_BIAS_F32, a_group_cols=gc, cta_pair=pair)
+        assert rel_l2(out, ref) < 2e-5
+    wide = torch.randn(M, 3 * N, device=DEV, generator=g)
+    resid = wide[:, N:2 * N]
+    before = wide.clone()
+    want = resid.clone()
+    idx = torch.randint(0, 5, (M,), device=DEV, generator=g, dtype=torch.int32)
+    gate = torch.randn(5, N, device=DEV, generator=g)
+    want = want + ref * gate[idx.long()]
+    ops.gemm(a, w, bias, resid, mode=_lib.EPI_RESID_GATE_F32, resid=resid, gate=gate, gate_row_index=idx, cta_pair=4)
+    assert rel_l2(resid, want) < 2e-5
+    assert torch.equal(wide[:, :N], before[:, :N]) and torch.equal(wide[:, 2 * N:], before[:, 2 * N:])
+
+
+def test_gemm_small_m_kernel_graph_replay():
+    """Captured and replayed back to back (the counters are re-armed inside the kernel), interleaved with the big-tile
+    split-K kernel that shares the workspace."""
+    g = torch.Generator(device=DEV).manual_seed(13)
+    M, K = 160, 4096
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w1 = (torch.randn(16384, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+    w2 = (torch.randn(4096, 16384, device=DEV, generator=g) / 128).bfloat16()
+    big_a = torch.randn(1280, K, device=DEV, generator=g).bfloat16()
+    h = torch.empty(M, 16384, device=DEV, dtype=torch.bfloat16)
+    y = torch.empty(M, 4096, device=DEV, dtype=torch.float32)
+    big = torch.empty(1280, 4096, device=DEV, dtype=torch.float32)
+
+    def run():
+        ops.gemm(a, w1, None, h, mode=_lib.EPI_GELU_BF16)
+        ops.gemm(h, w2, None, y, mode=_lib.EPI_BIAS_F32)
+        ops.gemm(big_a, w2[:, :K], None, big, mode=_lib.EPI_BIAS_F32)
+
+    run()
+    torch.cuda.synchronize()
+    want_y, want_big = y.clone(), big.clone()
+    ref = torch.nn.functional.gelu(a.float() @ w1.float().T, approximate="tanh").bfloat16().float() @ w2.float().T
+    assert rel_l2(want_y, ref) < 3e-3
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        run()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            run()
+            run()
+        for _ in range(4):
+            y.zero_()
+            big.zero_()
+            graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y, want_y) and torch.equal(big, want_big)
+
+
 def test_gemm_rejects_bad_shapes():
     a = torch.zeros(64, 96, device=DEV, dtype=torch.bfloat16)
     w = torch.zeros(64, 96, device=DEV, dtype=torch.bfloat16)
