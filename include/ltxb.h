@@ -75,6 +75,11 @@ enum {
   LTXB_EPI_COUNT = 5
 };
 
+/* ltxb_epilogue.flags.  LTXB_GEMM_CONST_W: W is not written by any kernel that may still be running ahead of this
+ * launch in the stream (model weights): the few-row kernel then starts streaming W while its stream predecessor is
+ * still finishing (programmatic dependent launch) and only the activations wait for it. */
+#define LTXB_GEMM_CONST_W 1
+
 typedef struct ltxb_epilogue {
   int32_t mode;                  /* LTXB_EPI_*                                       */
   int32_t gate_row_div;          /* >= 1; rows of `gate` = ceil(M / gate_row_div)    */
@@ -89,7 +94,7 @@ typedef struct ltxb_epilogue {
    * [K / g][M][g] with rows lda apart and groups a_group_stride elements apart — what the Ulysses gather
    * all-to-all delivers — and is read in place through a 3-D TMA map (no transposing copy). */
   int32_t a_group_cols;
-  int32_t reserved_;
+  int32_t flags;                 /* LTXB_GEMM_* bits                                 */
   int64_t a_group_stride;
 } ltxb_epilogue;
 

@@ -33,7 +33,7 @@ class Epilogue(C.Structure):
         ("gate_row_index", _vp),
         ("gate_table", _vp),
         ("a_group_cols", _i32),
-        ("reserved_", _i32),
+        ("flags", _i32),
         ("a_group_stride", _i64),
     ]
 

@@ -54,6 +54,23 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
   return LTXB_OK;
 }
 
+int encode_tmap_plain_2d(CUtensorMap* map, const void* base, int elem_bytes, const uint64_t* dims, uint64_t row_stride_bytes,
+                         const uint32_t* box) {
+  auto fn = encode_fn();
+  if (fn == nullptr) return set_error(LTXB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
+  cuuint64_t gdim[2] = {dims[0], dims[1]};
+  cuuint64_t gstr[1] = {row_stride_bytes};
+  cuuint32_t bdim[2] = {box[0], box[1]};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base),
+                  gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(LTXB_ERR_CUDA, "cuTensorMapEncodeTiled (plain 2-D, %d-byte elements) failed with CUresult %d (dims %llu x %llu, box %u x %u)",
+                     elem_bytes, static_cast<int>(r), static_cast<unsigned long long>(dims[0]), static_cast<unsigned long long>(dims[1]), box[0], box[1]);
+  return LTXB_OK;
+}
+
 std::atomic<long long> g_kernel_launches{0};
 
 bool pdl_enabled() {

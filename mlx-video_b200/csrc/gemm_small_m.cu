@@ -56,6 +56,9 @@ struct WsParams {
   const int* gate_row_index;
   const float* gate_table;
   int a_group_cols;
+  int const_w;      // LTXB_GEMM_CONST_W: the first stages' weight tiles are requested before the PDL wait
+  int out_tma;      // 0: per-thread global stores; 1: output chunks staged in shared memory, written by TMA; 2: staged, TMA add
+                    // into `out` (RESID_GATE with out == resid: out += (acc + bias) * g, one add per element)
   float* partials;  // [grid][m_pad / 8][2][128] float4: parked chunks
   int* counters;
   long long* trace;  // LTXB_WS_DEBUG builds, debug & 8: [grid][4] globaltimer at PDL wait / accumulator / met / done (tail of the workspace)
@@ -88,6 +91,13 @@ __device__ __forceinline__ void ws_epilogue_bar() { asm volatile("bar.sync 1, 25
 template <int kEpi>
 __device__ __forceinline__ void ws_finish_chunk(const WsParams& p, const float* acc, int m0, long long n, float bias_n,
                                                 float table_n) {
+  if (WS_DBG(16)) {  // timing experiment: no output stores (the values still have to be produced)
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < kWsChunk; ++i) t += acc[i];
+    if (t == 123.456f) reinterpret_cast<float*>(p.out)[0] = t;
+    return;
+  }
   float v[kWsChunk];
 #pragma unroll
   for (int i = 0; i < kWsChunk; ++i) v[i] = acc[i] + bias_n;
@@ -129,9 +139,50 @@ __device__ __forceinline__ void ws_finish_chunk(const WsParams& p, const float* 
   }
 }
 
+// The same epilogue into a shared-memory chunk tile [8 tokens][128 columns] (row-major, what the TMA store reads):
+// `dst` = this thread's column in the tile.  RESID_GATE stages the gated update only, the TMA adds it into the residual.
+template <int kEpi>
+__device__ __forceinline__ void ws_stage_chunk(const WsParams& p, const float* acc, int m0, long long n, bool n_ok, float bias_n,
+                                               float table_n, uint8_t* dst) {
+  float v[kWsChunk];
+#pragma unroll
+  for (int i = 0; i < kWsChunk; ++i) v[i] = acc[i] + bias_n;
+  if constexpr (kEpi == LTXB_EPI_GELU_BF16) {
+#pragma unroll
+    for (int i = 0; i < kWsChunk; ++i) v[i] = gelu_tanh(v[i]);
+  } else if constexpr (kEpi == LTXB_EPI_SILU_BF16) {
+#pragma unroll
+    for (int i = 0; i < kWsChunk; ++i) v[i] = silu(v[i]);
+  }
+  if constexpr (kEpi == LTXB_EPI_BIAS_BF16 || kEpi == LTXB_EPI_GELU_BF16 || kEpi == LTXB_EPI_SILU_BF16) {
+#pragma unroll
+    for (int i = 0; i < kWsChunk; ++i) *reinterpret_cast<__nv_bfloat16*>(dst + i * (kWsTileRows * 2)) = __float2bfloat16_rn(v[i]);
+  } else {
+    if constexpr (kEpi == LTXB_EPI_RESID_GATE_F32) {
+      if (p.gate != nullptr) {
+        float g[kWsChunk];
+#pragma unroll
+        for (int i = 0; i < kWsChunk; ++i) {
+          const int m = m0 + i;
+          g[i] = 0.f;
+          if (m < p.M && n_ok) {
+            const long long grow = p.gate_row_index != nullptr ? __ldg(p.gate_row_index + m) : m / p.gate_row_div;
+            g[i] = __ldg(p.gate + grow * p.gate_ld + n) + table_n;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kWsChunk; ++i) v[i] *= g[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kWsChunk; ++i) *reinterpret_cast<float*>(dst + i * (kWsTileRows * 4)) = v[i];
+  }
+}
+
 template <int kEpi>
 __global__ void __launch_bounds__(kWsThreads, 2)
-gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const WsParams p) {
+gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_out, const WsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   WsSmemHeader* hdr = reinterpret_cast<WsSmemHeader*>(smem);
@@ -156,6 +207,7 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
+    if (p.out_tma != 0) tma_prefetch_desc(&tmap_out);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -174,7 +226,20 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   tc_fence_after_sync();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&hdr->tmem_base);
   pdl_launch_dependents();
-  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
+  // Weights no running kernel writes (LTXB_GEMM_CONST_W) start streaming NOW, under the stream predecessor's tail: the
+  // producer fills every stage's weight half, the token rows follow after the wait.
+  const int n0_w = tile * (2 * kWsTileRows) + static_cast<int>(cta_rank) * kWsTileRows;
+  int prefetched = 0;
+  if (p.const_w && !WS_DBG(4)) {
+    prefetched = min(num_stages, kb1 - kb0);
+    if (warp == 0 && lane == 0) {
+      for (int s = 0; s < prefetched; ++s) {
+        if (is_leader) mbar_arrive_expect_tx(&hdr->full[s], stage_bytes * 2);
+        tma_load_2d_pair(tiles + static_cast<size_t>(s) * stage_bytes, &tmap_w, mapa_u32(smem_u32(&hdr->full[s]), 0), (kb0 + s) * kWsBlockK, n0_w);
+      }
+    }
+  }
+  pdl_wait();  // everything above overlapped the previous kernel's tail; activations / outputs are touched only below
 #ifdef LTXB_WS_DEBUG
   const long long t_pdl = ws_globaltimer();
   long long t_acc = t_pdl, t_met = 0;
@@ -184,16 +249,17 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // ===================== TMA producer: this CTA's 128 weight rows + its half of the token rows =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      const int n0 = tile * (2 * kWsTileRows) + static_cast<int>(cta_rank) * kWsTileRows;
+      const int n0 = n0_w;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&hdr->empty[stage], phase ^ 1);
+        const bool w_done = (kb - kb0) < prefetched;  // this stage's weight tile and byte count went out before the wait
+        if (!w_done) mbar_wait(&hdr->empty[stage], phase ^ 1);
         uint8_t* sw = tiles + static_cast<size_t>(stage) * stage_bytes;
         uint8_t* sx = sw + kWsWBytes;
         const int ka = kb * kWsBlockK;
         const bool skip_x = WS_DBG(1) && kb != kb0, skip_w = WS_DBG(4) && kb != kb0;
-        if (is_leader) mbar_arrive_expect_tx(&hdr->full[stage], (stage_bytes - (skip_x ? p.n_mma * x_box_bytes : 0) - (skip_w ? kWsWBytes : 0)) * 2);  // both CTAs report on the leader's barrier
+        if (is_leader && !w_done) mbar_arrive_expect_tx(&hdr->full[stage], (stage_bytes - (skip_x ? p.n_mma * x_box_bytes : 0) - (skip_w ? kWsWBytes : 0)) * 2);  // both CTAs report on the leader's barrier
         const uint32_t bar = mapa_u32(smem_u32(&hdr->full[stage]), 0);
-        if (!skip_w) tma_load_2d_pair(sw, &tmap_w, bar, ka, n0);
+        if (!skip_w && !w_done) tma_load_2d_pair(sw, &tmap_w, bar, ka, n0);
         for (int j = 0; j < p.n_mma && !skip_x; ++j) {
           const int row0 = j * mma_n + static_cast<int>(cta_rank) * box_rows;
           if (p.a_group_cols > 0) tma_load_3d_pair(sx + j * x_box_bytes, &tmap_x, bar, ka % p.a_group_cols, row0, ka / p.a_group_cols);
@@ -242,6 +308,42 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     const bool epi_leader = (warp == 2 && lane == 0);
     const int chunks = p.m_pad / kWsChunk;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    // ---- output staging (p.out_tma): the four warps of a half fill chunk tiles in the (now idle) operand stages, one
+    // thread hands them to the TMA.  A round = as many consecutive chunks as the half's share of the stages holds.
+    constexpr int kEsize = (kEpi == LTXB_EPI_BIAS_F32 || kEpi == LTXB_EPI_RESID_GATE_F32) ? 4 : 2;
+    constexpr int kChunkBytes = kWsChunk * kWsTileRows * kEsize;
+    const uint32_t half_bytes = ((static_cast<uint32_t>(num_stages) * stage_bytes) / 2) & ~1023u;
+    uint8_t* half_stage = tiles + half * half_bytes;
+    const int stage_cap = static_cast<int>(half_bytes / kChunkBytes) & ~1;
+    const bool staged = p.out_tma != 0;
+    const bool half_issuer = (((warp - 2) & 3) == 0) && lane == 0;
+    const int n0_cta = tile * (2 * kWsTileRows) + static_cast<int>(cta_rank) * kWsTileRows;
+    int staged_k = 0, staged_c0 = 0;
+    auto half_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory"); };
+    auto flush = [&](bool last) {  // warp-uniform and identical in the four warps of the half
+      if (staged_k == 0) return;
+      fence_proxy_async_smem();
+      half_bar();
+      if (half_issuer) {
+        for (int i = 0; i < staged_k; ++i) {
+          if (p.out_tma == 2) tma_reduce_add_2d(&tmap_out, half_stage + i * kChunkBytes, n0_cta, (staged_c0 + i) * kWsChunk);
+          else tma_store_2d(&tmap_out, half_stage + i * kChunkBytes, n0_cta, (staged_c0 + i) * kWsChunk);
+        }
+        tma_store_commit();
+        if (!last) tma_store_wait_read();
+      }
+      if (!last) half_bar();
+      staged_k = 0;
+    };
+    auto emit = [&](const float* vals, int c) {  // chunk c: consecutive within a round
+      if (!staged) {
+        if (n_ok) ws_finish_chunk<kEpi>(p, vals, c * kWsChunk, n, bias_n, table_n);
+        return;
+      }
+      if (staged_k == 0) staged_c0 = c;
+      ws_stage_chunk<kEpi>(p, vals, c * kWsChunk, n, n_ok, bias_n, table_n, half_stage + staged_k * kChunkBytes + lane_row * kEsize);
+      if (++staged_k == stage_cap) flush(false);
+    };
     mbar_wait(&hdr->tmem_full, 0);
     tc_fence_after_sync();
 #ifdef LTXB_WS_DEBUG
@@ -255,11 +357,10 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         uint32_t r[16];
         tmem_ld_x16(t_row + g * 16, r);
         tmem_wait_ld();
-        if (n_ok) {
-          ws_finish_chunk<kEpi>(p, reinterpret_cast<const float*>(r), g * 16, n, bias_n, table_n);
-          ws_finish_chunk<kEpi>(p, reinterpret_cast<const float*>(r) + kWsChunk, g * 16 + kWsChunk, n, bias_n, table_n);
-        }
+        emit(reinterpret_cast<const float*>(r), 2 * g);
+        emit(reinterpret_cast<const float*>(r) + kWsChunk, 2 * g + 1);
       }
+      flush(true);
     } else {
       // ---- reduce-scatter over the `splits` pairs of this weight tile: split s owns chunks [own0, own1)
       const int own0 = (chunks * split) / p.splits, own1 = (chunks * (split + 1)) / p.splits;
@@ -284,16 +385,14 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       ws_epilogue_bar();
       int* arrive = p.counters + tile * 2 + static_cast<int>(cta_rank);
       if (epi_leader) {
-        __threadfence();
-        atomicAdd(arrive, 1);
+        red_release_gpu_add(arrive, 1);
         const long long t0 = clock64();
-        while (*reinterpret_cast<volatile int*>(arrive) < p.splits) {
+        while (ld_acquire_gpu(arrive) < p.splits) {
           if (clock64() - t0 > LTXB_WATCHDOG_CYCLES) {
-            printf("ltxb: small-M split-K watchdog: tile %d split %d sees %d of %d arrivals\n", tile, split, *reinterpret_cast<volatile int*>(arrive), p.splits);
+            printf("ltxb: small-M split-K watchdog: tile %d split %d sees %d of %d arrivals\n", tile, split, ld_acquire_gpu(arrive), p.splits);
             __trap();
           }
         }
-        __threadfence();
       }
       ws_epilogue_bar();
 #ifdef LTXB_WS_DEBUG
@@ -352,11 +451,10 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           if (has_b) add_part(1);
           o = ob + 1;
         }
-        if (n_ok) {
-          ws_finish_chunk<kEpi>(p, v[0], c * kWsChunk, n, bias_n, table_n);
-          if (two) ws_finish_chunk<kEpi>(p, v[1], (c + 1) * kWsChunk, n, bias_n, table_n);
-        }
+        emit(v[0], c);
+        if (two) emit(v[1], c + 1);
       }
+      flush(true);
       // the last pair to leave re-arms the counters for the next launch
       ws_epilogue_bar();
       if (epi_leader) {
@@ -369,6 +467,7 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
   }
 
+  if (p.out_tma != 0 && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) tma_store_wait_read();  // the staged tiles stay valid until read
 #ifdef LTXB_WS_DEBUG
   if (WS_DBG(8) && threadIdx.x == 64 && p.trace != nullptr) {  // warp 2 lane 0 = the epilogue leader
     long long* t = p.trace + static_cast<size_t>(blockIdx.x) * 4;
@@ -389,11 +488,12 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 // host side
 // ------------------------------------------------------------------------------------------------
 template <int kEpi>
-static int launch_ws(const CUtensorMap& tx, const CUtensorMap& tw, const WsParams& p, int grid, size_t smem, cudaStream_t stream) {
+static int launch_ws(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& to, const WsParams& p, int grid, size_t smem,
+                     cudaStream_t stream) {
   auto kernel = gemm_small_m_kernel<kEpi>;
   static PerDeviceOnce configured;
   if (configured.first()) LTXB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-  LTXB_CUDA(launch_kernel(kernel, dim3(grid), dim3(kWsThreads), smem, stream, 2, tx, tw, p));
+  LTXB_CUDA(launch_kernel(kernel, dim3(grid), dim3(kWsThreads), smem, stream, 2, tx, tw, to, p));
   return LTXB_OK;
 }
 
@@ -411,25 +511,36 @@ int launch_gemm_small_m(const void* A, int64_t lda, const void* W, int64_t ldw, 
   p.tmem_cols = 32;
   while (p.tmem_cols < p.m_pad) p.tmem_cols *= 2;
   const size_t stage_bytes = kWsWBytes + static_cast<size_t>(p.m_pad / 2) * kWsBlockK * 2;
-  // two CTAs per SM when both the accumulators (<= 256 TMEM columns each) and >= 3 stages fit twice
-  int per_sm = p.tmem_cols <= 256 ? 2 : 1;
-  size_t budget = 113 * 1024 - 1024 - kWsHeader;
-  if (per_sm == 2 && budget / stage_bytes < 3) per_sm = 1;
-  if (per_sm == 1) budget = 232448 - 1024 - kWsHeader;
-  p.num_stages = static_cast<int>(std::min<size_t>(kWsMaxStages, budget / stage_bytes));
-  const size_t smem = 1024 + kWsHeader + p.num_stages * stage_bytes;
-  const int slots = (sms / 2) * per_sm;  // co-resident CTA pairs
   const int tiles = (N + 2 * kWsTileRows - 1) / (2 * kWsTileRows);
   const int num_kb = K / kWsBlockK;
   static const int env_min_kb = [] { const char* e = getenv("LTXB_GEMM_SMALL_M_MIN_KB"); return e ? atoi(e) : 4; }();
   static const int env_max_splits = [] { const char* e = getenv("LTXB_GEMM_SMALL_M_MAX_SPLITS"); return e ? atoi(e) : 16; }();
-  int splits = 1;
-  if (partials != nullptr && counters != nullptr && tiles * 2 <= kWsDepartOffset) {
-    splits = std::max(1, std::min({slots / tiles, num_kb / std::max(1, env_min_kb), env_max_splits}));
-    if (want_splits > 0) splits = std::min({want_splits, num_kb, std::max(1, slots / tiles)});
-    // every CTA of the grid parks into its own slot
-    while (splits > 1 && static_cast<long long>(tiles) * splits * 2 * p.m_pad * kWsTileRows * 4 > partial_bytes) --splits;
+  static const int env_per_sm = [] { const char* e = getenv("LTXB_GEMM_SMALL_M_PER_SM"); return e ? atoi(e) : 0; }();
+  const bool can_split = partials != nullptr && counters != nullptr && tiles * 2 <= kWsDepartOffset;
+  auto splits_for = [&](int slots) {
+    if (!can_split) return 1;
+    int s = std::max(1, std::min({slots / tiles, num_kb / std::max(1, env_min_kb), env_max_splits}));
+    if (want_splits > 0) s = std::min({want_splits, num_kb, std::max(1, slots / tiles)});
+    return s;
+  };
+  // One CTA per SM with all of its shared memory as stages (8 x 26 KB at 160 tokens), or two per SM with half each (when
+  // both accumulators fit 256 TMEM columns): two per SM doubles the pair slots, i.e. allows more k-range splits, but every
+  // split adds reduce-scatter traffic and the deeper pipeline streams faster.  Measured at 160 tokens
+  // (profiles/r2/gemm_small_m.md): one per SM wins whenever it still fills the machine (>= 85 % of the SM pairs busy).
+  const int pairs = sms / 2;
+  int per_sm = 1;
+  if (p.tmem_cols <= 256 && (113 * 1024 - 1024 - kWsHeader) / stage_bytes >= 3) {
+    const int s1 = splits_for(pairs);
+    const bool fills = tiles <= pairs && tiles * s1 * 100 >= pairs * 85;
+    per_sm = (env_per_sm == 1 || env_per_sm == 2) ? env_per_sm : (fills ? 1 : 2);
   }
+  const size_t budget = (per_sm == 2 ? 113 * 1024 : 232448) - 1024 - kWsHeader;
+  p.num_stages = static_cast<int>(std::min<size_t>(kWsMaxStages, budget / stage_bytes));
+  const size_t smem = 1024 + kWsHeader + p.num_stages * stage_bytes;
+  const int slots = pairs * per_sm;  // co-resident CTA pairs
+  int splits = splits_for(slots);
+  // every CTA of the grid parks into its own slot
+  while (splits > 1 && static_cast<long long>(tiles) * splits * 2 * p.m_pad * kWsTileRows * 4 > partial_bytes) --splits;
   p.splits = splits;
   p.bias = epi->bias;
   p.out = out;
@@ -443,6 +554,8 @@ int launch_gemm_small_m(const void* A, int64_t lda, const void* W, int64_t ldw, 
   p.gate_table = epi->gate_table;
   p.partials = partials;
   p.counters = counters;
+  static const int env_const_w = [] { const char* e = getenv("LTXB_GEMM_CONST_W"); return e ? atoi(e) : 1; }();
+  p.const_w = (env_const_w && (epi->flags & LTXB_GEMM_CONST_W)) ? 1 : 0;
 #ifdef LTXB_WS_DEBUG
   {
     const char* e = getenv("LTXB_WS_DEBUG");
@@ -476,13 +589,31 @@ int launch_gemm_small_m(const void* A, int64_t lda, const void* W, int64_t ldw, 
     int rc = encode_tmap_bf16(&tw, W, 2, dims, strides, box);
     if (rc) return rc;
   }
+  // Output through shared memory + TMA (16x fewer store instructions than a 2-byte store per thread and token, measured:
+  // 2.7 us of a 3.6 us epilogue at 160 tokens were the stores).  RESID_GATE is an in-place update of the residual stream
+  // (out == resid) on the model path: the TMA adds the gated update into it; other aliasing keeps the per-thread path.
+  static const int env_tma = [] { const char* e = getenv("LTXB_GEMM_SMALL_M_TMA_OUT"); return e ? atoi(e) : 1; }();
+  CUtensorMap to{};
+  const bool f32_out = (epi->mode == LTXB_EPI_BIAS_F32 || epi->mode == LTXB_EPI_RESID_GATE_F32);
+  const int esize = f32_out ? 4 : 2;
+  p.out_tma = 0;
+  if (env_tma && aligned16(out) && (static_cast<uint64_t>(ldo) * esize) % 16 == 0 && N % (16 / esize) == 0) {
+    if (epi->mode != LTXB_EPI_RESID_GATE_F32) p.out_tma = 1;
+    else if (epi->resid == out && epi->ldr == ldo) p.out_tma = 2;
+  }
+  if (p.out_tma != 0) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+    const uint32_t box[2] = {kWsTileRows, kWsChunk};
+    int rc = encode_tmap_plain_2d(&to, out, esize, dims, static_cast<uint64_t>(ldo) * esize, box);
+    if (rc) return rc;
+  }
   const int grid = tiles * splits * 2;
   switch (epi->mode) {
-    case LTXB_EPI_BIAS_BF16: return launch_ws<LTXB_EPI_BIAS_BF16>(tx, tw, p, grid, smem, stream);
-    case LTXB_EPI_GELU_BF16: return launch_ws<LTXB_EPI_GELU_BF16>(tx, tw, p, grid, smem, stream);
-    case LTXB_EPI_SILU_BF16: return launch_ws<LTXB_EPI_SILU_BF16>(tx, tw, p, grid, smem, stream);
-    case LTXB_EPI_BIAS_F32: return launch_ws<LTXB_EPI_BIAS_F32>(tx, tw, p, grid, smem, stream);
-    case LTXB_EPI_RESID_GATE_F32: return launch_ws<LTXB_EPI_RESID_GATE_F32>(tx, tw, p, grid, smem, stream);
+    case LTXB_EPI_BIAS_BF16: return launch_ws<LTXB_EPI_BIAS_BF16>(tx, tw, to, p, grid, smem, stream);
+    case LTXB_EPI_GELU_BF16: return launch_ws<LTXB_EPI_GELU_BF16>(tx, tw, to, p, grid, smem, stream);
+    case LTXB_EPI_SILU_BF16: return launch_ws<LTXB_EPI_SILU_BF16>(tx, tw, to, p, grid, smem, stream);
+    case LTXB_EPI_BIAS_F32: return launch_ws<LTXB_EPI_BIAS_F32>(tx, tw, to, p, grid, smem, stream);
+    case LTXB_EPI_RESID_GATE_F32: return launch_ws<LTXB_EPI_RESID_GATE_F32>(tx, tw, to, p, grid, smem, stream);
     default: return set_error(LTXB_ERR_BAD_ARG, "ltxb_gemm_bf16: unknown epilogue mode %d", epi->mode);
   }
 }

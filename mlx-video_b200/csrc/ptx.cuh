@@ -34,6 +34,17 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Release / acquire on a global flag at GPU scope (inter-CTA hand-off through L2): the release orders this thread's — and, by
+// cumulativity, every write a CTA barrier ordered before it — earlier writes before the add; the acquire orders later reads.
+__device__ __forceinline__ void red_release_gpu_add(int* flag, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* flag) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+  return v;
+}
+
 // Register re-balancing between warpgroups of one CTA (all four warps of the warpgroup must execute it).
 template <int kRegs>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
@@ -144,6 +155,21 @@ __device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* m
       ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+
+// TMA stores of a shared-memory tile (bulk async-group completion): plain store, and element-wise add into global memory
+// (performed at L2; f32 / bf16 by the tensor map's data type).  The issuing thread commits the group and must wait for the
+// shared-memory READS to finish before the tile is reused or the CTA exits.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM management

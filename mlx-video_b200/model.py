@@ -202,7 +202,7 @@ class LTXModel:
         shape = (Bc * Tc, w.shape[0])
         kv = self.workspace.get(pre + "text_kv", shape, BF16, self.device) if cache is None else cache.stacked(shape, self.device)
         if cache is None or not cache.valid:
-            ops.gemm(ctx.reshape(Bc * Tc, -1), w, b, kv)
+            ops.gemm(ctx.reshape(Bc * Tc, -1), w, b, kv, const_w=True)
             ops.qknorm_rope_segments(kv, kn.shape[0], 2 * H * dh, Bc, Tc, H, dh, kn, eps)
         return kv
 

@@ -108,10 +108,12 @@ def gemm(
     block_n: int = 0,
     cta_pair: int = -1,
     a_group_cols: int = 0,
+    const_w: bool = False,
 ) -> torch.Tensor:
     """out = epilogue(a @ w.T).  a: bf16 [..., K]; w: bf16 [N, K] (nn.Linear layout); see ltxb.h.
     a_group_cols = g > 0: ``a`` is a contiguous [K / g, M, g] tensor (head-group-major, as the Ulysses gather
-    all-to-all delivers it) standing for the [M, K] operand."""
+    all-to-all delivers it) standing for the [M, K] operand.  const_w: ``w`` is a model weight no kernel ahead in the
+    stream writes (LTXB_GEMM_CONST_W): the few-row kernel may start streaming it before its predecessor has finished."""
     _prep(a)
     if a_group_cols > 0:
         assert a.dim() == 3 and a.is_contiguous() and a.shape[2] == a_group_cols
@@ -128,6 +130,7 @@ def gemm(
     epi = Epilogue()
     epi.mode = mode
     epi.gate_row_div = gate_row_div
+    epi.flags = 1 if const_w else 0
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N
         epi.bias = bias.data_ptr()

@@ -178,7 +178,7 @@ class UlyssesGroup:
             raise _lib.LtxbError(f"sequence parallelism needs B == 1 and heads ({H}) divisible by ranks ({P})")
         hp = H // P
         qkv = ws.get(tag + ".qkv", (Tl, 3 * inner), BF16, dev)
-        ops.gemm(xq, attn.qkv_weight, attn.qkv_bias, qkv)
+        ops.gemm(xq, attn.qkv_weight, attn.qkv_bias, qkv, const_w=True)
         if self.peers is not None:
             return self._self_attention_fused(attn, qkv, Tl, pe), hp * dh
         send = ws.get(tag + ".a2a_send", (P, Tl, 3, hp * dh), BF16, dev)
@@ -260,7 +260,7 @@ class UlyssesGroup:
             full = parts.view(self.size * Tl, 2 * inner)
             o = attn.sdpa(ws, "av.v2a", q, full[:, :inner], full[:, inner:], Ba, Ta, self.size * Tl, None)
         ops.gemm(o, attn.to_out.weight, attn.to_out.bias, ax, _lib.EPI_RESID_GATE_F32, resid=ax, gate=gate,
-                 gate_table=gate_table, gate_row_div=row_div, gate_row_index=row_index)
+                 gate_table=gate_table, gate_row_div=row_div, gate_row_index=row_index, const_w=True)
 
 
 class ParallelLayout:

@@ -147,7 +147,7 @@ class Linear:
         if out is None:
             dt = F32 if mode == _lib.EPI_BIAS_F32 else BF16
             out = torch.empty((*x.shape[:-1], self.weight.shape[0]), dtype=dt, device=x.device)
-        ops.gemm(x2, self.weight, self.bias, out.view(-1, out.shape[-1]), mode)
+        ops.gemm(x2, self.weight, self.bias, out.view(-1, out.shape[-1]), mode, const_w=True)
         return out
 
 
@@ -214,18 +214,18 @@ class Attention:
             if not self.is_self:
                 raise ValueError("cross-attention module called without context")
             qkv = ws.get(tag + ".qkv", (B * Tq, 3 * inner), BF16, dev)
-            ops.gemm(xq, self.qkv_weight, self.qkv_bias, qkv)
+            ops.gemm(xq, self.qkv_weight, self.qkv_bias, qkv, const_w=True)
             q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
             Tk = Tq
         else:
             q = ws.get(tag + ".q", (B * Tq, inner), BF16, dev)
-            ops.gemm(xq, self.to_q.weight, self.to_q.bias, q)
+            ops.gemm(xq, self.to_q.weight, self.to_q.bias, q, const_w=True)
             kv = ws.get(tag + ".kv", (B * Tk, 2 * inner), BF16, dev) if kv_out is None else kv_out
             if not kv_ready:
                 if self.is_self:  # self-attention weights applied to an explicit context (attention.py:124-126)
-                    ops.gemm(context, self.qkv_weight[inner:], self.qkv_bias[inner:], kv)
+                    ops.gemm(context, self.qkv_weight[inner:], self.qkv_bias[inner:], kv, const_w=True)
                 else:
-                    ops.gemm(context, self.kv_weight, self.kv_bias, kv)
+                    ops.gemm(context, self.kv_weight, self.kv_bias, kv, const_w=True)
             k, v = kv[:, :inner], kv[:, inner:]
         H, dh = self.heads, self.dim_head
         if context is None and k_pe is None and self.k_norm.weight.data_ptr() == self.qk_norm_weight[1].data_ptr():
@@ -268,10 +268,10 @@ class Attention:
             o = self.sdpa(ws, tag, q, k, v, B, Tq, Tq if context is None else Tk, kv_bias)
         if defer:
             y = ws.get(tag + ".y", (B * Tq, self.query_dim), BF16, resid.device)
-            ops.gemm(o, self.to_out.weight, self.to_out.bias, y, _lib.EPI_BIAS_BF16, a_group_cols=group_cols)
+            ops.gemm(o, self.to_out.weight, self.to_out.bias, y, _lib.EPI_BIAS_BF16, a_group_cols=group_cols, const_w=True)
             return y
         ops.gemm(o, self.to_out.weight, self.to_out.bias, resid, _lib.EPI_RESID_GATE_F32, resid=resid, gate=gate,
-                 gate_table=gate_table, gate_row_div=row_div, gate_row_index=row_index, a_group_cols=group_cols)
+                 gate_table=gate_table, gate_row_div=row_div, gate_row_index=row_index, a_group_cols=group_cols, const_w=True)
         return None
 
     def __call__(self, x: Tensor, context: Optional[Tensor] = None, mask: Optional[Tensor] = None, pe=None,
@@ -323,9 +323,9 @@ class FeedForward:
 
     def fused(self, ws: Workspace, tag: str, x: Tensor, resid: Tensor, gate, gate_table, row_div, row_index) -> None:
         h = ws.get(tag + ".h", (x.shape[0], self.proj_in.weight.shape[0]), BF16, x.device)
-        ops.gemm(x, self.proj_in.weight, self.proj_in.bias, h, _lib.EPI_GELU_BF16)
+        ops.gemm(x, self.proj_in.weight, self.proj_in.bias, h, _lib.EPI_GELU_BF16, const_w=True)
         ops.gemm(h, self.proj_out.weight, self.proj_out.bias, resid, _lib.EPI_RESID_GATE_F32, resid=resid, gate=gate,
-                 gate_table=gate_table, gate_row_div=row_div, gate_row_index=row_index)
+                 gate_table=gate_table, gate_row_div=row_div, gate_row_index=row_index, const_w=True)
 
     def __call__(self, x: Tensor) -> Tensor:
         h = self.proj_in(x, mode=_lib.EPI_GELU_BF16)

@@ -171,6 +171,24 @@ def test_gemm_small_m_kernel_group_major_rows_and_strides():
     assert torch.equal(wide[:, :N], before[:, :N]) and torch.equal(wide[:, 2 * N:], before[:, 2 * N:])
 
 
+def test_gemm_small_m_kernel_const_weights_flag():
+    """LTXB_GEMM_CONST_W (weights requested before the programmatic-launch wait) gives the same bits as without it, also when
+    a split has fewer k-blocks than pipeline stages."""
+    g = torch.Generator(device=DEV).manual_seed(17)
+    for M, N, K, splits in [(160, 4096, 4096, 0), (160, 4096, 256, 2), (68, 2048, 128, 1), (320, 12288, 4096, 0), (16, 512, 64, 1)]:
+        a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+        w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+        bias = torch.randn(N, device=DEV, generator=g)
+        outs = []
+        for const_w in (False, True, True):
+            out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+            ops.gemm(a, w, bias, out, mode=_lib.EPI_BIAS_F32, cta_pair=4, block_n=splits, const_w=const_w)
+            outs.append(out)
+        torch.cuda.synchronize()
+        assert rel_l2(outs[0], a.float() @ w.float().T + bias) < 2e-5
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+
+
 def test_gemm_small_m_kernel_graph_replay():
     """Captured and replayed back to back (the counters are re-armed inside the kernel), interleaved with the big-tile
     split-K kernel that shares the workspace."""
@@ -185,8 +203,9 @@ def test_gemm_small_m_kernel_graph_replay():
     big = torch.empty(1280, 4096, device=DEV, dtype=torch.float32)
 
     def run():
-        ops.gemm(a, w1, None, h, mode=_lib.EPI_GELU_BF16)
-        ops.gemm(h, w2, None, y, mode=_lib.EPI_BIAS_F32)
+        # const_w: the weights start streaming before the producer of `h` has finished; `h` itself must still wait for it
+        ops.gemm(a, w1, None, h, mode=_lib.EPI_GELU_BF16, const_w=True)
+        ops.gemm(h, w2, None, y, mode=_lib.EPI_BIAS_F32, const_w=True)
         ops.gemm(big_a, w2[:, :K], None, big, mode=_lib.EPI_BIAS_F32)
 
     run()
