@@ -47,6 +47,7 @@ SIGNATURES = {
     "ltxb_set_device": (C.c_int, [_i32]),
     "ltxb_kernel_launches": (C.c_int64, []),
     "ltxb_gemm_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, C.POINTER(Epilogue), _i32, _i32, _vp]),
+    "ltxb_gemm_qw_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _i32, _vp]),
     "ltxb_gemm_workspace_bytes": (C.c_int64, []),
     "ltxb_gemm_set_workspace": (C.c_int, [_vp, _i64, _vp]),
     "ltxb_rmsnorm_modulate": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),

@@ -62,8 +62,11 @@ int encode_tmap_plain_2d(CUtensorMap* map, const void* base, int elem_bytes, con
   cuuint64_t gstr[1] = {row_stride_bytes};
   cuuint32_t bdim[2] = {box[0], box[1]};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base),
-                  gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+  const CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base),
+                  gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  // loads of narrow byte tiles (32 / 64 bytes per row and k-block): a miss brings the row's next k-blocks too
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(LTXB_ERR_CUDA, "cuTensorMapEncodeTiled (plain 2-D, %d-byte elements) failed with CUresult %d (dims %llu x %llu, box %u x %u)",

@@ -40,7 +40,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box);
 
-// 2-D map without swizzle for TMA STORES of a row-major shared-memory tile (elem_bytes 2 = bf16, 4 = f32): dims / box
+// 2-D map without swizzle: TMA STORES of a row-major shared-memory tile, loads of raw byte tiles (elem_bytes 1 = bytes, 2 = bf16, 4 = f32): dims / box
 // innermost-first, row stride in bytes.
 int encode_tmap_plain_2d(CUtensorMap* map, const void* base, int elem_bytes, const uint64_t* dims, uint64_t row_stride_bytes,
                          const uint32_t* box);

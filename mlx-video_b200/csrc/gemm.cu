@@ -831,6 +831,37 @@ extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   return dispatch_epi<1>(epi->mode, ta, tw, p, grid, smem, s);
 }
 
+extern "C" int ltxb_gemm_qw_bf16(const void* A, int64_t lda, const uint32_t* Wq, int64_t ldq, const void* scales, const void* biases,
+                                 int64_t lds, int32_t aux_f32, int32_t group_size, int32_t bits, void* out, int64_t ldo, int32_t M,
+                                 int32_t N, int32_t K, const ltxb_epilogue* epi, int32_t splits, void* stream) {
+  LTXB_CHECK_ARG(A && Wq && scales && biases && out && epi, "ltxb_gemm_qw_bf16: null pointer");
+  LTXB_CHECK_ARG(M > 0 && N > 0 && K > 0, "ltxb_gemm_qw_bf16: non-positive shape M=%d N=%d K=%d", M, N, K);
+  LTXB_CHECK_SUPPORTED(bits == 4 || bits == 8, "ltxb_gemm_qw_bf16: bits=%d (4 and 8 are built; expand other widths with ltxb_dequant_affine_bf16)", bits);
+  LTXB_CHECK_SUPPORTED(group_size == 32 || group_size == 64 || group_size == 128, "ltxb_gemm_qw_bf16: group_size=%d (32, 64 and 128 are built)", group_size);
+  LTXB_CHECK_SUPPORTED(gemm_small_m_supported(M, N, K), "ltxb_gemm_qw_bf16: the packed-weight kernel is the few-row one: M=%d must be <= 512 and K=%d a multiple of 64 (expand the weights with ltxb_dequant_affine_bf16 for more rows)", M, K);
+  LTXB_CHECK_SUPPORTED(N % 16 == 0 && K % group_size == 0, "ltxb_gemm_qw_bf16: N=%d must be a multiple of 16 and K=%d of the group size %d", N, K, group_size);
+  LTXB_CHECK_ARG(aligned16(A) && aligned16(Wq) && aligned16(out), "ltxb_gemm_qw_bf16: pointers must be 16-byte aligned");
+  LTXB_CHECK_SUPPORTED(lda % 8 == 0 && ldo % 8 == 0 && (lda >= K || epi->a_group_cols > 0) && ldo >= N && ldq % 4 == 0 &&
+                           ldq >= static_cast<int64_t>(K) * bits / 32 && lds >= K / group_size,
+                       "ltxb_gemm_qw_bf16: leading dimensions must cover the row (lda, ldo multiples of 8, ldq of 4 words)");
+  LTXB_CHECK_ARG(epi->mode >= 0 && epi->mode < LTXB_EPI_COUNT, "ltxb_gemm_qw_bf16: bad epilogue mode %d", epi->mode);
+  LTXB_CHECK_ARG(splits >= 0, "ltxb_gemm_qw_bf16: splits=%d", splits);
+  if (epi->bias) LTXB_CHECK_ARG(aligned16(epi->bias), "ltxb_gemm_qw_bf16: bias must be 16-byte aligned");
+  if (epi->mode == LTXB_EPI_RESID_GATE_F32) {
+    LTXB_CHECK_ARG(epi->resid && aligned16(epi->resid) && epi->ldr % 4 == 0 && epi->ldr >= N,
+                   "ltxb_gemm_qw_bf16: residual epilogue needs a 16-byte aligned f32 resid with ldr %% 4 == 0");
+    if (epi->gate) LTXB_CHECK_ARG(epi->gate_row_index || epi->gate_row_div >= 1, "ltxb_gemm_qw_bf16: gate_row_div must be >= 1");
+  }
+  if (epi->mode == LTXB_EPI_BIAS_F32 || epi->mode == LTXB_EPI_RESID_GATE_F32)
+    LTXB_CHECK_SUPPORTED(ldo % 4 == 0, "ltxb_gemm_qw_bf16: f32 output needs ldo %% 4 == 0");
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const SkWorkspace ws = (dev >= 0 && dev < kMaxDevices) ? g_sk_ws[dev] : SkWorkspace{};
+  const WsPacked packed{scales, biases, lds, group_size, bits, aux_f32 != 0};
+  return launch_gemm_small_m(A, lda, Wq, ldq, out, ldo, M, N, K, epi, ws.partials, ws.partials ? kSkPartialBytes : 0, ws.counters, splits,
+                             reinterpret_cast<cudaStream_t>(stream), &packed);
+}
+
 extern "C" int64_t ltxb_gemm_workspace_bytes(void) { return kSkCounterInts * sizeof(int) + kSkPartialBytes; }
 
 extern "C" int ltxb_gemm_set_workspace(void* workspace, int64_t bytes, void* stream) {

@@ -56,6 +56,12 @@ struct WsParams {
   const int* gate_row_index;
   const float* gate_table;
   int a_group_cols;
+  // packed weights (kWBits 4 / 8): MLX affine groups, out = bf16(scales * q + biases) (ltxb_dequant_affine_bf16's arithmetic)
+  const void* scales;
+  const void* biases;
+  long long lds;
+  int group;    // columns per (scale, bias) pair: 32, 64 or 128
+  int aux_f32;  // scales / biases are f32 (else bf16)
   int const_w;      // LTXB_GEMM_CONST_W: the first stages' weight tiles are requested before the PDL wait
   int out_tma;      // 0: per-thread global stores; 1: output chunks staged in shared memory, written by TMA; 2: staged, TMA add
                     // into `out` (RESID_GATE with out == resid: out += (acc + bias) * g, one add per element)
@@ -79,6 +85,7 @@ __device__ __forceinline__ long long ws_globaltimer() {
 struct WsSmemHeader {
   uint64_t full[kWsMaxStages];
   uint64_t empty[kWsMaxStages];
+  uint64_t raw_full[kWsMaxStages];  // packed weights only: the raw tile of a stage has landed
   uint64_t tmem_full;
   uint32_t tmem_base;
 };
@@ -179,7 +186,11 @@ __device__ __forceinline__ void ws_stage_chunk(const WsParams& p, const float* a
   }
 }
 
-template <int kEpi>
+// kWBits = 16: W is bf16 and lands in the MMA's swizzled layout by TMA.  kWBits = 4 / 8: W is MLX affine-quantised; TMA
+// brings the PACKED tile (4 / 8 KB instead of 16 KB per k-block — the weight stream is what bounds this kernel) and the
+// eight epilogue warps, idle during the main loop, expand it to bf16 in shared memory in exactly the arithmetic of
+// ltxb_dequant_affine_bf16 (so the result is bit-identical to dequantise-then-GEMM) before the MMA reads it.
+template <int kEpi, int kWBits>
 __global__ void __launch_bounds__(kWsThreads, 2)
 gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_out, const WsParams p) {
@@ -200,8 +211,12 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   const int kb1 = (num_kb * (split + 1)) / p.splits;
   const int mma_n = p.m_pad / p.n_mma;  // tokens per MMA
   const int box_rows = mma_n / 2;       // token rows this CTA stages per MMA
+  constexpr bool kPacked = (kWBits != 16);
+  constexpr uint32_t kRawRowBytes = kPacked ? kWsBlockK * kWBits / 8 : 0;  // packed bytes of one weight row per k-block
+  constexpr uint32_t kRawBytes = kWsTileRows * kRawRowBytes;
   const uint32_t x_box_bytes = box_rows * kWsBlockK * 2;
-  const uint32_t stage_bytes = kWsWBytes + p.n_mma * x_box_bytes;
+  const uint32_t raw_off = kWsWBytes + p.n_mma * x_box_bytes;  // stage = [W bf16][token boxes][raw packed W]
+  const uint32_t stage_bytes = raw_off + kRawBytes;
   const int num_stages = p.num_stages;
 
   if (warp == 0 && lane == 0) {
@@ -212,8 +227,9 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < num_stages; ++s) {
-        mbar_init(&hdr->full[s], 1);
+        mbar_init(&hdr->full[s], kPacked ? 1 + 2 * 8 : 1);  // packed: + the eight expanding warps of both CTAs
         mbar_init(&hdr->empty[s], 1);
+        mbar_init(&hdr->raw_full[s], 1);
       }
       mbar_init(&hdr->tmem_full, 1);
       fence_mbar_init();
@@ -230,12 +246,18 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   // producer fills every stage's weight half, the token rows follow after the wait.
   const int n0_w = tile * (2 * kWsTileRows) + static_cast<int>(cta_rank) * kWsTileRows;
   int prefetched = 0;
-  if (p.const_w && !WS_DBG(4)) {
+  if (p.const_w) {
     prefetched = min(num_stages, kb1 - kb0);
     if (warp == 0 && lane == 0) {
       for (int s = 0; s < prefetched; ++s) {
-        if (is_leader) mbar_arrive_expect_tx(&hdr->full[s], stage_bytes * 2);
-        tma_load_2d_pair(tiles + static_cast<size_t>(s) * stage_bytes, &tmap_w, mapa_u32(smem_u32(&hdr->full[s]), 0), (kb0 + s) * kWsBlockK, n0_w);
+        uint8_t* st = tiles + static_cast<size_t>(s) * stage_bytes;
+        if constexpr (kPacked) {
+          mbar_arrive_expect_tx(&hdr->raw_full[s], kRawBytes);
+          tma_load_2d(st + raw_off, &tmap_w, &hdr->raw_full[s], (kb0 + s) * static_cast<int>(kRawRowBytes), n0_w);
+        } else {
+          if (is_leader) mbar_arrive_expect_tx(&hdr->full[s], stage_bytes * 2);
+          tma_load_2d_pair(st, &tmap_w, mapa_u32(smem_u32(&hdr->full[s]), 0), (kb0 + s) * kWsBlockK, n0_w);
+        }
       }
     }
   }
@@ -251,16 +273,23 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       uint32_t stage = 0, phase = 0;
       const int n0 = n0_w;
       for (int kb = kb0; kb < kb1; ++kb) {
-        const bool w_done = (kb - kb0) < prefetched;  // this stage's weight tile and byte count went out before the wait
+        const bool w_done = (kb - kb0) < prefetched;  // this stage's weight tile went out before the wait
         if (!w_done) mbar_wait(&hdr->empty[stage], phase ^ 1);
         uint8_t* sw = tiles + static_cast<size_t>(stage) * stage_bytes;
         uint8_t* sx = sw + kWsWBytes;
         const int ka = kb * kWsBlockK;
-        const bool skip_x = WS_DBG(1) && kb != kb0, skip_w = WS_DBG(4) && kb != kb0;
-        if (is_leader && !w_done) mbar_arrive_expect_tx(&hdr->full[stage], (stage_bytes - (skip_x ? p.n_mma * x_box_bytes : 0) - (skip_w ? kWsWBytes : 0)) * 2);  // both CTAs report on the leader's barrier
-        const uint32_t bar = mapa_u32(smem_u32(&hdr->full[stage]), 0);
-        if (!skip_w && !w_done) tma_load_2d_pair(sw, &tmap_w, bar, ka, n0);
-        for (int j = 0; j < p.n_mma && !skip_x; ++j) {
+        const uint32_t bar = mapa_u32(smem_u32(&hdr->full[stage]), 0);  // both CTAs report their bytes on the leader's barrier
+        if constexpr (kPacked) {
+          if (!w_done) {
+            mbar_arrive_expect_tx(&hdr->raw_full[stage], kRawBytes);
+            tma_load_2d(sw + raw_off, &tmap_w, &hdr->raw_full[stage], kb * static_cast<int>(kRawRowBytes), n0);
+          }
+          if (is_leader) mbar_arrive_expect_tx(&hdr->full[stage], p.n_mma * x_box_bytes * 2);
+        } else {
+          if (is_leader && !w_done) mbar_arrive_expect_tx(&hdr->full[stage], stage_bytes * 2);
+          if (!w_done) tma_load_2d_pair(sw, &tmap_w, bar, ka, n0);
+        }
+        for (int j = 0; j < p.n_mma; ++j) {
           const int row0 = j * mma_n + static_cast<int>(cta_rank) * box_rows;
           if (p.a_group_cols > 0) tma_load_3d_pair(sx + j * x_box_bytes, &tmap_x, bar, ka % p.a_group_cols, row0, ka / p.a_group_cols);
           else tma_load_2d_pair(sx + j * x_box_bytes, &tmap_x, bar, ka, row0);
@@ -295,6 +324,112 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       umma_commit_pair(&hdr->tmem_full, 3);
     }
   } else {
+    if constexpr (kPacked) {
+      // ===================== packed weights: expand raw -> bf16 in the MMA's swizzled layout =====================
+      // thread = (weight row, half of the k-block): 32 levels -> 32 bf16 = four 16-byte chunks of the row's 128 bytes,
+      // chunk c stored at position c ^ (row % 8) (the 128-byte swizzle the TMA would have applied)
+      const int t = static_cast<int>(threadIdx.x) - 64;
+      const int row = t & (kWsTileRows - 1), khalf = t >> 7;
+      const long long row_abs = static_cast<long long>(n0_w) + row;
+      const bool row_ok = row_abs < p.N;
+      // (scale, bias) of this thread's 32 columns change every k-block (group 64) — and a load issued under a saturated HBM
+      // stream takes microseconds to come back — so they are fetched 16 bytes at a time (8 bf16 / 4 f32 groups of the row)
+      // one chunk AHEAD of the one in use: the wait lands on a load issued several k-blocks earlier
+      const int esz = p.aux_f32 ? 4 : 2;
+      const int chunk_groups = 16 / esz;
+      const int groups_per_row = p.K / p.group;
+      const bool chunked = (groups_per_row % chunk_groups == 0) && ((p.lds * esz) % 16 == 0) &&
+                           ((reinterpret_cast<uintptr_t>(p.scales) | reinterpret_cast<uintptr_t>(p.biases)) % 16 == 0);
+      const int group_shift = p.group == 32 ? 5 : (p.group == 64 ? 6 : 7);
+      auto group_of = [&](int kb) { return (kb * kWsBlockK + khalf * 32) >> group_shift; };
+      auto load_chunk = [&](int c, uint4& S, uint4& B) {
+        S = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0, 0);
+        if (!row_ok || c * chunk_groups >= groups_per_row) return;
+        const size_t off = (static_cast<size_t>(row_abs) * p.lds + static_cast<size_t>(c) * chunk_groups) * esz;
+        S = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.scales) + off));
+        B = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.biases) + off));
+      };
+      auto pick = [&](const uint4& V, int i) -> float {  // element i of a chunk without indexing registers dynamically
+        if (p.aux_f32) {
+          const uint32_t lo = (i & 1) ? V.y : V.x, hi = (i & 1) ? V.w : V.z;
+          return __uint_as_float((i & 2) ? hi : lo);
+        }
+        const uint32_t a = (i & 2) ? V.y : V.x, b = (i & 2) ? V.w : V.z;
+        const uint32_t wd = (i & 4) ? b : a;
+        return __uint_as_float((i & 1) ? (wd & 0xffff0000u) : (wd << 16));
+      };
+      auto load_scalar = [&](int kb, float& sc, float& bi) {  // layouts the 16-byte chunks do not fit
+        sc = 0.f, bi = 0.f;
+        if (!row_ok) return;
+        const long long a = row_abs * p.lds + group_of(kb);
+        if (p.aux_f32) {
+          sc = __ldg(static_cast<const float*>(p.scales) + a);
+          bi = __ldg(static_cast<const float*>(p.biases) + a);
+        } else {
+          sc = __bfloat162float(static_cast<const __nv_bfloat16*>(p.scales)[a]);
+          bi = __bfloat162float(static_cast<const __nv_bfloat16*>(p.biases)[a]);
+        }
+      };
+      const uint32_t tiles_u32 = smem_u32(tiles);
+      const uint32_t raw_thread_off = raw_off + row * kRawRowBytes + khalf * (kRawRowBytes / 2);
+      uint32_t dst_off[4];  // chunk c of the row's 128 bytes sits at position c ^ (row % 8): the TMA's 128-byte swizzle
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst_off[j] = row * 128 + (((khalf * 4 + j) ^ (row & 7)) << 4);
+      uint32_t stage = 0, phase = 0;
+      uint4 s_cur, b_cur, s_next, b_next;
+      int cur_chunk = group_of(kb0) / chunk_groups;
+      if (chunked) {
+        load_chunk(cur_chunk, s_cur, b_cur);
+        load_chunk(cur_chunk + 1, s_next, b_next);
+      }
+      for (int kb = kb0; kb < kb1; ++kb) {
+        float sc, bi;
+        if (chunked) {
+          const int g = group_of(kb);
+          if (g / chunk_groups != cur_chunk) {
+            s_cur = s_next, b_cur = b_next;
+            ++cur_chunk;
+            load_chunk(cur_chunk + 1, s_next, b_next);
+          }
+          const int gi = g - cur_chunk * chunk_groups;
+          sc = pick(s_cur, gi), bi = pick(b_cur, gi);
+        } else {
+          load_scalar(kb, sc, bi);
+        }
+        mbar_wait(&hdr->raw_full[stage], phase);
+        const uint32_t st = tiles_u32 + stage * stage_bytes;  // shared-space addresses: LDS / STS, no generic-pointer arithmetic
+        uint32_t w[kWBits];  // 4-bit: 4 words (32 levels), 8-bit: 8 words
+        if (!WS_DBG(32)) {  // (timing experiment: hand the stage on without expanding it)
+        lds128(st + raw_thread_off, w[0], w[1], w[2], w[3]);
+        if constexpr (kWBits == 8) lds128(st + raw_thread_off + 16, w[4], w[5], w[6], w[7]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v[8];
+          // level -> float through the 2^23 trick (bits 0x4B0000qq = 8388608 + q, exact), then scales * q + biases with
+          // the two roundings of ltxb_dequant_affine_bf16
+          if constexpr (kWBits == 4) {
+            const uint32_t lo = w[j] & 0x0F0F0F0Fu, hi = (w[j] >> 4) & 0x0F0F0F0Fu;  // even / odd levels, one per byte
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t bits = __byte_perm((e & 1) ? hi : lo, 0x4B000000u, 0x7540u | (e >> 1));
+              v[e] = __fadd_rn(__fmul_rn(sc, __uint_as_float(bits) - 8388608.0f), bi);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t bits = __byte_perm(w[2 * j + (e >> 2)], 0x4B000000u, 0x7540u | (e & 3));
+              v[e] = __fadd_rn(__fmul_rn(sc, __uint_as_float(bits) - 8388608.0f), bi);
+            }
+          }
+          sts128(st + dst_off[j], pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> the (pair leader's) tensor core reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&hdr->full[stage], 0);
+        if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
+      }
+    }
     // ===================== epilogue: thread = output column, walks the tokens =====================
     // Eight warps, two per TMEM lane quarter: the epilogue is a long run of per-token address / convert / store
     // instructions per thread, so it is paced by how many warps the four schedulers can interleave.
@@ -487,10 +622,10 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int kEpi>
+template <int kEpi, int kWBits>
 static int launch_ws(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& to, const WsParams& p, int grid, size_t smem,
                      cudaStream_t stream) {
-  auto kernel = gemm_small_m_kernel<kEpi>;
+  auto kernel = gemm_small_m_kernel<kEpi, kWBits>;
   static PerDeviceOnce configured;
   if (configured.first()) LTXB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   LTXB_CUDA(launch_kernel(kernel, dim3(grid), dim3(kWsThreads), smem, stream, 2, tx, tw, to, p));
@@ -501,7 +636,8 @@ bool gemm_small_m_supported(int M, int N, int K) { return M >= 1 && M <= 512 && 
 
 int launch_gemm_small_m(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
                         const ltxb_epilogue* epi, float* partials, long long partial_bytes, int* counters, int want_splits,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const WsPacked* packed) {
+  const int w_bits = packed != nullptr ? packed->bits : 16;
   const int sms = num_sms();
   if (sms <= 0) return set_error(LTXB_ERR_NO_DEVICE, "ltxb_gemm_bf16: no CUDA device");
   WsParams p{};
@@ -510,7 +646,10 @@ int launch_gemm_small_m(const void* A, int64_t lda, const void* W, int64_t ldw, 
   p.m_pad = p.n_mma == 1 ? ((M + 15) / 16) * 16 : ((M + 31) / 32) * 32;
   p.tmem_cols = 32;
   while (p.tmem_cols < p.m_pad) p.tmem_cols *= 2;
-  const size_t stage_bytes = kWsWBytes + static_cast<size_t>(p.m_pad / 2) * kWsBlockK * 2;
+  // the schedule (CTAs per SM, k-range splits) is decided on the bf16 stage size for packed weights too, so that both paths
+  // add their partial sums in the same order (bit-identical results); only the stage COUNT follows the real size
+  const size_t stage_bytes_sched = kWsWBytes + static_cast<size_t>(p.m_pad / 2) * kWsBlockK * 2;
+  const size_t stage_bytes = stage_bytes_sched + (w_bits != 16 ? kWsTileRows * kWsBlockK * w_bits / 8 : 0);
   const int tiles = (N + 2 * kWsTileRows - 1) / (2 * kWsTileRows);
   const int num_kb = K / kWsBlockK;
   static const int env_min_kb = [] { const char* e = getenv("LTXB_GEMM_SMALL_M_MIN_KB"); return e ? atoi(e) : 4; }();
@@ -529,7 +668,7 @@ int launch_gemm_small_m(const void* A, int64_t lda, const void* W, int64_t ldw, 
   // (profiles/r2/gemm_small_m.md): one per SM wins whenever it still fills the machine (>= 85 % of the SM pairs busy).
   const int pairs = sms / 2;
   int per_sm = 1;
-  if (p.tmem_cols <= 256 && (113 * 1024 - 1024 - kWsHeader) / stage_bytes >= 3) {
+  if (p.tmem_cols <= 256 && (113 * 1024 - 1024 - kWsHeader) / stage_bytes_sched >= 3 && (113 * 1024 - 1024 - kWsHeader) / stage_bytes >= 2) {
     const int s1 = splits_for(pairs);
     const bool fills = tiles <= pairs && tiles * s1 * 100 >= pairs * 85;
     per_sm = (env_per_sm == 1 || env_per_sm == 2) ? env_per_sm : (fills ? 1 : 2);
@@ -554,6 +693,9 @@ int launch_gemm_small_m(const void* A, int64_t lda, const void* W, int64_t ldw, 
   p.gate_table = epi->gate_table;
   p.partials = partials;
   p.counters = counters;
+  if (packed != nullptr) {
+    p.scales = packed->scales, p.biases = packed->biases, p.lds = packed->lds, p.group = packed->group, p.aux_f32 = packed->aux_f32;
+  }
   static const int env_const_w = [] { const char* e = getenv("LTXB_GEMM_CONST_W"); return e ? atoi(e) : 1; }();
   p.const_w = (env_const_w && (epi->flags & LTXB_GEMM_CONST_W)) ? 1 : 0;
 #ifdef LTXB_WS_DEBUG
@@ -582,7 +724,12 @@ int launch_gemm_small_m(const void* A, int64_t lda, const void* W, int64_t ldw, 
     int rc = encode_tmap_bf16(&tx, A, 2, dims, strides, box);
     if (rc) return rc;
   }
-  {
+  if (packed != nullptr) {  // the packed tile as bytes: 64 levels = 32 / 64 bytes per row and k-block, 128 rows
+    const uint64_t dims[2] = {static_cast<uint64_t>(K) * w_bits / 8, static_cast<uint64_t>(N)};
+    const uint32_t box[2] = {static_cast<uint32_t>(kWsBlockK * w_bits / 8), kWsTileRows};
+    int rc = encode_tmap_plain_2d(&tw, W, 1, dims, static_cast<uint64_t>(ldw) * 4, box);
+    if (rc) return rc;
+  } else {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
     const uint32_t box[2] = {kWsBlockK, kWsTileRows};
@@ -608,14 +755,19 @@ int launch_gemm_small_m(const void* A, int64_t lda, const void* W, int64_t ldw, 
     if (rc) return rc;
   }
   const int grid = tiles * splits * 2;
-  switch (epi->mode) {
-    case LTXB_EPI_BIAS_BF16: return launch_ws<LTXB_EPI_BIAS_BF16>(tx, tw, to, p, grid, smem, stream);
-    case LTXB_EPI_GELU_BF16: return launch_ws<LTXB_EPI_GELU_BF16>(tx, tw, to, p, grid, smem, stream);
-    case LTXB_EPI_SILU_BF16: return launch_ws<LTXB_EPI_SILU_BF16>(tx, tw, to, p, grid, smem, stream);
-    case LTXB_EPI_BIAS_F32: return launch_ws<LTXB_EPI_BIAS_F32>(tx, tw, to, p, grid, smem, stream);
-    case LTXB_EPI_RESID_GATE_F32: return launch_ws<LTXB_EPI_RESID_GATE_F32>(tx, tw, to, p, grid, smem, stream);
-    default: return set_error(LTXB_ERR_BAD_ARG, "ltxb_gemm_bf16: unknown epilogue mode %d", epi->mode);
+#define LTXB_WS_DISPATCH(BITS)                                                                                         \
+  switch (epi->mode) {                                                                                                 \
+    case LTXB_EPI_BIAS_BF16: return launch_ws<LTXB_EPI_BIAS_BF16, BITS>(tx, tw, to, p, grid, smem, stream);             \
+    case LTXB_EPI_GELU_BF16: return launch_ws<LTXB_EPI_GELU_BF16, BITS>(tx, tw, to, p, grid, smem, stream);             \
+    case LTXB_EPI_SILU_BF16: return launch_ws<LTXB_EPI_SILU_BF16, BITS>(tx, tw, to, p, grid, smem, stream);             \
+    case LTXB_EPI_BIAS_F32: return launch_ws<LTXB_EPI_BIAS_F32, BITS>(tx, tw, to, p, grid, smem, stream);               \
+    case LTXB_EPI_RESID_GATE_F32: return launch_ws<LTXB_EPI_RESID_GATE_F32, BITS>(tx, tw, to, p, grid, smem, stream);   \
+    default: return set_error(LTXB_ERR_BAD_ARG, "ltxb_gemm: unknown epilogue mode %d", epi->mode);                     \
   }
+  if (w_bits == 4) { LTXB_WS_DISPATCH(4) }
+  if (w_bits == 8) { LTXB_WS_DISPATCH(8) }
+  LTXB_WS_DISPATCH(16)
+#undef LTXB_WS_DISPATCH
 }
 
 }  // namespace ltxb

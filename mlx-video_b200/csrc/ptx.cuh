@@ -73,12 +73,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// arrive on the barrier at the same smem offset in CTA `cta` of this cluster
+// arrive on the barrier at the same smem offset in CTA `cta` of this cluster.  Default semantics (.release at CTA scope),
+// as the CUTLASS cluster pipelines use for TMEM / transformed-operand hand-offs: what the arrive publishes is TMEM reads
+// retired by tcgen05.wait::ld or shared-memory writes already pushed to the async proxy by fence.proxy.async.  The
+// explicit .release.cluster form compiles to MEMBAR.ALL.GPU, which also drains every global load / store the thread has
+// in flight (measured: 1.4 us per k-block in the packed-weight expander, profiles/r2/gemm_small_m.md).
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+#ifdef LTXB_REMOTE_ARRIVE_CLUSTER_RELEASE  // A/B builds only
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+#else
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+#endif
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
@@ -109,6 +117,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+
+// 16-byte shared-memory accesses by shared-space address (a generic pointer would compile to LD / ST with 64-bit arithmetic)
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 // generic-proxy writes (st.shared) -> visible to the async proxy (UMMA / TMA reads of smem)

@@ -154,6 +154,9 @@ def apply_lora_to_model(model, lora_specs: Iterable[LoraSpec], verbose: bool = F
         _report(spec, applied, skipped, verbose)
     if total:
         model.clear_caches()  # projected-context caches (and the graphs that fill them) were computed with the old weights
+        from .packed import REGISTRY as packed_registry
+
+        packed_registry.clear()  # the merged weights exist in bf16 only: packed copies kept by load_weights(keep_packed=True) are stale
     return model
 
 

@@ -229,14 +229,19 @@ class LTXModel:
     def num_parameters(self) -> int:
         return sum(t.numel() for _, t in self.named_parameters())
 
-    def load_weights(self, weights: Dict[str, Tensor], strict: bool = True, quant_meta: Optional[dict] = None) -> None:
+    def load_weights(self, weights: Dict[str, Tensor], strict: bool = True, quant_meta: Optional[dict] = None,
+                     keep_packed: bool = False) -> None:
         """Copy a state dict (reference names) into the device layout.  Strict: every model parameter
         must be present (ValueError otherwise, ltx.py:874-881) and unknown keys are an error.
         MLX affine-quantised linears (``X.weight`` uint32 beside ``X.scales`` / ``X.biases``, the tensors
         ``nn.QuantizedLinear`` holds after ltx.py:641-725) are expanded to bf16 on the device at this point
         (``ltxb_dequant_affine_bf16``); group size and bits follow from the tensor shapes and must agree with
-        ``quant_meta`` (the checkpoint's quantization.json, ltx.py:649-668) when that is given."""
+        ``quant_meta`` (the checkpoint's quantization.json, ltx.py:649-668) when that is given.
+        keep_packed: the packed words, scales and biases also stay on the device (packed.py) and few-row products
+        (M <= 256: sequence-parallel shards, the audio stream, AdaLN rows) stream THEM instead of the expansion
+        (``ltxb_gemm_qw_bf16``, bit-identical results, a quarter / half of the weight bytes)."""
         from .checkpoint import quant_layout
+        from .packed import REGISTRY as packed_registry
 
         params = self.parameters()
         quantised = {k[: -len(".scales")] for k in weights if k.endswith(".scales")}
@@ -259,14 +264,18 @@ class LTXModel:
                 group_size, bits = quant_layout(name, tuple(src.shape), tuple(scales.shape), tuple(dst.shape), quant_meta)
                 aux_dtype = BF16 if scales.dtype == BF16 else F32  # f16 scales are widened (plumbing), bf16 / f32 are read as stored
                 dev = dst.device
-                ops.dequant_affine(src.to(dev).contiguous(), scales.to(dev, aux_dtype).contiguous(),
-                                   biases.to(dev, aux_dtype).contiguous(), dst, group_size, bits)
+                src_d, scales_d, biases_d = src.to(dev).contiguous(), scales.to(dev, aux_dtype).contiguous(), biases.to(dev, aux_dtype).contiguous()
+                ops.dequant_affine(src_d, scales_d, biases_d, dst, group_size, bits)
+                if keep_packed:
+                    packed_registry.register(dst, src_d, scales_d, biases_d, group_size, bits)
                 continue
             if src.dtype in (torch.uint32, torch.int32, torch.uint8):
                 raise ValueError(f"{name} is an integer tensor without .scales / .biases siblings")
             if tuple(src.shape) != tuple(dst.shape):
                 raise ValueError(f"shape mismatch for {name}: checkpoint {tuple(src.shape)} vs model {tuple(dst.shape)}")
             dst.copy_(src.to(device=dst.device, dtype=dst.dtype))  # plumbing: H2D copy + storage cast
+        if keep_packed:
+            packed_registry.merge_adjacent()
         self.clear_caches()  # projected-context caches and captured graphs belong to the old weights
 
     def sanitize(self, weights: Dict[str, Tensor]) -> Dict[str, Tensor]:
@@ -304,7 +313,7 @@ class LTXModel:
 
     @classmethod
     def from_pretrained(cls, model_path, config: LTXModelConfig, strict: bool = True,
-                        weights_override: Optional[Dict[str, Tensor]] = None, device=None) -> "LTXModel":
+                        weights_override: Optional[Dict[str, Tensor]] = None, device=None, keep_packed: bool = False) -> "LTXModel":
         """ltx.py:535-885: reads safetensors file(s), renames upstream keys, rounds fp32 tensors to bf16 values
         (ltx.py:613-615), expands MLX-quantised linears (ltx.py:641-725), IGNORES tensors the configured model does
         not have (audio weights beside a video-only config, ltx.py:739-740) and, when ``strict``, raises ValueError
@@ -326,12 +335,12 @@ class LTXModel:
                     meta = read_quantization_meta(checkpoint_files(model_path)[0])
                 except (OSError, ValueError, IndexError):
                     meta = None
-            model.load_weights(given, strict=strict, quant_meta=meta)
+            model.load_weights(given, strict=strict, quant_meta=meta, keep_packed=keep_packed)
             return model
         weights = load_transformer_weights(model_path, config, expected=expected)
         meta = read_quantization_meta(checkpoint_files(model_path)[0]) if any(k.endswith(".scales") for k in weights) else None
         try:
-            model.load_weights(weights, strict=strict, quant_meta=meta)
+            model.load_weights(weights, strict=strict, quant_meta=meta, keep_packed=keep_packed)
         except ValueError as e:
             if str(e).startswith("Missing "):
                 raise ValueError(str(e).replace(" parameters:", " parameters after load (sample:", 1) + ").") from None

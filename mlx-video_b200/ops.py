@@ -10,6 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import Epilogue, check, lib
+from .packed import REGISTRY as _packed
 
 _device_set: set = set()
 
@@ -94,6 +95,29 @@ def _ld(t: torch.Tensor) -> int:
     return ld
 
 
+def _epilogue(mode, N, bias, resid, gate, gate_table, gate_row_div, gate_row_index, const_w) -> "Epilogue":
+    epi = Epilogue()
+    epi.mode = mode
+    epi.gate_row_div = gate_row_div
+    epi.flags = 1 if const_w else 0
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+        epi.bias = bias.data_ptr()
+    if mode == _lib.EPI_RESID_GATE_F32:
+        assert resid is not None and resid.dtype == torch.float32
+        epi.resid = resid.data_ptr()
+        epi.ldr = _ld(resid)
+        if gate is not None:
+            assert gate.dtype == torch.float32 and gate.shape[-1] == N
+            epi.gate = gate.data_ptr()
+            epi.gate_ld = _ld(gate)
+            epi.gate_row_index = _ptr(gate_row_index)
+            if gate_table is not None:
+                assert gate_table.dtype == torch.float32 and gate_table.numel() == N
+                epi.gate_table = gate_table.data_ptr()
+    return epi
+
+
 def gemm(
     a: torch.Tensor,
     w: torch.Tensor,
@@ -127,30 +151,67 @@ def gemm(
         assert out.dtype == torch.float32
     else:
         assert out.dtype == torch.bfloat16
-    epi = Epilogue()
-    epi.mode = mode
-    epi.gate_row_div = gate_row_div
-    epi.flags = 1 if const_w else 0
-    if bias is not None:
-        assert bias.dtype == torch.float32 and bias.numel() == N
-        epi.bias = bias.data_ptr()
-    if mode == _lib.EPI_RESID_GATE_F32:
-        assert resid is not None and resid.dtype == torch.float32
-        epi.resid = resid.data_ptr()
-        epi.ldr = _ld(resid)
-        if gate is not None:
-            assert gate.dtype == torch.float32 and gate.shape[-1] == N
-            epi.gate = gate.data_ptr()
-            epi.gate_ld = _ld(gate)
-            epi.gate_row_index = _ptr(gate_row_index)
-            if gate_table is not None:
-                assert gate_table.dtype == torch.float32 and gate_table.numel() == N
-                epi.gate_table = gate_table.data_ptr()
+    if block_n == 0 and cta_pair < 0 and M <= _packed.max_rows and N >= 128 and K >= 256 and len(_packed):  # = where ltxb_gemm_bf16 picks the few-row kernel
+        hit = _packed.lookup(w)  # a quantised linear kept packed (packed.py): stream the packed words instead
+        if hit is not None:
+            return gemm_qw(a, hit[0], hit[1], hit[2], hit[3], hit[4], bias, out, mode, resid, gate, gate_table, gate_row_div,
+                           gate_row_index, 0, a_group_cols, const_w)
+    epi = _epilogue(mode, N, bias, resid, gate, gate_table, gate_row_div, gate_row_index, const_w)
     lda = _ld(a)
     if a_group_cols > 0:
         epi.a_group_cols, epi.a_group_stride, lda = a_group_cols, M * a_group_cols, a_group_cols
     _call("ltxb_gemm_bf16", 2.0 * M * N * K, a.data_ptr(), lda, w.data_ptr(), _ld(w), out.data_ptr(), _ld(out), M, N, K,
                             C.byref(epi), block_n, cta_pair, _stream())
+    return out
+
+
+def gemm_qw(
+    a: torch.Tensor,
+    packed: torch.Tensor,
+    scales: torch.Tensor,
+    biases: torch.Tensor,
+    group_size: int,
+    bits: int,
+    bias: Optional[torch.Tensor],
+    out: torch.Tensor,
+    mode: int = _lib.EPI_BIAS_BF16,
+    resid: Optional[torch.Tensor] = None,
+    gate: Optional[torch.Tensor] = None,
+    gate_table: Optional[torch.Tensor] = None,
+    gate_row_div: int = 1,
+    gate_row_index: Optional[torch.Tensor] = None,
+    splits: int = 0,
+    a_group_cols: int = 0,
+    const_w: bool = False,
+) -> torch.Tensor:
+    """out = epilogue(a @ dequant(packed, scales, biases).T) for FEW rows (M <= 512) with the MLX affine-quantised weight
+    kept packed in HBM (``ltxb_gemm_qw_bf16``): uint32 / int32 [N, K*bits/32], scales / biases bf16 or f32 [N, K/group_size].
+    Bit-identical to ``dequant_affine`` followed by ``gemm(..., cta_pair=4, block_n=splits)``."""
+    _prep(a)
+    if a_group_cols > 0:
+        assert a.dim() == 3 and a.is_contiguous() and a.shape[2] == a_group_cols
+        M, K = a.shape[1], a.shape[0] * a.shape[2]
+    else:
+        M, K = _rows(a), a.shape[-1]
+    N = packed.shape[0]
+    for t in (packed, scales, biases):
+        if not t.is_cuda:
+            raise _lib.LtxbError("ltxb ops need CUDA tensors; there is no CPU fallback on this path")
+    assert a.dtype == torch.bfloat16 and packed.dtype in (torch.uint32, torch.int32) and packed.dim() == 2 and packed.stride(1) == 1
+    assert scales.dtype == biases.dtype and scales.dtype in (torch.bfloat16, torch.float32)
+    assert scales.shape == biases.shape and scales.stride() == biases.stride() and scales.stride(1) == 1
+    if packed.shape[1] != K * bits // 32 or scales.shape != (N, K // group_size):
+        raise ValueError(f"quantised tensors {tuple(packed.shape)} / {tuple(scales.shape)} do not describe a {N}x{K} weight at "
+                         f"{bits} bits, group {group_size}")
+    assert _rows(out) == M and out.shape[-1] == N
+    assert out.dtype == (torch.float32 if mode in (_lib.EPI_BIAS_F32, _lib.EPI_RESID_GATE_F32) else torch.bfloat16)
+    epi = _epilogue(mode, N, bias, resid, gate, gate_table, gate_row_div, gate_row_index, const_w)
+    lda = _ld(a)
+    if a_group_cols > 0:
+        epi.a_group_cols, epi.a_group_stride, lda = a_group_cols, M * a_group_cols, a_group_cols
+    _call("ltxb_gemm_qw_bf16", 2.0 * M * N * K, a.data_ptr(), lda, packed.data_ptr(), packed.stride(0), scales.data_ptr(), biases.data_ptr(),
+          scales.stride(0), int(scales.dtype == torch.float32), group_size, bits, out.data_ptr(), _ld(out), M, N, K, C.byref(epi), splits,
+          _stream())
     return out
 
 

@@ -55,5 +55,15 @@ for M, N, K in shapes:
             row[name] = timed(lambda r: ops.gemm(a, ws[r], bias, out, mode=_lib.EPI_BIAS_BF16, **kw))
         except Exception as e:  # noqa: BLE001
             row[name] = str(e)[:60]
+    if os.environ.get("LTXB_BENCH_PACKED", "1") != "0":
+        for bits in (8, 4):  # packed weights (ltxb_gemm_qw_bf16): random words, unit scales — timing only
+            pk = [torch.randint(-2**31, 2**31 - 1, (N, K * bits // 32), device=dev, dtype=torch.int32) for _ in range(COPIES)]
+            sc = torch.full((N, K // 64), 0.01, device=dev, dtype=torch.bfloat16)
+            bi = torch.zeros(N, K // 64, device=dev, dtype=torch.bfloat16)
+            try:
+                row[f"packed_w{bits}"] = timed(lambda r: ops.gemm_qw(a, pk[r], sc, bi, 64, bits, bias, out, mode=_lib.EPI_BIAS_BF16, const_w=True))
+            except Exception as e:  # noqa: BLE001
+                row[f"packed_w{bits}"] = str(e)[:60]
+            del pk
     row["cublas"] = timed(lambda r: torch.matmul(a, ws[r].T, out=out))
     print(json.dumps(row), flush=True)

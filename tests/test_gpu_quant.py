@@ -46,6 +46,83 @@ def test_dequant_argument_errors():
         ops.dequant_affine(torch.zeros(8, 24, dtype=torch.int32, device=DEV), s, s, out, 64, 3)
 
 
+def _quantised(N, K, group_size, bits, aux, seed):
+    g = torch.Generator().manual_seed(seed)
+    w = (torch.randn(N, K, generator=g) / (K ** 0.5)).to(aux)
+    packed, s, b = O.affine_quantize(w, group_size, bits)
+    return torch.from_numpy(packed.view(np.int32)).to(DEV), s.to(DEV), b.to(DEV)
+
+
+# (M, N, K, group, bits): sequence-parallel shards, audio tokens, AdaLN rows, ragged N, two-MMA token ranges, one k-block
+QW_SHAPES = [(160, 4096, 4096, 64, 4), (160, 4096, 4096, 64, 8), (160, 12288, 4096, 128, 4), (160, 4096, 16384, 64, 4),
+             (68, 2048, 2048, 32, 4), (68, 2048, 2048, 32, 8), (1, 1024, 512, 64, 8), (200, 272, 1024, 128, 8),
+             (320, 4096, 4096, 64, 4), (500, 784, 256, 32, 4), (16, 256, 64, 64, 4)]
+
+
+@pytest.mark.parametrize("aux", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M_,N,K,group_size,bits", QW_SHAPES)
+def test_packed_weight_gemm_is_bit_identical_to_dequant_then_gemm(M_, N, K, group_size, bits, aux):
+    """ltxb_gemm_qw_bf16 (packed tiles from HBM, expanded in shared memory) == ltxb_dequant_affine_bf16 + the few-row bf16 GEMM
+    with the same k-range splits, bit for bit; and both agree with an fp32 matmul over the dequantised weight."""
+    packed, s, b = _quantised(N, K, group_size, bits, aux, 11 * bits + group_size + M_)
+    g = torch.Generator(device=DEV).manual_seed(M_ + N)
+    a = torch.randn(M_, K, device=DEV, generator=g).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g)
+    w = torch.empty(N, K, dtype=torch.bfloat16, device=DEV)
+    ops.dequant_affine(packed, s, b, w, group_size, bits)
+    ref = a.float() @ w.float().T + bias
+    for splits in (0, 1, 3):
+        want = torch.empty(M_, N, device=DEV, dtype=torch.float32)
+        ops.gemm(a, w, bias, want, mode=M._lib.EPI_BIAS_F32, cta_pair=4, block_n=splits)
+        got = torch.empty(M_, N, device=DEV, dtype=torch.float32)
+        ops.gemm_qw(a, packed, s, b, group_size, bits, bias, got, mode=M._lib.EPI_BIAS_F32, splits=splits)
+        again = torch.empty(M_, N, device=DEV, dtype=torch.float32)
+        ops.gemm_qw(a, packed, s, b, group_size, bits, bias, again, mode=M._lib.EPI_BIAS_F32, splits=splits, const_w=True)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), f"splits={splits}: max |diff| {float((got - want).abs().max())}"
+        assert torch.equal(got, again)
+        assert rel_l2(got, ref) < 2e-5
+
+
+@pytest.mark.parametrize("mode", ["bias_bf16", "gelu", "silu", "resid_gate"])
+def test_packed_weight_gemm_epilogues(mode):
+    E = M._lib
+    M_, N, K, group_size, bits = 160, 4096, 4096, 64, 4
+    packed, s, b = _quantised(N, K, group_size, bits, torch.bfloat16, 5)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    a = torch.randn(M_, K, device=DEV, generator=g).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g)
+    w = torch.empty(N, K, dtype=torch.bfloat16, device=DEV)
+    ops.dequant_affine(packed, s, b, w, group_size, bits)
+    if mode == "resid_gate":
+        resid = torch.randn(M_, N, device=DEV, generator=g)
+        gate = torch.randn(2, N, device=DEV, generator=g)
+        table = torch.randn(N, device=DEV, generator=g)
+        want, got = resid.clone(), resid.clone()
+        ops.gemm(a, w, bias, want, mode=E.EPI_RESID_GATE_F32, resid=want, gate=gate, gate_table=table, gate_row_div=80, cta_pair=4)
+        ops.gemm_qw(a, packed, s, b, group_size, bits, bias, got, mode=E.EPI_RESID_GATE_F32, resid=got, gate=gate, gate_table=table, gate_row_div=80)
+    else:
+        m = {"bias_bf16": E.EPI_BIAS_BF16, "gelu": E.EPI_GELU_BF16, "silu": E.EPI_SILU_BF16}[mode]
+        want = torch.empty(M_, N, device=DEV, dtype=torch.bfloat16)
+        got = torch.empty_like(want)
+        ops.gemm(a, w, bias, want, mode=m, cta_pair=4)
+        ops.gemm_qw(a, packed, s, b, group_size, bits, bias, got, mode=m)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+
+
+def test_packed_weight_gemm_argument_errors():
+    packed, s, b = _quantised(256, 512, 64, 4, torch.bfloat16, 3)
+    a = torch.zeros(600, 512, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(M.LtxbError, match="few-row"):
+        ops.gemm_qw(a, packed, s, b, 64, 4, None, torch.empty(600, 256, dtype=torch.bfloat16, device=DEV))
+    p2, s2, b2 = _quantised(256, 512, 64, 2, torch.bfloat16, 3)
+    with pytest.raises(M.LtxbError, match="bits"):
+        ops.gemm_qw(a[:8], p2, s2, b2, 64, 2, None, torch.empty(8, 256, dtype=torch.bfloat16, device=DEV))
+    with pytest.raises(ValueError):
+        ops.gemm_qw(a[:8], packed, s, b, 64, 8, None, torch.empty(8, 256, dtype=torch.bfloat16, device=DEV))
+
+
 @pytest.mark.parametrize("variant", sorted(QF.VARIANTS))
 def test_from_pretrained_quantised_checkpoint(golden, tmp_path, variant):
     g = golden("quant")
@@ -70,6 +147,17 @@ def test_from_pretrained_quantised_checkpoint(golden, tmp_path, variant):
     model2 = M.LTXModel.from_pretrained(None, product_config(cfg), strict=True, weights_override=in_memory, device=DEV)
     got2, _ = model2(video=to_dev(QF.inputs(variant)), audio=None)
     assert torch.equal(got2, got)
+    # keep_packed: few-row products stream the packed words (ltxb_gemm_qw_bf16) — same bits as the expanded path
+    from mlx_video_b200.packed import REGISTRY
+
+    model3 = M.LTXModel.from_pretrained(path, product_config(cfg), strict=True, device=DEV, keep_packed=True)
+    assert 0 < len(REGISTRY) <= n_q  # q | k | v of one fused matrix merge into one entry
+    launches = M._lib.lib.ltxb_kernel_launches()
+    got3, _ = model3(video=to_dev(QF.inputs(variant)), audio=None)
+    torch.cuda.synchronize()
+    assert torch.equal(got3, got), f"packed-weight path differs: {rel_l2(got3.float(), got.float()):.3e}"
+    assert M._lib.lib.ltxb_kernel_launches() > launches
+    REGISTRY.clear()
     # LoRA on top: the reference attaches runtime adapters to a quantised model (lora.py:219-275); here the same call
     # merges into the expanded weights — compared with the velocity the reference's adapters produced
     spec = lora.LoraSpec(QF.write_lora(variant, tmp_path), QF.LORA_STRENGTH)
