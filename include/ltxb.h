@@ -104,14 +104,14 @@ int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void*
                    int32_t N, int32_t K, const ltxb_epilogue* epi, int32_t block_n, int32_t cta_pair,
                    void* stream);
 
-/* K1 over MLX affine-quantised weights, for FEW rows (M <= 512) — nn.QuantizedLinear on the DiT path (ltx.py:641-725 loads
+/* K1 over MLX affine-quantised weights, for FEW rows (M <= 256) — nn.QuantizedLinear on the DiT path (ltx.py:641-725 loads
  * such checkpoints; mx.quantized_matmul):  acc[m,n] = sum_k A[m,k] * bf16(scales[n, k/G] * q[n,k] + biases[n, k/G]).
  * Wq: uint32 [N, ldq], 32/bits levels per word, lowest bits first (MLX packing); scales / biases [N, lds], bf16 or f32
  * (aux_f32); G = group_size (32, 64, 128); bits 4 or 8.  The packed tiles are what travels from HBM (a quarter / half of
- * the bf16 bytes — at few rows the weight stream bounds the GEMM) and are expanded in shared memory with the arithmetic
- * of ltxb_dequant_affine_bf16, so the result is bit-identical to ltxb_dequant_affine_bf16 followed by ltxb_gemm_bf16
+ * the bf16 bytes — at few rows the weight stream bounds the GEMM) and are expanded on the SM, into tensor memory, with the
+ * arithmetic of ltxb_dequant_affine_bf16, so the result is bit-identical to ltxb_dequant_affine_bf16 followed by ltxb_gemm_bf16
  * (cta_pair 4, same splits).  Same epilogues as ltxb_gemm_bf16; splits = k-range pieces per weight tile, 0 = choose.
- * More than 512 rows: LTXB_ERR_UNSUPPORTED (expand the weights once and call ltxb_gemm_bf16 — that regime is tensor-bound). */
+ * More than 256 rows: LTXB_ERR_UNSUPPORTED (expand the weights once and call ltxb_gemm_bf16 — that regime is tensor-bound). */
 int ltxb_gemm_qw_bf16(const void* A, int64_t lda, const uint32_t* Wq, int64_t ldq, const void* scales, const void* biases,
                       int64_t lds, int32_t aux_f32, int32_t group_size, int32_t bits, void* out, int64_t ldo, int32_t M,
                       int32_t N, int32_t K, const ltxb_epilogue* epi, int32_t splits, void* stream);

@@ -25,6 +25,7 @@
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 
 namespace ltxb {
@@ -62,6 +63,7 @@ struct WsParams {
   long long lds;
   int group;    // columns per (scale, bias) pair: 32, 64 or 128
   int aux_f32;  // scales / biases are f32 (else bf16)
+  uint32_t magic;  // 0x4B000000 (bits of 2^23): see the expanding warps
   int const_w;      // LTXB_GEMM_CONST_W: the first stages' weight tiles are requested before the PDL wait
   int out_tma;      // 0: per-thread global stores; 1: output chunks staged in shared memory, written by TMA; 2: staged, TMA add
                     // into `out` (RESID_GATE with out == resid: out += (acc + bias) * g, one add per element)
@@ -78,14 +80,21 @@ __device__ __forceinline__ long long ws_globaltimer() {
   return t;
 }
 #define WS_DBG(bit) ((p.debug & (bit)) != 0)
+// role profiling (debug & 64): cycles a role's lane 0 spent in a barrier wait, accumulated per role, printed by CTA 0
+#define WS_TIMED_WAIT(acc, call)            \
+  do {                                      \
+    const long long t0__ = clock64();       \
+    call;                                   \
+    (acc) += clock64() - t0__;              \
+  } while (0)
 #else
+#define WS_TIMED_WAIT(acc, call) call
 #define WS_DBG(bit) false
 #endif
 
 struct WsSmemHeader {
   uint64_t full[kWsMaxStages];
   uint64_t empty[kWsMaxStages];
-  uint64_t raw_full[kWsMaxStages];  // packed weights only: the raw tile of a stage has landed
   uint64_t tmem_full;
   uint32_t tmem_base;
 };
@@ -186,11 +195,186 @@ __device__ __forceinline__ void ws_stage_chunk(const WsParams& p, const float* a
   }
 }
 
-// kWBits = 16: W is bf16 and lands in the MMA's swizzled layout by TMA.  kWBits = 4 / 8: W is MLX affine-quantised; TMA
-// brings the PACKED tile (4 / 8 KB instead of 16 KB per k-block — the weight stream is what bounds this kernel) and the
-// eight epilogue warps, idle during the main loop, expand it to bf16 in shared memory in exactly the arithmetic of
-// ltxb_dequant_affine_bf16 (so the result is bit-identical to dequantise-then-GEMM) before the MMA reads it.
-template <int kEpi, int kWBits>
+// The epilogue shared by the bf16 and the packed-weight kernels (warps 2..9 of a CTA): accumulator [128 weight rows (lanes)]
+// [m_pad tokens (columns)] at `tmem_acc` -> reduce-scatter over the k-range splits -> fused epilogue -> global memory.
+// `stage_area`: the operand stages, idle once the accumulator is complete, reused for the TMA output tiles.
+template <int kEpi>
+__device__ __forceinline__ void ws_epilogue(const WsParams& p, const CUtensorMap* tmap_out, uint64_t* tmem_full, uint8_t* stage_area,
+                                            uint32_t stage_area_bytes, uint32_t tmem_acc, int tile, int split, uint32_t cta_rank,
+                                            int warp, int lane, long long* dbg) {
+  // ===================== epilogue: thread = output column, walks the tokens =====================
+  // Eight warps, two per TMEM lane quarter: the epilogue is a long run of per-token address / convert / store
+  // instructions per thread, so it is paced by how many warps the four schedulers can interleave.
+  const int quarter = warp & 3;          // TMEM lanes [32 * quarter, +32) belong to this warp
+  const int half = (warp - 2) >> 2;      // which half of the token chunks this warp walks
+  const int lane_row = quarter * 32 + lane;
+  const long long n = static_cast<long long>(tile) * (2 * kWsTileRows) + cta_rank * kWsTileRows + lane_row;
+  const bool n_ok = n < p.N;
+  const float bias_n = (p.bias != nullptr && n_ok) ? __ldg(p.bias + n) : 0.f;
+  const float table_n = (p.gate_table != nullptr && n_ok) ? __ldg(p.gate_table + n) : 0.f;
+  const bool epi_leader = (warp == 2 && lane == 0);
+  const int chunks = p.m_pad / kWsChunk;
+  const uint32_t t_row = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
+  // ---- output staging (p.out_tma): the four warps of a half fill chunk tiles in the (now idle) operand stages, one
+  // thread hands them to the TMA.  A round = as many consecutive chunks as the half's share of the stages holds.
+  constexpr int kEsize = (kEpi == LTXB_EPI_BIAS_F32 || kEpi == LTXB_EPI_RESID_GATE_F32) ? 4 : 2;
+  constexpr int kChunkBytes = kWsChunk * kWsTileRows * kEsize;
+  const uint32_t half_bytes = (stage_area_bytes / 2) & ~1023u;
+  uint8_t* half_stage = stage_area + half * half_bytes;
+  const int stage_cap = static_cast<int>(half_bytes / kChunkBytes) & ~1;
+  const bool staged = p.out_tma != 0;
+  const bool half_issuer = (((warp - 2) & 3) == 0) && lane == 0;
+  const int n0_cta = tile * (2 * kWsTileRows) + static_cast<int>(cta_rank) * kWsTileRows;
+  int staged_k = 0, staged_c0 = 0;
+  auto half_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory"); };
+  auto flush = [&](bool last) {  // warp-uniform and identical in the four warps of the half
+    if (staged_k == 0) return;
+    fence_proxy_async_smem();
+    half_bar();
+    if (half_issuer) {
+      for (int i = 0; i < staged_k; ++i) {
+        if (p.out_tma == 2) tma_reduce_add_2d(tmap_out, half_stage + i * kChunkBytes, n0_cta, (staged_c0 + i) * kWsChunk);
+        else tma_store_2d(tmap_out, half_stage + i * kChunkBytes, n0_cta, (staged_c0 + i) * kWsChunk);
+      }
+      tma_store_commit();
+      if (!last) tma_store_wait_read();
+    }
+    if (!last) half_bar();
+    staged_k = 0;
+  };
+  auto emit = [&](const float* vals, int c) {  // chunk c: consecutive within a round
+    if (!staged) {
+      if (n_ok) ws_finish_chunk<kEpi>(p, vals, c * kWsChunk, n, bias_n, table_n);
+      return;
+    }
+    if (staged_k == 0) staged_c0 = c;
+    ws_stage_chunk<kEpi>(p, vals, c * kWsChunk, n, n_ok, bias_n, table_n, half_stage + staged_k * kChunkBytes + lane_row * kEsize);
+    if (++staged_k == stage_cap) flush(false);
+  };
+  mbar_wait(tmem_full, 0);
+  tc_fence_after_sync();
+#ifdef LTXB_WS_DEBUG
+  dbg[0] = ws_globaltimer();
+#endif
+  if (WS_DBG(2)) {
+  } else if (p.splits == 1) {
+    const int groups = chunks / 2;  // 16-token groups (m_pad is a multiple of 16)
+    const int g0 = half == 0 ? 0 : (groups + 1) / 2, g1 = half == 0 ? (groups + 1) / 2 : groups;
+    for (int g = g0; g < g1; ++g) {
+      uint32_t r[16];
+      tmem_ld_x16(t_row + g * 16, r);
+      tmem_wait_ld();
+      emit(reinterpret_cast<const float*>(r), 2 * g);
+      emit(reinterpret_cast<const float*>(r) + kWsChunk, 2 * g + 1);
+    }
+    flush(true);
+  } else {
+    // ---- reduce-scatter over the `splits` pairs of this weight tile: split s owns chunks [own0, own1)
+    const int own0 = (chunks * split) / p.splits, own1 = (chunks * (split + 1)) / p.splits;
+    const size_t slot_f4 = static_cast<size_t>(p.m_pad / 4) * kWsTileRows;  // float4 per CTA slot
+    float4* my_slot = reinterpret_cast<float4*>(p.partials) + static_cast<size_t>(blockIdx.x) * slot_f4 + lane_row;
+    for (int c = 2 * half; c < chunks; c += 4) {  // 16-token groups, alternating between the two warps of a quarter
+      if (c >= own0 && c + 2 <= own1) continue;
+      uint32_t r[16];
+      tmem_ld_x16(t_row + c * kWsChunk, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cc = c + h;
+        if (cc >= own0 && cc < own1) continue;
+        // slot layout [chunk][half 0..1][128 lanes] float4: a warp's 32 lanes touch 512 contiguous bytes
+        __stcg(my_slot + (cc * 2 + 0) * kWsTileRows, make_float4(__uint_as_float(r[8 * h]), __uint_as_float(r[8 * h + 1]), __uint_as_float(r[8 * h + 2]), __uint_as_float(r[8 * h + 3])));
+        __stcg(my_slot + (cc * 2 + 1) * kWsTileRows, make_float4(__uint_as_float(r[8 * h + 4]), __uint_as_float(r[8 * h + 5]), __uint_as_float(r[8 * h + 6]), __uint_as_float(r[8 * h + 7])));
+      }
+    }
+    // release / acquire through the leader: the CTA barrier orders every warp's parked chunks before the leader's fence
+    // (cumulativity), and the readers' loads after its acquire
+    ws_epilogue_bar();
+    int* arrive = p.counters + tile * 2 + static_cast<int>(cta_rank);
+    if (epi_leader) {
+      red_release_gpu_add(arrive, 1);
+      const long long t0 = clock64();
+      while (ld_acquire_gpu(arrive) < p.splits) {
+        if (clock64() - t0 > LTXB_WATCHDOG_CYCLES) {
+          printf("ltxb: small-M split-K watchdog: tile %d split %d sees %d of %d arrivals\n", tile, split, ld_acquire_gpu(arrive), p.splits);
+          __trap();
+        }
+      }
+    }
+    ws_epilogue_bar();
+#ifdef LTXB_WS_DEBUG
+    if (epi_leader) dbg[1] = ws_globaltimer();
+#endif
+    const float4* tile_slots = reinterpret_cast<const float4*>(p.partials) + (static_cast<size_t>(tile) * p.splits * 2 + cta_rank) * slot_f4 + lane_row;
+    const int mid = own0 + (own1 - own0 + 1) / 2;
+    const int c_begin = half == 0 ? own0 : mid, c_end = half == 0 ? mid : own1;
+    // two chunks per pass, the parts of two other splits loaded together; parts are added in split order with the own
+    // accumulator at its own position, so the sum does not depend on arrival order
+    for (int c = c_begin; c < c_end; c += 2) {
+      const bool two = (c + 1 < c_end);
+      uint32_t r[2][8];
+      tmem_ld_x8(t_row + c * kWsChunk, r[0]);
+      if (two) tmem_ld_x8(t_row + (c + 1) * kWsChunk, r[1]);
+      float v[2][kWsChunk];
+#pragma unroll
+      for (int i = 0; i < kWsChunk; ++i) v[0][i] = 0.f, v[1][i] = 0.f;
+      bool own_pending = true;
+      int o = 0;
+      while (o < p.splits || own_pending) {
+        // next two OTHER splits in order
+        int oa = o;
+        if (oa == split) ++oa;
+        int ob = oa + 1;
+        if (ob == split) ++ob;
+        const bool has_a = oa < p.splits, has_b = ob < p.splits;
+        float4 ld[2][2][2];
+        if (has_a) {
+          const float4* src = tile_slots + static_cast<size_t>(oa) * 2 * slot_f4 + (c * 2) * kWsTileRows;
+          ld[0][0][0] = __ldcg(src), ld[0][0][1] = __ldcg(src + kWsTileRows);
+          if (two) ld[0][1][0] = __ldcg(src + 2 * kWsTileRows), ld[0][1][1] = __ldcg(src + 3 * kWsTileRows);
+        }
+        if (has_b) {
+          const float4* src = tile_slots + static_cast<size_t>(ob) * 2 * slot_f4 + (c * 2) * kWsTileRows;
+          ld[1][0][0] = __ldcg(src), ld[1][0][1] = __ldcg(src + kWsTileRows);
+          if (two) ld[1][1][0] = __ldcg(src + 2 * kWsTileRows), ld[1][1][1] = __ldcg(src + 3 * kWsTileRows);
+        }
+        auto add_own = [&]() {
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < kWsChunk; ++i) v[0][i] += __uint_as_float(r[0][i]), v[1][i] += two ? __uint_as_float(r[1][i]) : 0.f;
+          own_pending = false;
+        };
+        auto add_part = [&](int b) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (q == 1 && !two) break;
+            v[q][0] += ld[b][q][0].x, v[q][1] += ld[b][q][0].y, v[q][2] += ld[b][q][0].z, v[q][3] += ld[b][q][0].w;
+            v[q][4] += ld[b][q][1].x, v[q][5] += ld[b][q][1].y, v[q][6] += ld[b][q][1].z, v[q][7] += ld[b][q][1].w;
+          }
+        };
+        if (own_pending && (!has_a || split < oa)) add_own();
+        if (has_a) add_part(0);
+        if (own_pending && (!has_b || split < ob)) add_own();
+        if (has_b) add_part(1);
+        o = ob + 1;
+      }
+      emit(v[0], c);
+      if (two) emit(v[1], c + 1);
+    }
+    flush(true);
+    // the last pair to leave re-arms the counters for the next launch
+    ws_epilogue_bar();
+    if (epi_leader) {
+      int* depart = p.counters + kWsDepartOffset + tile * 2 + static_cast<int>(cta_rank);
+      if (atomicAdd(depart, 1) == p.splits - 1) {
+        *arrive = 0;
+        *depart = 0;
+      }
+    }
+  }
+}
+
+template <int kEpi>
 __global__ void __launch_bounds__(kWsThreads, 2)
 gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_out, const WsParams p) {
@@ -211,12 +395,8 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   const int kb1 = (num_kb * (split + 1)) / p.splits;
   const int mma_n = p.m_pad / p.n_mma;  // tokens per MMA
   const int box_rows = mma_n / 2;       // token rows this CTA stages per MMA
-  constexpr bool kPacked = (kWBits != 16);
-  constexpr uint32_t kRawRowBytes = kPacked ? kWsBlockK * kWBits / 8 : 0;  // packed bytes of one weight row per k-block
-  constexpr uint32_t kRawBytes = kWsTileRows * kRawRowBytes;
   const uint32_t x_box_bytes = box_rows * kWsBlockK * 2;
-  const uint32_t raw_off = kWsWBytes + p.n_mma * x_box_bytes;  // stage = [W bf16][token boxes][raw packed W]
-  const uint32_t stage_bytes = raw_off + kRawBytes;
+  const uint32_t stage_bytes = kWsWBytes + p.n_mma * x_box_bytes;  // stage = [W tile][token boxes]
   const int num_stages = p.num_stages;
 
   if (warp == 0 && lane == 0) {
@@ -227,9 +407,8 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < num_stages; ++s) {
-        mbar_init(&hdr->full[s], kPacked ? 1 + 2 * 8 : 1);  // packed: + the eight expanding warps of both CTAs
+        mbar_init(&hdr->full[s], 1);
         mbar_init(&hdr->empty[s], 1);
-        mbar_init(&hdr->raw_full[s], 1);
       }
       mbar_init(&hdr->tmem_full, 1);
       fence_mbar_init();
@@ -250,21 +429,15 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     prefetched = min(num_stages, kb1 - kb0);
     if (warp == 0 && lane == 0) {
       for (int s = 0; s < prefetched; ++s) {
-        uint8_t* st = tiles + static_cast<size_t>(s) * stage_bytes;
-        if constexpr (kPacked) {
-          mbar_arrive_expect_tx(&hdr->raw_full[s], kRawBytes);
-          tma_load_2d(st + raw_off, &tmap_w, &hdr->raw_full[s], (kb0 + s) * static_cast<int>(kRawRowBytes), n0_w);
-        } else {
-          if (is_leader) mbar_arrive_expect_tx(&hdr->full[s], stage_bytes * 2);
-          tma_load_2d_pair(st, &tmap_w, mapa_u32(smem_u32(&hdr->full[s]), 0), (kb0 + s) * kWsBlockK, n0_w);
-        }
+        if (is_leader) mbar_arrive_expect_tx(&hdr->full[s], stage_bytes * 2);
+        tma_load_2d_pair(tiles + static_cast<size_t>(s) * stage_bytes, &tmap_w, mapa_u32(smem_u32(&hdr->full[s]), 0), (kb0 + s) * kWsBlockK, n0_w);
       }
     }
   }
   pdl_wait();  // everything above overlapped the previous kernel's tail; activations / outputs are touched only below
+  long long dbg[2] = {0, 0};  // LTXB_WS_DEBUG builds: accumulator complete / split partners met
 #ifdef LTXB_WS_DEBUG
   const long long t_pdl = ws_globaltimer();
-  long long t_acc = t_pdl, t_met = 0;
 #endif
 
   if (warp == 0) {
@@ -279,16 +452,8 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         uint8_t* sx = sw + kWsWBytes;
         const int ka = kb * kWsBlockK;
         const uint32_t bar = mapa_u32(smem_u32(&hdr->full[stage]), 0);  // both CTAs report their bytes on the leader's barrier
-        if constexpr (kPacked) {
-          if (!w_done) {
-            mbar_arrive_expect_tx(&hdr->raw_full[stage], kRawBytes);
-            tma_load_2d(sw + raw_off, &tmap_w, &hdr->raw_full[stage], kb * static_cast<int>(kRawRowBytes), n0);
-          }
-          if (is_leader) mbar_arrive_expect_tx(&hdr->full[stage], p.n_mma * x_box_bytes * 2);
-        } else {
-          if (is_leader && !w_done) mbar_arrive_expect_tx(&hdr->full[stage], stage_bytes * 2);
-          if (!w_done) tma_load_2d_pair(sw, &tmap_w, bar, ka, n0);
-        }
+        if (is_leader && !w_done) mbar_arrive_expect_tx(&hdr->full[stage], stage_bytes * 2);
+        if (!w_done) tma_load_2d_pair(sw, &tmap_w, bar, ka, n0);
         for (int j = 0; j < p.n_mma; ++j) {
           const int row0 = j * mma_n + static_cast<int>(cta_rank) * box_rows;
           if (p.a_group_cols > 0) tma_load_3d_pair(sx + j * x_box_bytes, &tmap_x, bar, ka % p.a_group_cols, row0, ka / p.a_group_cols);
@@ -304,309 +469,45 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA): D[256 weight rows, tokens] += W_tile . X^T =====================
-    if (lane == 0 && is_leader) {
+    // The whole warp runs the loop (waits, fences) and one elected lane issues: control flow stays warp-uniform and the
+    // descriptors are two 32-bit words with compile-time k offsets — a lone `lane == 0` thread needed ~100 cycles per
+    // MMA (profiles/r2/attention_s64_notes.md), which at four MMAs per k-block would pace this kernel.
+    if (is_leader) {
+      const bool issuer = elect_one();
       const uint32_t idesc = make_idesc_bf16(2 * kWsTileRows, mma_n, 0, 0);
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B, descriptor version 1, 128-byte swizzle
+      const uint32_t tiles_lo = ((smem_u32(tiles) & 0x3FFFFu) >> 4) | (1u << 16);
       uint32_t stage = 0, phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&hdr->full[stage], phase);
         tc_fence_after_sync();
-        const uint32_t sa = smem_u32(tiles + static_cast<size_t>(stage) * stage_bytes);
-        const uint64_t wdesc = make_smem_desc_sw128(sa, 16, 1024);
-        for (int j = 0; j < p.n_mma; ++j) {
-          const uint64_t xdesc = make_smem_desc_sw128(sa + kWsWBytes + j * x_box_bytes, 16, 1024);
+        if (issuer) {
+          const uint32_t w_lo = tiles_lo + ((stage * stage_bytes) >> 4);
+          for (int j = 0; j < p.n_mma; ++j) {
+            const uint32_t x_lo = w_lo + ((kWsWBytes + j * x_box_bytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < kWsBlockK / 16; ++k)
-            umma_bf16_ss<2>(tmem_base + j * mma_n, wdesc + 2 * k, xdesc + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            for (int k = 0; k < kWsBlockK / 16; ++k)
+              umma_bf16_ss<2>(tmem_base + j * mma_n, desc_from_words(w_lo + 2 * k, kDescHi), desc_from_words(x_lo + 2 * k, kDescHi), idesc,
+                              (kb != kb0 || k != 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&hdr->empty[stage], 3);
         }
-        umma_commit_pair(&hdr->empty[stage], 3);
+        __syncwarp();
         if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
       }
-      umma_commit_pair(&hdr->tmem_full, 3);
+      if (issuer) umma_commit_pair(&hdr->tmem_full, 3);
+      __syncwarp();
     }
   } else {
-    if constexpr (kPacked) {
-      // ===================== packed weights: expand raw -> bf16 in the MMA's swizzled layout =====================
-      // thread = (weight row, half of the k-block): 32 levels -> 32 bf16 = four 16-byte chunks of the row's 128 bytes,
-      // chunk c stored at position c ^ (row % 8) (the 128-byte swizzle the TMA would have applied)
-      const int t = static_cast<int>(threadIdx.x) - 64;
-      const int row = t & (kWsTileRows - 1), khalf = t >> 7;
-      const long long row_abs = static_cast<long long>(n0_w) + row;
-      const bool row_ok = row_abs < p.N;
-      // (scale, bias) of this thread's 32 columns change every k-block (group 64) — and a load issued under a saturated HBM
-      // stream takes microseconds to come back — so they are fetched 16 bytes at a time (8 bf16 / 4 f32 groups of the row)
-      // one chunk AHEAD of the one in use: the wait lands on a load issued several k-blocks earlier
-      const int esz = p.aux_f32 ? 4 : 2;
-      const int chunk_groups = 16 / esz;
-      const int groups_per_row = p.K / p.group;
-      const bool chunked = (groups_per_row % chunk_groups == 0) && ((p.lds * esz) % 16 == 0) &&
-                           ((reinterpret_cast<uintptr_t>(p.scales) | reinterpret_cast<uintptr_t>(p.biases)) % 16 == 0);
-      const int group_shift = p.group == 32 ? 5 : (p.group == 64 ? 6 : 7);
-      auto group_of = [&](int kb) { return (kb * kWsBlockK + khalf * 32) >> group_shift; };
-      auto load_chunk = [&](int c, uint4& S, uint4& B) {
-        S = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0, 0);
-        if (!row_ok || c * chunk_groups >= groups_per_row) return;
-        const size_t off = (static_cast<size_t>(row_abs) * p.lds + static_cast<size_t>(c) * chunk_groups) * esz;
-        S = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.scales) + off));
-        B = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.biases) + off));
-      };
-      auto pick = [&](const uint4& V, int i) -> float {  // element i of a chunk without indexing registers dynamically
-        if (p.aux_f32) {
-          const uint32_t lo = (i & 1) ? V.y : V.x, hi = (i & 1) ? V.w : V.z;
-          return __uint_as_float((i & 2) ? hi : lo);
-        }
-        const uint32_t a = (i & 2) ? V.y : V.x, b = (i & 2) ? V.w : V.z;
-        const uint32_t wd = (i & 4) ? b : a;
-        return __uint_as_float((i & 1) ? (wd & 0xffff0000u) : (wd << 16));
-      };
-      auto load_scalar = [&](int kb, float& sc, float& bi) {  // layouts the 16-byte chunks do not fit
-        sc = 0.f, bi = 0.f;
-        if (!row_ok) return;
-        const long long a = row_abs * p.lds + group_of(kb);
-        if (p.aux_f32) {
-          sc = __ldg(static_cast<const float*>(p.scales) + a);
-          bi = __ldg(static_cast<const float*>(p.biases) + a);
-        } else {
-          sc = __bfloat162float(static_cast<const __nv_bfloat16*>(p.scales)[a]);
-          bi = __bfloat162float(static_cast<const __nv_bfloat16*>(p.biases)[a]);
-        }
-      };
-      const uint32_t tiles_u32 = smem_u32(tiles);
-      const uint32_t raw_thread_off = raw_off + row * kRawRowBytes + khalf * (kRawRowBytes / 2);
-      uint32_t dst_off[4];  // chunk c of the row's 128 bytes sits at position c ^ (row % 8): the TMA's 128-byte swizzle
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dst_off[j] = row * 128 + (((khalf * 4 + j) ^ (row & 7)) << 4);
-      uint32_t stage = 0, phase = 0;
-      uint4 s_cur, b_cur, s_next, b_next;
-      int cur_chunk = group_of(kb0) / chunk_groups;
-      if (chunked) {
-        load_chunk(cur_chunk, s_cur, b_cur);
-        load_chunk(cur_chunk + 1, s_next, b_next);
-      }
-      for (int kb = kb0; kb < kb1; ++kb) {
-        float sc, bi;
-        if (chunked) {
-          const int g = group_of(kb);
-          if (g / chunk_groups != cur_chunk) {
-            s_cur = s_next, b_cur = b_next;
-            ++cur_chunk;
-            load_chunk(cur_chunk + 1, s_next, b_next);
-          }
-          const int gi = g - cur_chunk * chunk_groups;
-          sc = pick(s_cur, gi), bi = pick(b_cur, gi);
-        } else {
-          load_scalar(kb, sc, bi);
-        }
-        mbar_wait(&hdr->raw_full[stage], phase);
-        const uint32_t st = tiles_u32 + stage * stage_bytes;  // shared-space addresses: LDS / STS, no generic-pointer arithmetic
-        uint32_t w[kWBits];  // 4-bit: 4 words (32 levels), 8-bit: 8 words
-        if (!WS_DBG(32)) {  // (timing experiment: hand the stage on without expanding it)
-        lds128(st + raw_thread_off, w[0], w[1], w[2], w[3]);
-        if constexpr (kWBits == 8) lds128(st + raw_thread_off + 16, w[4], w[5], w[6], w[7]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float v[8];
-          // level -> float through the 2^23 trick (bits 0x4B0000qq = 8388608 + q, exact), then scales * q + biases with
-          // the two roundings of ltxb_dequant_affine_bf16
-          if constexpr (kWBits == 4) {
-            const uint32_t lo = w[j] & 0x0F0F0F0Fu, hi = (w[j] >> 4) & 0x0F0F0F0Fu;  // even / odd levels, one per byte
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const uint32_t bits = __byte_perm((e & 1) ? hi : lo, 0x4B000000u, 0x7540u | (e >> 1));
-              v[e] = __fadd_rn(__fmul_rn(sc, __uint_as_float(bits) - 8388608.0f), bi);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const uint32_t bits = __byte_perm(w[2 * j + (e >> 2)], 0x4B000000u, 0x7540u | (e & 3));
-              v[e] = __fadd_rn(__fmul_rn(sc, __uint_as_float(bits) - 8388608.0f), bi);
-            }
-          }
-          sts128(st + dst_off[j], pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-        }
-        }
-        fence_proxy_async_smem();  // generic-proxy writes -> the (pair leader's) tensor core reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive_remote(&hdr->full[stage], 0);
-        if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
-      }
-    }
-    // ===================== epilogue: thread = output column, walks the tokens =====================
-    // Eight warps, two per TMEM lane quarter: the epilogue is a long run of per-token address / convert / store
-    // instructions per thread, so it is paced by how many warps the four schedulers can interleave.
-    const int quarter = warp & 3;          // TMEM lanes [32 * quarter, +32) belong to this warp
-    const int half = (warp - 2) >> 2;      // which half of the token chunks this warp walks
-    const int lane_row = quarter * 32 + lane;
-    const long long n = static_cast<long long>(tile) * (2 * kWsTileRows) + cta_rank * kWsTileRows + lane_row;
-    const bool n_ok = n < p.N;
-    const float bias_n = (p.bias != nullptr && n_ok) ? __ldg(p.bias + n) : 0.f;
-    const float table_n = (p.gate_table != nullptr && n_ok) ? __ldg(p.gate_table + n) : 0.f;
-    const bool epi_leader = (warp == 2 && lane == 0);
-    const int chunks = p.m_pad / kWsChunk;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    // ---- output staging (p.out_tma): the four warps of a half fill chunk tiles in the (now idle) operand stages, one
-    // thread hands them to the TMA.  A round = as many consecutive chunks as the half's share of the stages holds.
-    constexpr int kEsize = (kEpi == LTXB_EPI_BIAS_F32 || kEpi == LTXB_EPI_RESID_GATE_F32) ? 4 : 2;
-    constexpr int kChunkBytes = kWsChunk * kWsTileRows * kEsize;
-    const uint32_t half_bytes = ((static_cast<uint32_t>(num_stages) * stage_bytes) / 2) & ~1023u;
-    uint8_t* half_stage = tiles + half * half_bytes;
-    const int stage_cap = static_cast<int>(half_bytes / kChunkBytes) & ~1;
-    const bool staged = p.out_tma != 0;
-    const bool half_issuer = (((warp - 2) & 3) == 0) && lane == 0;
-    const int n0_cta = tile * (2 * kWsTileRows) + static_cast<int>(cta_rank) * kWsTileRows;
-    int staged_k = 0, staged_c0 = 0;
-    auto half_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory"); };
-    auto flush = [&](bool last) {  // warp-uniform and identical in the four warps of the half
-      if (staged_k == 0) return;
-      fence_proxy_async_smem();
-      half_bar();
-      if (half_issuer) {
-        for (int i = 0; i < staged_k; ++i) {
-          if (p.out_tma == 2) tma_reduce_add_2d(&tmap_out, half_stage + i * kChunkBytes, n0_cta, (staged_c0 + i) * kWsChunk);
-          else tma_store_2d(&tmap_out, half_stage + i * kChunkBytes, n0_cta, (staged_c0 + i) * kWsChunk);
-        }
-        tma_store_commit();
-        if (!last) tma_store_wait_read();
-      }
-      if (!last) half_bar();
-      staged_k = 0;
-    };
-    auto emit = [&](const float* vals, int c) {  // chunk c: consecutive within a round
-      if (!staged) {
-        if (n_ok) ws_finish_chunk<kEpi>(p, vals, c * kWsChunk, n, bias_n, table_n);
-        return;
-      }
-      if (staged_k == 0) staged_c0 = c;
-      ws_stage_chunk<kEpi>(p, vals, c * kWsChunk, n, n_ok, bias_n, table_n, half_stage + staged_k * kChunkBytes + lane_row * kEsize);
-      if (++staged_k == stage_cap) flush(false);
-    };
-    mbar_wait(&hdr->tmem_full, 0);
-    tc_fence_after_sync();
-#ifdef LTXB_WS_DEBUG
-    t_acc = ws_globaltimer();
-#endif
-    if (WS_DBG(2)) {
-    } else if (p.splits == 1) {
-      const int groups = chunks / 2;  // 16-token groups (m_pad is a multiple of 16)
-      const int g0 = half == 0 ? 0 : (groups + 1) / 2, g1 = half == 0 ? (groups + 1) / 2 : groups;
-      for (int g = g0; g < g1; ++g) {
-        uint32_t r[16];
-        tmem_ld_x16(t_row + g * 16, r);
-        tmem_wait_ld();
-        emit(reinterpret_cast<const float*>(r), 2 * g);
-        emit(reinterpret_cast<const float*>(r) + kWsChunk, 2 * g + 1);
-      }
-      flush(true);
-    } else {
-      // ---- reduce-scatter over the `splits` pairs of this weight tile: split s owns chunks [own0, own1)
-      const int own0 = (chunks * split) / p.splits, own1 = (chunks * (split + 1)) / p.splits;
-      const size_t slot_f4 = static_cast<size_t>(p.m_pad / 4) * kWsTileRows;  // float4 per CTA slot
-      float4* my_slot = reinterpret_cast<float4*>(p.partials) + static_cast<size_t>(blockIdx.x) * slot_f4 + lane_row;
-      for (int c = 2 * half; c < chunks; c += 4) {  // 16-token groups, alternating between the two warps of a quarter
-        if (c >= own0 && c + 2 <= own1) continue;
-        uint32_t r[16];
-        tmem_ld_x16(t_row + c * kWsChunk, r);
-        tmem_wait_ld();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int cc = c + h;
-          if (cc >= own0 && cc < own1) continue;
-          // slot layout [chunk][half 0..1][128 lanes] float4: a warp's 32 lanes touch 512 contiguous bytes
-          __stcg(my_slot + (cc * 2 + 0) * kWsTileRows, make_float4(__uint_as_float(r[8 * h]), __uint_as_float(r[8 * h + 1]), __uint_as_float(r[8 * h + 2]), __uint_as_float(r[8 * h + 3])));
-          __stcg(my_slot + (cc * 2 + 1) * kWsTileRows, make_float4(__uint_as_float(r[8 * h + 4]), __uint_as_float(r[8 * h + 5]), __uint_as_float(r[8 * h + 6]), __uint_as_float(r[8 * h + 7])));
-        }
-      }
-      // release / acquire through the leader: the CTA barrier orders every warp's parked chunks before the leader's fence
-      // (cumulativity), and the readers' loads after its acquire
-      ws_epilogue_bar();
-      int* arrive = p.counters + tile * 2 + static_cast<int>(cta_rank);
-      if (epi_leader) {
-        red_release_gpu_add(arrive, 1);
-        const long long t0 = clock64();
-        while (ld_acquire_gpu(arrive) < p.splits) {
-          if (clock64() - t0 > LTXB_WATCHDOG_CYCLES) {
-            printf("ltxb: small-M split-K watchdog: tile %d split %d sees %d of %d arrivals\n", tile, split, ld_acquire_gpu(arrive), p.splits);
-            __trap();
-          }
-        }
-      }
-      ws_epilogue_bar();
-#ifdef LTXB_WS_DEBUG
-      if (epi_leader) t_met = ws_globaltimer();
-#endif
-      const float4* tile_slots = reinterpret_cast<const float4*>(p.partials) + (static_cast<size_t>(tile) * p.splits * 2 + cta_rank) * slot_f4 + lane_row;
-      const int mid = own0 + (own1 - own0 + 1) / 2;
-      const int c_begin = half == 0 ? own0 : mid, c_end = half == 0 ? mid : own1;
-      // two chunks per pass, the parts of two other splits loaded together; parts are added in split order with the own
-      // accumulator at its own position, so the sum does not depend on arrival order
-      for (int c = c_begin; c < c_end; c += 2) {
-        const bool two = (c + 1 < c_end);
-        uint32_t r[2][8];
-        tmem_ld_x8(t_row + c * kWsChunk, r[0]);
-        if (two) tmem_ld_x8(t_row + (c + 1) * kWsChunk, r[1]);
-        float v[2][kWsChunk];
-#pragma unroll
-        for (int i = 0; i < kWsChunk; ++i) v[0][i] = 0.f, v[1][i] = 0.f;
-        bool own_pending = true;
-        int o = 0;
-        while (o < p.splits || own_pending) {
-          // next two OTHER splits in order
-          int oa = o;
-          if (oa == split) ++oa;
-          int ob = oa + 1;
-          if (ob == split) ++ob;
-          const bool has_a = oa < p.splits, has_b = ob < p.splits;
-          float4 ld[2][2][2];
-          if (has_a) {
-            const float4* src = tile_slots + static_cast<size_t>(oa) * 2 * slot_f4 + (c * 2) * kWsTileRows;
-            ld[0][0][0] = __ldcg(src), ld[0][0][1] = __ldcg(src + kWsTileRows);
-            if (two) ld[0][1][0] = __ldcg(src + 2 * kWsTileRows), ld[0][1][1] = __ldcg(src + 3 * kWsTileRows);
-          }
-          if (has_b) {
-            const float4* src = tile_slots + static_cast<size_t>(ob) * 2 * slot_f4 + (c * 2) * kWsTileRows;
-            ld[1][0][0] = __ldcg(src), ld[1][0][1] = __ldcg(src + kWsTileRows);
-            if (two) ld[1][1][0] = __ldcg(src + 2 * kWsTileRows), ld[1][1][1] = __ldcg(src + 3 * kWsTileRows);
-          }
-          auto add_own = [&]() {
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < kWsChunk; ++i) v[0][i] += __uint_as_float(r[0][i]), v[1][i] += two ? __uint_as_float(r[1][i]) : 0.f;
-            own_pending = false;
-          };
-          auto add_part = [&](int b) {
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              if (q == 1 && !two) break;
-              v[q][0] += ld[b][q][0].x, v[q][1] += ld[b][q][0].y, v[q][2] += ld[b][q][0].z, v[q][3] += ld[b][q][0].w;
-              v[q][4] += ld[b][q][1].x, v[q][5] += ld[b][q][1].y, v[q][6] += ld[b][q][1].z, v[q][7] += ld[b][q][1].w;
-            }
-          };
-          if (own_pending && (!has_a || split < oa)) add_own();
-          if (has_a) add_part(0);
-          if (own_pending && (!has_b || split < ob)) add_own();
-          if (has_b) add_part(1);
-          o = ob + 1;
-        }
-        emit(v[0], c);
-        if (two) emit(v[1], c + 1);
-      }
-      flush(true);
-      // the last pair to leave re-arms the counters for the next launch
-      ws_epilogue_bar();
-      if (epi_leader) {
-        int* depart = p.counters + kWsDepartOffset + tile * 2 + static_cast<int>(cta_rank);
-        if (atomicAdd(depart, 1) == p.splits - 1) {
-          *arrive = 0;
-          *depart = 0;
-        }
-      }
-    }
+    ws_epilogue<kEpi>(p, &tmap_out, &hdr->tmem_full, tiles, static_cast<uint32_t>(num_stages) * stage_bytes, tmem_base, tile, split,
+                      cta_rank, warp, lane, dbg);
   }
 
   if (p.out_tma != 0 && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) tma_store_wait_read();  // the staged tiles stay valid until read
 #ifdef LTXB_WS_DEBUG
   if (WS_DBG(8) && threadIdx.x == 64 && p.trace != nullptr) {  // warp 2 lane 0 = the epilogue leader
     long long* t = p.trace + static_cast<size_t>(blockIdx.x) * 4;
-    t[0] = t_pdl, t[1] = t_acc, t[2] = t_met, t[3] = ws_globaltimer();
+    t[0] = t_pdl, t[1] = dbg[0], t[2] = dbg[1], t[3] = ws_globaltimer();
   }
 #endif
   // teardown: nobody may leave while the peer can still read this CTA's shared memory / TMEM
@@ -620,15 +521,345 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
+// Packed weights (MLX affine groups, 4 / 8 bits): the same GEMM with W streamed PACKED from HBM (a quarter / half of the
+// bf16 bytes — at few rows the weight stream is what bounds the product).
+//   * a stage holds the packed tile (4 / 8 KB) and this CTA's half of the token rows (10 KB at 160 tokens): up to 20
+//     stages in flight per SM.  That depth is the point: with a bf16 copy of the tile in every stage (first cut) only 7
+//     stages fit, and at a ~3 us round trip per stage the pipeline, not HBM, paced the kernel (measured: 49 us against the
+//     bf16 kernel's 29 us at 160 x 16384 x 4096, profiles/r2/gemm_small_m.md);
+//   * the eight epilogue warps, idle during the main loop, expand a tile in the arithmetic of ltxb_dequant_affine_bf16
+//     (bit-identical to dequantise-then-GEMM) and write it with tcgen05.st into a ring of A-operand slots in TENSOR MEMORY
+//     (one thread = one weight row = one TMEM lane: 32 columns per k-block, 8 slots behind the accumulator's 256 columns);
+//     the MMA reads A from TMEM (the form the attention kernel uses for P.V) and only the token rows from shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPkMaxSlots = 14;  // ring slots: as many as fit behind the accumulator (512 - m_pad columns, 32 each)
+constexpr int kPkSlotCols = kWsBlockK / 2;  // 64 bf16 of a weight row = 32 TMEM columns
+constexpr int kPkAccCols = 256;             // accumulator columns in front of the slot ring (m_pad <= 256)
+constexpr int kPkMaxStages = 20;
+struct PkSmemHeader {
+  uint64_t full[kPkMaxStages];      // (leader's) the token rows of both CTAs have landed
+  uint64_t raw_full[kPkMaxStages];  // this CTA's packed tile has landed
+  uint64_t empty[kPkMaxStages];     // the MMAs that read the stage have completed (both CTAs; the tile was expanded before them)
+  uint64_t a_full[kPkMaxSlots];     // (leader's) the expanding warps of both CTAs have filled the slot: 16 arrivals
+  uint64_t a_empty[kPkMaxSlots];    // the MMAs that read the slot have completed (both CTAs)
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+};
+static_assert(sizeof(PkSmemHeader) <= kWsHeader, "header overflow");
+
+template <int kEpi, int kWBits>
+__global__ void __launch_bounds__(kWsThreads, 1)
+gemm_small_m_packed_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                           const __grid_constant__ CUtensorMap tmap_out, const WsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  PkSmemHeader* hdr = reinterpret_cast<PkSmemHeader*>(smem);
+  uint8_t* tiles = smem + kWsHeader;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool is_leader = (cta_rank == 0);
+  const int pair_id = blockIdx.x >> 1;
+  const int tile = pair_id / p.splits;
+  const int split = pair_id - tile * p.splits;
+  const int num_kb = p.K / kWsBlockK;
+  const int kb0 = (num_kb * split) / p.splits;
+  const int kb1 = (num_kb * (split + 1)) / p.splits;
+  const int box_rows = p.m_pad / 2;  // token rows this CTA stages (one MMA: m_pad <= 256)
+  constexpr uint32_t kRawRowBytes = kWsBlockK * kWBits / 8;  // packed bytes of one weight row per k-block
+  constexpr uint32_t kRawBytes = kWsTileRows * kRawRowBytes;
+  const uint32_t x_bytes = box_rows * kWsBlockK * 2;
+  const uint32_t stage_bytes = x_bytes + kRawBytes;  // stage = [token rows (swizzled, 1024-aligned)][packed tile]
+  const int num_stages = p.num_stages;
+  const int n0_w = tile * (2 * kWsTileRows) + static_cast<int>(cta_rank) * kWsTileRows;
+  const uint32_t ring_col = (static_cast<uint32_t>(p.m_pad) + 31u) & ~31u;  // A-operand slots start behind the accumulator
+  const int num_slots = min(kPkMaxSlots, static_cast<int>((512u - ring_col) / kPkSlotCols));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    if (p.out_tma != 0) tma_prefetch_desc(&tmap_out);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < num_stages; ++s) {
+        mbar_init(&hdr->full[s], 1);
+        mbar_init(&hdr->raw_full[s], 1);
+        mbar_init(&hdr->empty[s], 1);
+      }
+      for (int s = 0; s < num_slots; ++s) {
+        mbar_init(&hdr->a_full[s], 2 * 8);
+        mbar_init(&hdr->a_empty[s], 1);
+      }
+      mbar_init(&hdr->tmem_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<2>(&hdr->tmem_base, 512);
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&hdr->tmem_base);
+  pdl_launch_dependents();
+  int prefetched = 0;
+  if (p.const_w) {  // packed tiles of weights no running kernel writes start streaming under the predecessor's tail
+    prefetched = min(num_stages, kb1 - kb0);
+    if (warp == 0 && lane == 0) {
+      for (int s = 0; s < prefetched; ++s) {
+        mbar_arrive_expect_tx(&hdr->raw_full[s], kRawBytes);
+        tma_load_2d(tiles + static_cast<size_t>(s) * stage_bytes + x_bytes, &tmap_w, &hdr->raw_full[s], (kb0 + s) * static_cast<int>(kRawRowBytes), n0_w);
+      }
+    }
+  }
+  pdl_wait();
+  long long dbg[2] = {0, 0};
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      long long w_empty = 0, t_loop = clock64();
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const bool w_done = (kb - kb0) < prefetched;
+        if (!w_done) WS_TIMED_WAIT(w_empty, mbar_wait(&hdr->empty[stage], phase ^ 1));
+        uint8_t* sx = tiles + static_cast<size_t>(stage) * stage_bytes;
+        const int ka = kb * kWsBlockK;
+        if (!w_done) {
+          mbar_arrive_expect_tx(&hdr->raw_full[stage], kRawBytes);
+          tma_load_2d(sx + x_bytes, &tmap_w, &hdr->raw_full[stage], kb * static_cast<int>(kRawRowBytes), n0_w);
+        }
+        if (is_leader) mbar_arrive_expect_tx(&hdr->full[stage], x_bytes * 2);  // both CTAs report on the leader's barrier
+        const uint32_t bar = mapa_u32(smem_u32(&hdr->full[stage]), 0);
+        const int row0 = static_cast<int>(cta_rank) * box_rows;
+        if (p.a_group_cols > 0) tma_load_3d_pair(sx, &tmap_x, bar, ka % p.a_group_cols, row0, ka / p.a_group_cols);
+        else tma_load_2d_pair(sx, &tmap_x, bar, ka, row0);
+        if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
+      }
+#ifdef LTXB_WS_DEBUG
+      if (WS_DBG(64) && blockIdx.x == 0) printf("ws roles: producer loop %lld cycles, %lld waiting for empty stages (%d k-blocks)\n", clock64() - t_loop, w_empty, kb1 - kb0);
+#endif
+      (void)t_loop, (void)w_empty;
+      for (int s = 0; s < num_stages; ++s) {  // no CTA retires while commit arrivals for its barriers are in flight
+        mbar_wait(&hdr->empty[stage], phase ^ 1);
+        if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader): D += A (TMEM slot) . X^T (shared memory) =====================
+    if (is_leader) {  // warp-uniform loop, one elected lane issues (see the bf16 kernel)
+      const bool issuer = elect_one();
+      const uint32_t idesc = make_idesc_bf16(2 * kWsTileRows, p.m_pad, 0, 0);
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t tiles_lo = ((smem_u32(tiles) & 0x3FFFFu) >> 4) | (1u << 16);
+      uint32_t stage = 0, phase = 0, slot = 0, sphase = 0;
+      long long w_full = 0, w_afull = 0, t_loop = clock64();
+      for (int kb = kb0; kb < kb1; ++kb) {
+        WS_TIMED_WAIT(w_full, mbar_wait(&hdr->full[stage], phase));
+        WS_TIMED_WAIT(w_afull, mbar_wait(&hdr->a_full[slot], sphase));
+        tc_fence_after_sync();
+        if (issuer) {
+          const uint32_t x_lo = tiles_lo + ((stage * stage_bytes) >> 4);
+          const uint32_t a_tmem = tmem_base + ring_col + slot * kPkSlotCols;
+#pragma unroll
+          for (int k = 0; k < kWsBlockK / 16; ++k)
+            umma_bf16_ts_pair(tmem_base, a_tmem + 8 * k, desc_from_words(x_lo + 2 * k, kDescHi), idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+          umma_commit_pair(&hdr->empty[stage], 3);
+          umma_commit_pair(&hdr->a_empty[slot], 3);
+        }
+        __syncwarp();
+        if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
+        if (++slot == static_cast<uint32_t>(num_slots)) slot = 0, sphase ^= 1;
+      }
+      if (issuer) umma_commit_pair(&hdr->tmem_full, 3);
+      __syncwarp();
+#ifdef LTXB_WS_DEBUG
+      if (WS_DBG(64) && blockIdx.x == 0 && lane == 0) printf("ws roles: MMA loop %lld cycles, %lld waiting for token rows, %lld for expanded tiles\n", clock64() - t_loop, w_full, w_afull);
+#endif
+      (void)t_loop, (void)w_full, (void)w_afull;
+    }
+  } else {
+    // ===================== expanding warps: packed tile -> bf16 A-operand slot in TMEM =====================
+    const int quarter = warp & 3, khalf = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;  // weight row of the tile = TMEM lane
+    const long long row_abs = static_cast<long long>(n0_w) + row;
+    const bool row_ok = row_abs < p.N;
+    // (scale, bias) of this thread's 32 columns: 16 bytes (8 bf16 / 4 f32 groups of the row) at a time, one chunk AHEAD
+    const int esz = p.aux_f32 ? 4 : 2;
+    const int chunk_groups = 16 / esz;
+    const int groups_per_row = p.K / p.group;
+    const bool chunked = (groups_per_row % chunk_groups == 0) && ((p.lds * esz) % 16 == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.scales) | reinterpret_cast<uintptr_t>(p.biases)) % 16 == 0);
+    const int group_shift = p.group == 32 ? 5 : (p.group == 64 ? 6 : 7);
+    auto group_of = [&](int kb) { return (kb * kWsBlockK + khalf * 32) >> group_shift; };
+    auto load_chunk = [&](int c, uint4& S, uint4& B) {
+      S = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0, 0);
+      if (!row_ok || c * chunk_groups >= groups_per_row) return;
+      const size_t off = (static_cast<size_t>(row_abs) * p.lds + static_cast<size_t>(c) * chunk_groups) * esz;
+      S = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.scales) + off));
+      B = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.biases) + off));
+    };
+    auto pick = [&](const uint4& V, int i) -> float {  // element i of a chunk without indexing registers dynamically
+      if (p.aux_f32) {
+        const uint32_t lo = (i & 1) ? V.y : V.x, hi = (i & 1) ? V.w : V.z;
+        return __uint_as_float((i & 2) ? hi : lo);
+      }
+      const uint32_t a = (i & 2) ? V.y : V.x, b = (i & 2) ? V.w : V.z;
+      const uint32_t wd = (i & 4) ? b : a;
+      return __uint_as_float((i & 1) ? (wd & 0xffff0000u) : (wd << 16));
+    };
+    auto load_scalar = [&](int kb, float& sc, float& bi) {  // layouts the 16-byte chunks do not fit
+      sc = 0.f, bi = 0.f;
+      if (!row_ok) return;
+      const long long a = row_abs * p.lds + group_of(kb);
+      if (p.aux_f32) {
+        sc = __ldg(static_cast<const float*>(p.scales) + a);
+        bi = __ldg(static_cast<const float*>(p.biases) + a);
+      } else {
+        sc = __bfloat162float(static_cast<const __nv_bfloat16*>(p.scales)[a]);
+        bi = __bfloat162float(static_cast<const __nv_bfloat16*>(p.biases)[a]);
+      }
+    };
+    const uint32_t tiles_u32 = smem_u32(tiles);
+    const uint32_t raw_thread_off = x_bytes + row * kRawRowBytes + khalf * (kRawRowBytes / 2);
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ring_col + khalf * (kPkSlotCols / 2);
+    const uint32_t magic = p.magic;  // 0x4B000000 from a kernel parameter, i.e. in a REGISTER: PRMT then takes its selector as the
+                                     // immediate (one instruction per level; a literal makes ptxas re-materialise the selectors)
+    uint32_t stage = 0, phase = 0, slot = 0, sphase = 0;
+    uint4 s_cur, b_cur, s_next, b_next;
+    int cur_chunk = group_of(kb0) / chunk_groups;
+    if (chunked) {
+      load_chunk(cur_chunk, s_cur, b_cur);
+      load_chunk(cur_chunk + 1, s_next, b_next);
+    }
+    long long w_raw = 0, w_aempty = 0, w_st = 0, t_loop = clock64();
+    auto aux_of = [&](int kb, float& sc, float& bi) {
+      if (chunked) {
+        const int g = group_of(kb);
+        if (g / chunk_groups != cur_chunk) {
+          s_cur = s_next, b_cur = b_next;
+          ++cur_chunk;
+          load_chunk(cur_chunk + 1, s_next, b_next);
+        }
+        const int gi = g - cur_chunk * chunk_groups;
+        sc = pick(s_cur, gi), bi = pick(b_cur, gi);
+      } else {
+        load_scalar(kb, sc, bi);
+      }
+    };
+    // level -> float through the 2^23 trick (bits 0x4B0000qq = 8388608 + q, exact), then scales * q + biases with the
+    // roundings of ltxb_dequant_affine_bf16: the product of a bf16 scale and an 8-bit level is exact in f32, so one fused
+    // multiply-add rounds like its multiply + add; f32 scales keep the two instructions
+    auto expand = [&](const uint32_t (&w)[kWBits], float sc, float bi, uint32_t (&packed)[16], auto fused) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v[8];
+        if constexpr (kWBits == 4) {
+          const uint32_t lo = w[j] & 0x0F0F0F0Fu, hi = (w[j] >> 4) & 0x0F0F0F0Fu;  // even / odd levels, one per byte
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float q = __uint_as_float(__byte_perm((e & 1) ? hi : lo, magic, 0x7540u | (e >> 1))) - 8388608.0f;
+            v[e] = decltype(fused)::value ? __fmaf_rn(sc, q, bi) : __fadd_rn(__fmul_rn(sc, q), bi);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float q = __uint_as_float(__byte_perm(w[2 * j + (e >> 2)], magic, 0x7540u | (e & 3))) - 8388608.0f;
+            v[e] = decltype(fused)::value ? __fmaf_rn(sc, q, bi) : __fadd_rn(__fmul_rn(sc, q), bi);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) packed[4 * j + e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+      }
+    };
+    auto load_raw = [&](uint32_t stg, uint32_t (&w)[kWBits]) {
+      const uint32_t st = tiles_u32 + stg * stage_bytes;
+      lds128(st + raw_thread_off, w[0], w[1], w[2], w[3]);
+      if constexpr (kWBits == 8) lds128(st + raw_thread_off + 16, w[4], w[5], w[6], w[7]);
+    };
+    // TWO k-blocks per trip: one trip is a chain of barrier polls, a shared-memory read, the expansion, a tensor-memory
+    // store and an arrive (~600 cycles of latency before any arithmetic, measured with LTXB_WS_DEBUG=64) — paired, the
+    // two chains overlap and the 64 independent level -> bf16 chains give the schedulers something to interleave
+    for (int kb = kb0; kb < kb1; kb += 2) {
+      const bool two = kb + 1 < kb1;
+      float sc0, bi0, sc1 = 0.f, bi1 = 0.f;
+      aux_of(kb, sc0, bi0);
+      if (two) aux_of(kb + 1, sc1, bi1);
+      const uint32_t stage0 = stage, phase0 = phase, slot0 = slot, sphase0 = sphase;
+      if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
+      if (++slot == static_cast<uint32_t>(num_slots)) slot = 0, sphase ^= 1;
+      const uint32_t stage1 = stage, phase1 = phase, slot1 = slot, sphase1 = sphase;
+      if (two) {
+        if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
+        if (++slot == static_cast<uint32_t>(num_slots)) slot = 0, sphase ^= 1;
+      }
+      uint32_t w0[kWBits], w1[kWBits], packed0[16], packed1[16];
+      WS_TIMED_WAIT(w_raw, mbar_wait(&hdr->raw_full[stage0], phase0));
+      load_raw(stage0, w0);
+      if (two) {
+        WS_TIMED_WAIT(w_raw, mbar_wait(&hdr->raw_full[stage1], phase1));
+        load_raw(stage1, w1);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kWBits; ++i) w1[i] = 0;
+      }
+#ifdef LTXB_WS_DEBUG
+      if (WS_DBG(32)) {  // timing experiment: no expansion arithmetic
+#pragma unroll
+        for (int i = 0; i < 16; ++i) packed0[i] = w0[i % kWBits], packed1[i] = w1[i % kWBits];
+      } else
+#endif
+      if (p.aux_f32) {
+        expand(w0, sc0, bi0, packed0, std::false_type{});
+        expand(w1, sc1, bi1, packed1, std::false_type{});
+      } else {
+        expand(w0, sc0, bi0, packed0, std::true_type{});
+        expand(w1, sc1, bi1, packed1, std::true_type{});
+      }
+      // the MMAs that read these slots one ring turn ago have completed
+      WS_TIMED_WAIT(w_aempty, mbar_wait(&hdr->a_empty[slot0], sphase0 ^ 1); if (two) mbar_wait(&hdr->a_empty[slot1], sphase1 ^ 1));
+      tc_fence_after_sync();
+      WS_TIMED_WAIT(w_st, tmem_st_x16(t_lane + slot0 * kPkSlotCols, packed0); if (two) tmem_st_x16(t_lane + slot1 * kPkSlotCols, packed1);
+                    tmem_wait_st(); tc_fence_before_sync(); __syncwarp(); if (lane == 0) {
+                      mbar_arrive_remote(&hdr->a_full[slot0], 0);
+                      if (two) mbar_arrive_remote(&hdr->a_full[slot1], 0);
+                    });
+    }
+#ifdef LTXB_WS_DEBUG
+    if (WS_DBG(64) && blockIdx.x == 0 && threadIdx.x == 64) printf("ws roles: expanding warp loop %lld cycles, %lld waiting for packed tiles, %lld for free slots, %lld in tcgen05.st + arrive\n", clock64() - t_loop, w_raw, w_aempty, w_st);
+#endif
+    (void)t_loop, (void)w_raw, (void)w_aempty, (void)w_st;
+    ws_epilogue<kEpi>(p, &tmap_out, &hdr->tmem_full, tiles, static_cast<uint32_t>(num_stages) * stage_bytes, tmem_base, tile, split,
+                      cta_rank, warp, lane, dbg);
+  }
+
+  if (p.out_tma != 0 && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) tma_store_wait_read();
+  __syncwarp();
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<2>(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 template <int kEpi, int kWBits>
 static int launch_ws(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& to, const WsParams& p, int grid, size_t smem,
                      cudaStream_t stream) {
-  auto kernel = gemm_small_m_kernel<kEpi, kWBits>;
   static PerDeviceOnce configured;
-  if (configured.first()) LTXB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-  LTXB_CUDA(launch_kernel(kernel, dim3(grid), dim3(kWsThreads), smem, stream, 2, tx, tw, to, p));
+  if constexpr (kWBits == 16) {
+    auto kernel = gemm_small_m_kernel<kEpi>;
+    if (configured.first()) LTXB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    LTXB_CUDA(launch_kernel(kernel, dim3(grid), dim3(kWsThreads), smem, stream, 2, tx, tw, to, p));
+  } else {
+    auto kernel = gemm_small_m_packed_kernel<kEpi, kWBits>;
+    if (configured.first()) LTXB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    LTXB_CUDA(launch_kernel(kernel, dim3(grid), dim3(kWsThreads), smem, stream, 2, tx, tw, to, p));
+  }
   return LTXB_OK;
 }
 
@@ -646,10 +877,13 @@ int launch_gemm_small_m(const void* A, int64_t lda, const void* W, int64_t ldw, 
   p.m_pad = p.n_mma == 1 ? ((M + 15) / 16) * 16 : ((M + 31) / 32) * 32;
   p.tmem_cols = 32;
   while (p.tmem_cols < p.m_pad) p.tmem_cols *= 2;
-  // the schedule (CTAs per SM, k-range splits) is decided on the bf16 stage size for packed weights too, so that both paths
-  // add their partial sums in the same order (bit-identical results); only the stage COUNT follows the real size
-  const size_t stage_bytes_sched = kWsWBytes + static_cast<size_t>(p.m_pad / 2) * kWsBlockK * 2;
-  const size_t stage_bytes = stage_bytes_sched + (w_bits != 16 ? kWsTileRows * kWsBlockK * w_bits / 8 : 0);
+  // packed weights: a stage is the packed tile + the token rows (the bf16 tile lives in tensor memory), one CTA per SM
+  const size_t stage_bytes = w_bits != 16 ? static_cast<size_t>(p.m_pad / 2) * kWsBlockK * 2 + kWsTileRows * kWsBlockK * w_bits / 8
+                                          : kWsWBytes + static_cast<size_t>(p.m_pad / 2) * kWsBlockK * 2;
+  if (w_bits != 16) {
+    LTXB_CHECK_SUPPORTED(M <= kPkAccCols, "ltxb_gemm_qw_bf16: M=%d: the packed-weight kernel keeps the expanded tiles in tensor memory behind a %d-column accumulator (expand the weights with ltxb_dequant_affine_bf16 for more rows)", M, kPkAccCols);
+    p.tmem_cols = 512;
+  }
   const int tiles = (N + 2 * kWsTileRows - 1) / (2 * kWsTileRows);
   const int num_kb = K / kWsBlockK;
   static const int env_min_kb = [] { const char* e = getenv("LTXB_GEMM_SMALL_M_MIN_KB"); return e ? atoi(e) : 4; }();
@@ -668,13 +902,13 @@ int launch_gemm_small_m(const void* A, int64_t lda, const void* W, int64_t ldw, 
   // (profiles/r2/gemm_small_m.md): one per SM wins whenever it still fills the machine (>= 85 % of the SM pairs busy).
   const int pairs = sms / 2;
   int per_sm = 1;
-  if (p.tmem_cols <= 256 && (113 * 1024 - 1024 - kWsHeader) / stage_bytes_sched >= 3 && (113 * 1024 - 1024 - kWsHeader) / stage_bytes >= 2) {
+  if (p.tmem_cols <= 256 && (113 * 1024 - 1024 - kWsHeader) / stage_bytes >= 3) {
     const int s1 = splits_for(pairs);
     const bool fills = tiles <= pairs && tiles * s1 * 100 >= pairs * 85;
     per_sm = (env_per_sm == 1 || env_per_sm == 2) ? env_per_sm : (fills ? 1 : 2);
   }
   const size_t budget = (per_sm == 2 ? 113 * 1024 : 232448) - 1024 - kWsHeader;
-  p.num_stages = static_cast<int>(std::min<size_t>(kWsMaxStages, budget / stage_bytes));
+  p.num_stages = static_cast<int>(std::min<size_t>(w_bits != 16 ? kPkMaxStages : kWsMaxStages, budget / stage_bytes));
   const size_t smem = 1024 + kWsHeader + p.num_stages * stage_bytes;
   const int slots = pairs * per_sm;  // co-resident CTA pairs
   int splits = splits_for(slots);
@@ -694,6 +928,7 @@ int launch_gemm_small_m(const void* A, int64_t lda, const void* W, int64_t ldw, 
   p.partials = partials;
   p.counters = counters;
   if (packed != nullptr) {
+    p.magic = 0x4B000000u;
     p.scales = packed->scales, p.biases = packed->biases, p.lds = packed->lds, p.group = packed->group, p.aux_f32 = packed->aux_f32;
   }
   static const int env_const_w = [] { const char* e = getenv("LTXB_GEMM_CONST_W"); return e ? atoi(e) : 1; }();

@@ -1,0 +1,9 @@
+#!/bin/bash
+export LTXB_LIB=$PWD/mlx-video_b200/csrc/libltxb_wsdbg.so
+for d in 64 96; do
+echo "== LTXB_WS_DEBUG=$d"
+LTXB_WS_DEBUG=$d LTXB_BENCH_VARIANTS=none LTXB_BENCH_PACKED=1 timeout 600 python scripts/gemm_small_m_bench.py 160x16384x4096 > /tmp/o.txt 2>&1
+grep "MMA loop" /tmp/o.txt | tail -3
+grep "expanding warp" /tmp/o.txt | tail -3
+grep "producer" /tmp/o.txt | tail -2
+done
