@@ -65,7 +65,7 @@ int64_t ltxb_kernel_launches(void);
  * cta_pair: 1 = cta_group::2 (two SMs share one 256-row tile), 0 = single CTA, -1 = choose; 2 / 3 = force the
  *   contiguous stream-K schedule (every SM an equal, contiguous share of the (tile, k-block) list; what -1 picks for
  *   M <= 640 when the tile count leaves a ragged wave) with single-CTA / pair tiles; 4 = force the few-row weight-streaming
- *   kernel (M <= 512: weight rows on the TMEM lanes, tokens as the MMA's N; what -1 picks for M <= 256), block_n then =
+ *   kernel (M <= 512: weight rows on the TMEM lanes, tokens as the MMA's N; what -1 picks for M <= 512), block_n then =
  *   k-range splits per weight tile (0 = choose).
  * ---------------------------------------------------------------------------------------------- */
 enum {
@@ -76,6 +76,19 @@ enum {
   LTXB_EPI_RESID_GATE_F32 = 4,
   LTXB_EPI_COUNT = 5
 };
+
+/* The flag barrier of the NVLink-fused Ulysses exchange (ltxb_peer_barrier) folded into the prologue of the kernel that
+ * consumes what the peers wrote: once the stream predecessor has completed, block 0 raises this rank's flag on every
+ * peer and every block waits for all peers' flags before it reads; the last block to leave advances the epoch.  Same
+ * flags / epoch counter as ltxb_peer_barrier (the two can be mixed); done_counter is one more device int, zero between
+ * launches.  Accepted by ltxb_gemm_bf16 / ltxb_gemm_qw_bf16 (ltxb_epilogue.peer_sync) and ltxb_attention_fwd_peers_sync. */
+typedef struct ltxb_peer_sync {
+  int32_t* flags[8];      /* flags[i] = rank i's flag array (n_peers ints), mapped into this process */
+  int32_t n_peers;        /* 1..8 */
+  int32_t my_rank;
+  int32_t* epoch_counter; /* device int: barriers this rank has passed */
+  int32_t* done_counter;  /* device int, zero between launches */
+} ltxb_peer_sync;
 
 /* ltxb_epilogue.flags.  LTXB_GEMM_CONST_W: W is not written by any kernel that may still be running ahead of this
  * launch in the stream (model weights): the few-row kernel then starts streaming W while its stream predecessor is
@@ -98,6 +111,8 @@ typedef struct ltxb_epilogue {
   int32_t a_group_cols;
   int32_t flags;                 /* LTXB_GEMM_* bits                                 */
   int64_t a_group_stride;
+  const ltxb_peer_sync* peer_sync; /* NULL, or: run the cross-GPU flag barrier before the first read of A (A = what the peers
+                                    * stored into this rank's receive buffer: the out-projection after ltxb_attention_fwd_peers) */
 } ltxb_epilogue;
 
 int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int32_t M,
@@ -269,6 +284,11 @@ int ltxb_attention_set_workspace(void* workspace, int64_t bytes);
 /* The same with the Ulysses sequence-gather all-to-all fused into the epilogue (B = 1): output row r is stored to
  * o_peers[r / rows_per_peer] + (r % rows_per_peer) * ldo — rank i's NVLink-mapped receive buffer, already offset
  * to this rank's head-group chunk — instead of a local O followed by a collective. */
+/* ..._sync: with the flag barrier that orders the peers' q/k/v stores (ltxb_qkv_norm_rope_scatter_peers on every rank)
+ * before this kernel's reads folded into its prologue (sync may be NULL = plain ltxb_attention_fwd_peers). */
+int ltxb_attention_fwd_peers_sync(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
+                                  void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, int64_t ldo, int32_t Tq,
+                                  int32_t Tk, int32_t H, int32_t dh, float scale, const ltxb_peer_sync* sync, void* stream);
 int ltxb_attention_fwd_peers(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
                              void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, int64_t ldo, int32_t Tq,
                              int32_t Tk, int32_t H, int32_t dh, float scale, void* stream);

@@ -19,6 +19,18 @@ LIB_PATH = Path(os.environ["LTXB_LIB"]) if os.environ.get("LTXB_LIB") else CSRC 
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 
+class PeerSync(C.Structure):
+    """Mirror of ``struct ltxb_peer_sync`` (the folded cross-GPU flag barrier)."""
+
+    _fields_ = [
+        ("flags", _vp * 8),
+        ("n_peers", _i32),
+        ("my_rank", _i32),
+        ("epoch_counter", _vp),
+        ("done_counter", _vp),
+    ]
+
+
 class Epilogue(C.Structure):
     """Mirror of ``struct ltxb_epilogue``."""
 
@@ -35,6 +47,7 @@ class Epilogue(C.Structure):
         ("a_group_cols", _i32),
         ("flags", _i32),
         ("a_group_stride", _i64),
+        ("peer_sync", C.POINTER(PeerSync)),
     ]
 
 
@@ -61,6 +74,7 @@ SIGNATURES = {
     "ltxb_qkv_norm_rope_scatter_peers": (C.c_int, [_vp, _i64, _i64, C.POINTER(_vp), _i32, _i64, _i64, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _i32, _vp]),
     "ltxb_peer_barrier": (C.c_int, [C.POINTER(_vp), _i32, _i32, _vp, _vp]),
     "ltxb_peer_broadcast": (C.c_int, [_vp, _i64, C.POINTER(_vp), _i32, _vp]),
+    "ltxb_attention_fwd_peers_sync": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, C.POINTER(_vp), _i32, _i32, _i64, _i32, _i32, _i32, _i32, _f32, C.POINTER(PeerSync), _vp]),
     "ltxb_attention_fwd_peers": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, C.POINTER(_vp), _i32, _i32, _i64, _i32, _i32, _i32, _i32, _f32, _vp]),
     "ltxb_attention_partial_floats": (C.c_int64, [_i32, _i32, _i32, _i32]),
     "ltxb_attention_partial": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),

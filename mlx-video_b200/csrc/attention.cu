@@ -343,12 +343,21 @@ using namespace ltxb;
 
 static int attention_impl(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
                           int64_t ldo, int32_t B, int32_t Tq, int32_t Tk, int32_t H, int32_t dh, float scale,
-                          const float* kv_bias, void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, void* stream);
+                          const float* kv_bias, void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, void* stream,
+                          const ltxb_peer_sync* sync = nullptr);
 
 extern "C" int ltxb_attention_fwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
                                   void* O, int64_t ldo, int32_t B, int32_t Tq, int32_t Tk, int32_t H, int32_t dh,
                                   float scale, const float* kv_bias, void* stream) {
   return attention_impl(Q, ldq, K, ldk, V, ldv, O, ldo, B, Tq, Tk, H, dh, scale, kv_bias, nullptr, 0, 0, stream);
+}
+
+extern "C" int ltxb_attention_fwd_peers_sync(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
+                                             void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, int64_t ldo, int32_t Tq,
+                                             int32_t Tk, int32_t H, int32_t dh, float scale, const ltxb_peer_sync* sync, void* stream) {
+  LTXB_CHECK_ARG(o_peers && n_peers >= 1 && n_peers <= 8 && rows_per_peer > 0 && n_peers * rows_per_peer >= Tq,
+                 "ltxb_attention_fwd_peers_sync: %d peers x %d rows do not cover Tq=%d", n_peers, rows_per_peer, Tq);
+  return attention_impl(Q, ldq, K, ldk, V, ldv, o_peers[0], ldo, 1, Tq, Tk, H, dh, scale, nullptr, o_peers, n_peers, rows_per_peer, stream, sync);
 }
 
 extern "C" int ltxb_attention_fwd_peers(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
@@ -396,7 +405,8 @@ extern "C" int ltxb_attention_merge(const float* parts, int64_t part_stride, int
 
 static int attention_impl(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
                           int64_t ldo, int32_t B, int32_t Tq, int32_t Tk, int32_t H, int32_t dh, float scale,
-                          const float* kv_bias, void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, void* stream) {
+                          const float* kv_bias, void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, void* stream,
+                          const ltxb_peer_sync* sync) {
   LTXB_CHECK_ARG(Q && K && V && O, "ltxb_attention_fwd: null pointer");
   if (B == 0 || Tq == 0) return LTXB_OK;
   LTXB_CHECK_ARG(B > 0 && Tq > 0 && Tk > 0 && H > 0, "ltxb_attention_fwd: bad shape B=%d Tq=%d Tk=%d H=%d", B, Tq, Tk, H);
@@ -418,9 +428,14 @@ static int attention_impl(const void* Q, int64_t ldq, const void* K, int64_t ldk
     p.o_peer[i] = reinterpret_cast<__nv_bfloat16*>(base);
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (int rc = peer_sync_from_abi(sync, &p.sync, "ltxb_attention_fwd_peers_sync")) return rc;
   // more than one query tile: two tiles per CTA ping-pong on the tensor core (attention_pair.cu)
   static const bool force_single = [] { const char* e = getenv("LTXB_ATTN_SINGLE"); return e != nullptr && atoi(e) != 0; }();
   if (Tq > kTileQ && !force_single) return launch_attention_pair(Q, ldq, K, ldk, V, ldv, p, dh, s);
+  if (p.sync.n_peers > 0) {  // the one-tile kernel has no folded barrier: run it as a kernel of its own
+    if (int rc = launch_peer_barrier(p.sync, s)) return rc;
+    p.sync = PeerSync{};
+  }
   if (dh == 128) return launch_attention<128>(Q, ldq, K, ldk, V, ldv, p, s);
   return launch_attention<64>(Q, ldq, K, ldk, V, ldv, p, s);
 }

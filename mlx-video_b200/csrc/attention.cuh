@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "peer_sync.cuh"
 
 namespace ltxb {
 
@@ -27,6 +28,9 @@ struct AttnParams {
   // ws_o + i*cmb_part_o and ws_ml + i*cmb_part_ml (strides in floats)
   int part_rows;
   long long cmb_job_stride, cmb_part_o, cmb_part_ml;
+  // cross-GPU flag barrier before the first read of Q / K / V (they were stored by the peers): folded into the prologue of
+  // attention_pair64_kernel; the launchers of the other kernels run the stand-alone barrier kernel first
+  PeerSync sync;
 };
 
 // where output row `row` of batch b, head h starts (local O or a peer's receive buffer)

@@ -493,6 +493,7 @@ attention_pair64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   pdl_launch_dependents();
   pdl_wait();
   if (threadIdx.x == 0) TRACE(3, 0, 2);  // predecessor kernel finished
+  const int sync_epoch = peer_sync_enter(p.sync);  // Q / K / V stored by the peers: flag barrier before the first load
 
   if (warp < 4) {
     reg_dealloc<kRegsIssue>();
@@ -750,6 +751,7 @@ attention_pair64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   tc_fence_before_sync();
   __syncthreads();
   if (threadIdx.x == 0) TRACE(3, 0, 6);  // output stored by every warp
+  if (threadIdx.x == 0) peer_sync_exit(p.sync, sync_epoch);
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc<1>(tmem_base, 512);
@@ -818,6 +820,10 @@ static int launch_pair(const void* Q, long long ldq, const void* K, long long ld
   // LTXB_ATTN_S64=0: the single-buffered 128-key-step kernel (kept for A/B runs)
   static const bool s64 = [] { const char* e = getenv("LTXB_ATTN_S64"); return e == nullptr || atoi(e) != 0; }();
   auto kernel = s64 ? attention_pair64_kernel<kDh> : attention_pair_kernel<kDh>;
+  if (p.sync.n_peers > 0 && !s64) {  // only the 64-key kernel has the folded barrier
+    if (int rc = launch_peer_barrier(p.sync, stream)) return rc;
+    p.sync = PeerSync{};
+  }
   static PerDeviceOnce configured;  // per instantiation and device
   if (configured.first()) {
     LTXB_CUDA(cudaFuncSetAttribute(attention_pair64_kernel<kDh>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -4,6 +4,7 @@
 // algorithmic bytes per element are stated next to each entry point in DESIGN.md.
 #include "common.cuh"
 #include <algorithm>
+#include "peer_sync.cuh"
 #include "ptx.cuh"
 
 namespace ltxb {
@@ -971,6 +972,15 @@ extern "C" int ltxb_timestep_groups(const float* t, int32_t n, int32_t cap, floa
                                                                                                     index, count));
   return LTXB_OK;
 }
+
+namespace ltxb {
+int launch_peer_barrier(const PeerSync& s, cudaStream_t stream) {
+  PeerFlags f{};
+  for (int i = 0; i < s.n_peers; ++i) f.p[i] = s.flags[i];
+  LTXB_CUDA(launch_kernel(peer_barrier_kernel, dim3(1), dim3(32), 0, stream, 1, f, s.n_peers, s.my_rank, s.epoch_counter));
+  return LTXB_OK;
+}
+}  // namespace ltxb
 
 extern "C" int ltxb_peer_barrier(int32_t* const* flag_ptrs, int32_t n_peers, int32_t my_rank, int32_t* epoch_counter,
                                  void* stream) {

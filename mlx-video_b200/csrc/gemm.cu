@@ -18,6 +18,7 @@
 //     pairs = 96 % wave efficiency instead of 54 % at BN=256).
 #include "common.cuh"
 #include "gemm_small_m.cuh"
+#include "peer_sync.cuh"
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -77,6 +78,7 @@ struct GemmParams {
   // tile-major unit list (U = tiles * k-blocks), boundaries rounded to sk_gran k-blocks
   int sk_contig;
   int sk_gran;
+  PeerSync sync;  // cross-GPU flag barrier before the first read of A (n_peers 0: none)
 };
 
 // Tiles are dealt to clusters round-robin, all clusters marching through K in lockstep (tiles that share an A
@@ -283,6 +285,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   pdl_launch_dependents();
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
   if (threadIdx.x == 0) GTRACE(2);  // predecessor complete
+  const int sync_epoch = peer_sync_enter(p.sync);  // A was written by the peers: flag barrier before the first load
 
   if (warp < 4) {
   reg_dealloc<kRegsIssue>();
@@ -559,6 +562,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncwarp();
   tc_fence_before_sync();
   if constexpr (kCtas == 2) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x == 0) peer_sync_exit(p.sync, sync_epoch);
   if (threadIdx.x == 0) GTRACE(7);  // teardown sync passed
   if (warp == 1) {
     tc_fence_after_sync();
@@ -709,7 +713,9 @@ extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   // (gemm_small_m.cu).  cta_pair 4 forces it (block_n then = number of k-range splits, 0 = choose); LTXB_GEMM_SMALL_M is the
   // largest M the library sends there on its own (0 disables).
   {
-    static const int env_small_m = [] { const char* e = getenv("LTXB_GEMM_SMALL_M"); return e ? atoi(e) : 256; }();
+    // measured (profiles/r2/gemm_small_m.md): at 160 rows the few-row kernel wins everywhere, at 320 rows (two MMAs per
+    // k-slice) on three of the four LTX-2 shapes (-20 %) and loses 4 % on the fourth, beyond 512 it does not apply
+    static const int env_small_m = [] { const char* e = getenv("LTXB_GEMM_SMALL_M"); return e ? atoi(e) : 512; }();
     const bool forced = (cta_pair == 4);
     if (forced) LTXB_CHECK_SUPPORTED(gemm_small_m_supported(M, N, K), "ltxb_gemm_bf16: the small-M kernel needs M <= 512 (M=%d N=%d K=%d)", M, N, K);
     if (forced || (cta_pair < 0 && block_n == 0 && M <= env_small_m && N >= 128 && K >= 256 && gemm_small_m_supported(M, N, K) && env_pair < 0 && env_bn == 0)) {
@@ -781,6 +787,7 @@ extern "C" int ltxb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   p.gate_row_div = epi->gate_row_div > 0 ? epi->gate_row_div : 1;
   p.gate_row_index = epi->gate_row_index;
   p.gate_table = epi->gate_table;
+  if (int rc = peer_sync_from_abi(epi->peer_sync, &p.sync, "ltxb_gemm_bf16")) return rc;
 
   CUtensorMap ta, tw;
   if (epi->a_group_cols > 0) {

@@ -22,6 +22,7 @@
 //     store 32 consecutive columns of one row: coalesced 64 / 128-byte stores instead of one row per lane.
 #include "common.cuh"
 #include "gemm_small_m.cuh"
+#include "peer_sync.cuh"
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -69,6 +70,7 @@ struct WsParams {
                     // into `out` (RESID_GATE with out == resid: out += (acc + bias) * g, one add per element)
   float* partials;  // [grid][m_pad / 8][2][128] float4: parked chunks
   int* counters;
+  PeerSync sync;    // cross-GPU flag barrier before the first read of the token rows (n_peers 0: none)
   long long* trace;  // LTXB_WS_DEBUG builds, debug & 8: [grid][4] globaltimer at PDL wait / accumulator / met / done (tail of the workspace)
   int debug;  // LTXB_WS_DEBUG builds only: 1 = no token loads after the first k-block, 2 = no epilogue, 4 = no weight loads
               // after the first k-block, 8 = every CTA records its life-cycle times (timing experiments; results are wrong)
@@ -435,6 +437,7 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
   }
   pdl_wait();  // everything above overlapped the previous kernel's tail; activations / outputs are touched only below
+  const int sync_epoch = peer_sync_enter(p.sync);  // token rows written by the peers: flag barrier before the first load
   long long dbg[2] = {0, 0};  // LTXB_WS_DEBUG builds: accumulator complete / split partners met
 #ifdef LTXB_WS_DEBUG
   const long long t_pdl = ws_globaltimer();
@@ -514,6 +517,7 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   __syncwarp();
   tc_fence_before_sync();
   cluster_sync_all();
+  if (threadIdx.x == 0) peer_sync_exit(p.sync, sync_epoch);
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc<2>(tmem_base, p.tmem_cols);
@@ -614,6 +618,7 @@ gemm_small_m_packed_kernel(const __grid_constant__ CUtensorMap tmap_x, const __g
     }
   }
   pdl_wait();
+  const int sync_epoch = peer_sync_enter(p.sync);
   long long dbg[2] = {0, 0};
 
   if (warp == 0) {
@@ -838,6 +843,7 @@ gemm_small_m_packed_kernel(const __grid_constant__ CUtensorMap tmap_x, const __g
   __syncwarp();
   tc_fence_before_sync();
   cluster_sync_all();
+  if (threadIdx.x == 0) peer_sync_exit(p.sync, sync_epoch);
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc<2>(tmem_base, 512);
@@ -927,6 +933,7 @@ int launch_gemm_small_m(const void* A, int64_t lda, const void* W, int64_t ldw, 
   p.gate_table = epi->gate_table;
   p.partials = partials;
   p.counters = counters;
+  if (int rc = peer_sync_from_abi(epi->peer_sync, &p.sync, "ltxb_gemm")) return rc;
   if (packed != nullptr) {
     p.magic = 0x4B000000u;
     p.scales = packed->scales, p.biases = packed->biases, p.lds = packed->lds, p.group = packed->group, p.aux_f32 = packed->aux_f32;

@@ -95,8 +95,10 @@ def _ld(t: torch.Tensor) -> int:
     return ld
 
 
-def _epilogue(mode, N, bias, resid, gate, gate_table, gate_row_div, gate_row_index, const_w) -> "Epilogue":
+def _epilogue(mode, N, bias, resid, gate, gate_table, gate_row_div, gate_row_index, const_w, peer_sync=None) -> "Epilogue":
     epi = Epilogue()
+    if peer_sync is not None:  # a _lib.PeerSync the caller keeps alive (PeerMemory.sync): flag barrier before the first read of A
+        epi.peer_sync = C.pointer(peer_sync)
     epi.mode = mode
     epi.gate_row_div = gate_row_div
     epi.flags = 1 if const_w else 0
@@ -133,6 +135,7 @@ def gemm(
     cta_pair: int = -1,
     a_group_cols: int = 0,
     const_w: bool = False,
+    peer_sync=None,
 ) -> torch.Tensor:
     """out = epilogue(a @ w.T).  a: bf16 [..., K]; w: bf16 [N, K] (nn.Linear layout); see ltxb.h.
     a_group_cols = g > 0: ``a`` is a contiguous [K / g, M, g] tensor (head-group-major, as the Ulysses gather
@@ -155,8 +158,8 @@ def gemm(
         hit = _packed.lookup(w)  # a quantised linear kept packed (packed.py): stream the packed words instead
         if hit is not None:
             return gemm_qw(a, hit[0], hit[1], hit[2], hit[3], hit[4], bias, out, mode, resid, gate, gate_table, gate_row_div,
-                           gate_row_index, 0, a_group_cols, const_w)
-    epi = _epilogue(mode, N, bias, resid, gate, gate_table, gate_row_div, gate_row_index, const_w)
+                           gate_row_index, 0, a_group_cols, const_w, peer_sync)
+    epi = _epilogue(mode, N, bias, resid, gate, gate_table, gate_row_div, gate_row_index, const_w, peer_sync)
     lda = _ld(a)
     if a_group_cols > 0:
         epi.a_group_cols, epi.a_group_stride, lda = a_group_cols, M * a_group_cols, a_group_cols
@@ -183,6 +186,7 @@ def gemm_qw(
     splits: int = 0,
     a_group_cols: int = 0,
     const_w: bool = False,
+    peer_sync=None,
 ) -> torch.Tensor:
     """out = epilogue(a @ dequant(packed, scales, biases).T) for FEW rows (M <= 512) with the MLX affine-quantised weight
     kept packed in HBM (``ltxb_gemm_qw_bf16``): uint32 / int32 [N, K*bits/32], scales / biases bf16 or f32 [N, K/group_size].
@@ -205,7 +209,7 @@ def gemm_qw(
                          f"{bits} bits, group {group_size}")
     assert _rows(out) == M and out.shape[-1] == N
     assert out.dtype == (torch.float32 if mode in (_lib.EPI_BIAS_F32, _lib.EPI_RESID_GATE_F32) else torch.bfloat16)
-    epi = _epilogue(mode, N, bias, resid, gate, gate_table, gate_row_div, gate_row_index, const_w)
+    epi = _epilogue(mode, N, bias, resid, gate, gate_table, gate_row_div, gate_row_index, const_w, peer_sync)
     lda = _ld(a)
     if a_group_cols > 0:
         epi.a_group_cols, epi.a_group_stride, lda = a_group_cols, M * a_group_cols, a_group_cols
@@ -679,10 +683,16 @@ def qkv_norm_rope_scatter_peers(qkv: torch.Tensor, inner: int, group_bases, T: i
 
 
 def attention_peers(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o_bases, rows_per_peer: int, ldo: int, Tq: int, Tk: int,
-                    H: int, dh: int, scale: float) -> None:
-    """Attention (B = 1) whose output rows [i*rows_per_peer, (i+1)*rows_per_peer) go to ``o_bases[i]``."""
+                    H: int, dh: int, scale: float, peer_sync=None) -> None:
+    """Attention (B = 1) whose output rows [i*rows_per_peer, (i+1)*rows_per_peer) go to ``o_bases[i]``.  peer_sync (a
+    _lib.PeerSync kept alive by the caller): q / k / v were stored by the peers — the flag barrier that orders those stores
+    before this kernel's reads runs in its prologue instead of as a launch of its own."""
     _prep(q)
     assert q.dtype == k.dtype == v.dtype == torch.bfloat16
+    if peer_sync is not None:
+        _call("ltxb_attention_fwd_peers_sync", 4.0 * H * Tq * Tk * dh, q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v),
+              _ptr_array(o_bases), len(o_bases), rows_per_peer, ldo, Tq, Tk, H, dh, scale, C.pointer(peer_sync), _stream())
+        return
     _call("ltxb_attention_fwd_peers", 4.0 * H * Tq * Tk * dh, q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v),
           _ptr_array(o_bases), len(o_bases), rows_per_peer, ldo, Tq, Tk, H, dh, scale, _stream())
 

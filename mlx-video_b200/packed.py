@@ -32,7 +32,7 @@ class _Entry:
 class PackedWeights:
     def __init__(self) -> None:
         self.entries: List[_Entry] = []
-        self.max_rows = 256  # what ltxb_gemm_bf16 itself sends to the few-row kernel
+        self.max_rows = 256  # the packed kernel's limit (tensor-memory ring behind a 256-column accumulator)
         self._cache: Dict[tuple, Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, int, int]]] = {}
 
     def __len__(self) -> int:

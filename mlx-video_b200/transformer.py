@@ -259,19 +259,22 @@ class Attention:
         epilogue carries bias, gate and residual add (transformer.py:254,257-261).
         ``defer=True``: the projection (bias included) is returned as bf16 instead and the CALLER adds it — the
         next sub-layer's norm kernel does, in the pass that reads the row anyway (ops.residual_rmsnorm_modulate)."""
-        group_cols = 0
+        group_cols, peer_sync = 0, None
         if seq_parallel is not None and context is None and self.is_self:
             # rows are sharded across ranks: projections local, heads <-> sequence all-to-all around the attention
             o, group_cols = seq_parallel.self_attention(self, ws, tag, xq, B, Tq, pe)
+            peer_sync = seq_parallel.take_pending_sync() if hasattr(seq_parallel, "take_pending_sync") else None
         else:
             q, k, v = self.project(ws, tag, xq, B, Tq, context, Tk, pe, k_pe, kv_out, kv_ready)
             o = self.sdpa(ws, tag, q, k, v, B, Tq, Tq if context is None else Tk, kv_bias)
         if defer:
             y = ws.get(tag + ".y", (B * Tq, self.query_dim), BF16, resid.device)
-            ops.gemm(o, self.to_out.weight, self.to_out.bias, y, _lib.EPI_BIAS_BF16, a_group_cols=group_cols, const_w=True)
+            ops.gemm(o, self.to_out.weight, self.to_out.bias, y, _lib.EPI_BIAS_BF16, a_group_cols=group_cols, const_w=True,
+                     peer_sync=peer_sync)
             return y
         ops.gemm(o, self.to_out.weight, self.to_out.bias, resid, _lib.EPI_RESID_GATE_F32, resid=resid, gate=gate,
-                 gate_table=gate_table, gate_row_div=row_div, gate_row_index=row_index, a_group_cols=group_cols, const_w=True)
+                 gate_table=gate_table, gate_row_div=row_div, gate_row_index=row_index, a_group_cols=group_cols, const_w=True,
+                 peer_sync=peer_sync)
         return None
 
     def __call__(self, x: Tensor, context: Optional[Tensor] = None, mask: Optional[Tensor] = None, pe=None,

@@ -131,7 +131,7 @@ def test_gemm_small_m_kernel(M, N, K):
         b = gemm_case(M, N, K, _lib.EPI_BIAS_F32, pair=4, bn=splits)
         assert torch.equal(a, b), f"small-M kernel with {splits} splits differs between two runs"
         assert rel_l2(a, auto) < 2e-5
-    if M <= 256:  # what the library picks on its own for few rows
+    if M <= 512:  # what the library picks on its own for few rows
         assert torch.equal(auto, gemm_case(M, N, K, _lib.EPI_BIAS_F32))
 
 

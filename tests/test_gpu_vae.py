@@ -157,7 +157,8 @@ def test_decoder_chunked_rows_and_errors(decoder):
     finally:
         type(model).max_rows_per_chunk = old
     model.decode_noise_scale = 0.025
-    assert torch.equal(full, chunked)
+    # (not bit-equal: a 200-row chunk runs the few-row GEMM kernel, whose k-range splits add in a different order)
+    assert rel_l2(chunked, full) < 1e-5
     with pytest.raises(_lib.LtxbError):
         model(x.cpu())
     with pytest.raises(ValueError):
