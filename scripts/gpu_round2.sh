@@ -19,6 +19,8 @@ PY
 grep -A24 "^--- distilled" $out/bench.err > $out/bench_kernel_table.txt; cat $out/bench_kernel_table.txt
 timeout 300 python scripts/attn_sweep.py > $out/attn_sweep.txt 2>&1; cat $out/attn_sweep.txt
 timeout 300 python scripts/gemm_sweep.py > $out/gemm_sweep.txt 2>&1; cat $out/gemm_sweep.txt
+timeout 300 python scripts/gemm_small_m_bench.py 160x4096x4096 160x12288x4096 160x16384x4096 160x4096x16384 68x2048x2048 320x4096x4096 > $out/gemm_few_rows.txt 2>&1; cat $out/gemm_few_rows.txt
+timeout 300 python bench.py --workload shard160 --workloads none --no-cpu-baseline --no-parity --steps 10 --warmup 3 --kernel-table > $out/bench_shard160.json 2> $out/bench_shard160.err; grep -A8 "^--- shard160" $out/bench_shard160.err
 timeout 200 python scripts/vae_bench.py > $out/vae_bench.json 2>&1; cat $out/vae_bench.json
 timeout 200 python scripts/upsampler_bench.py 2>&1 | tail -1 > $out/upsampler_bench.json; cat $out/upsampler_bench.json
 [ "$2" = "skip-ncu" ] && exit 0
@@ -34,6 +36,8 @@ echo "gemm full rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base function -k 'regex:^(attention|norm_modulate|qknorm_rope)' -s 20 -c 6 \
     -o $out/others $CMD2 > $out/ncu_others.log 2>&1
 echo "others full rc=$?"
+LTXB_BENCH_VARIANTS=small_m LTXB_BENCH_PACKED=0 timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_small_m_kernel -s 10 -c 2 -o $out/gemm_few_rows python scripts/gemm_small_m_bench.py 160x16384x4096 > $out/ncu_gemm_few_rows.log 2>&1
+echo "few-row gemm full rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:attention_pair -s 2 -c 1 -o $out/attn_5184 python scripts/attn_one.py 1 5184 5184 32 128 5 > $out/ncu_attn_5184.log 2>&1
 echo "attention 5184 full rc=$?"
 ls -la $out
