@@ -117,7 +117,8 @@ def test_gemm_contiguous_stream_k_epilogues(mode):
 # token ranges (M > 256), K down to one k-block per split.
 WS_SHAPES = [(160, 4096, 4096), (160, 12288, 4096), (160, 16384, 4096), (160, 4096, 16384), (68, 2048, 2048), (136, 2048, 8192),
              (1, 4096, 1024), (2, 36864, 4096), (16, 256, 64), (200, 272, 1024), (256, 4096, 4096), (255, 1040, 512),
-             (320, 4096, 4096), (320, 16384, 4096), (512, 4096, 4096), (257, 784, 256), (500, 12288, 4096)]
+             (320, 4096, 4096), (320, 16384, 4096), (512, 4096, 4096), (257, 784, 256), (500, 12288, 4096),
+             (200, 1024, 27648), (136, 512, 13824), (200, 128, 3456)]  # + VAE decoder convolutions in row chunks: K = 27 * C
 
 
 @pytest.mark.parametrize("M,N,K", WS_SHAPES)

@@ -157,8 +157,11 @@ def test_decoder_chunked_rows_and_errors(decoder):
     finally:
         type(model).max_rows_per_chunk = old
     model.decode_noise_scale = 0.025
-    # (not bit-equal: a 200-row chunk runs the few-row GEMM kernel, whose k-range splits add in a different order)
-    assert rel_l2(chunked, full) < 1e-5
+    # Not bit-equal: a 200-row chunk runs the few-row GEMM kernel, whose k-range splits add in a different order, and every
+    # layer rounds its activations to bf16 operands again — a last-bit difference in f32 flips a bf16 rounding here and
+    # there (measured 1.5e-3 over the whole decoder; the decoder itself sits 6.7e-3 from the reference's output).  The
+    # few-row kernel at these K = 27 * C shapes is checked against fp32 in tests/test_gpu_kernels.py.
+    assert rel_l2(chunked, full) < 4e-3 and cosine(chunked, full) > 0.9999
     with pytest.raises(_lib.LtxbError):
         model(x.cpu())
     with pytest.raises(ValueError):
