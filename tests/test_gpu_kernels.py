@@ -38,7 +38,8 @@ def gemm_case(M, N, K, mode, pair=-1, bn=0, seed=0):
         kw = dict(resid=out, gate=gsl, gate_table=table, gate_row_div=div)
     ops.gemm(a, w, bias, out, mode=mode, block_n=bn, cta_pair=pair, **kw)
     torch.cuda.synchronize()
-    tol = 2e-5 if out.dtype == torch.float32 else 4e-3  # fp32 out: summation order only; bf16 out: output rounding
+    # fp32 out: summation order only (of the kernel's and of the reference's own fp32 matmul: grows ~sqrt(K)); bf16 out: output rounding
+    tol = 2e-5 * max(1.0, (K / 16384) ** 0.5) if out.dtype == torch.float32 else 4e-3
     err = rel_l2(out.float(), ref)
     assert torch.isfinite(out.float()).all() and err <= tol, f"gemm M={M} N={N} K={K} mode={mode} pair={pair} bn={bn}: {err:.3e}"
     return out
