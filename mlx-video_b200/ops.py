@@ -19,10 +19,14 @@ launches = 0          # kernels launched by the library since import (refreshed 
 _profile = None       # optional list: when set, every launch is bracketed by CUDA events -> (name, flops_or_bytes, start, end)
 
 
+_profile_shapes: list = []  # (M, N, K) of every ltxb_gemm_bf16 launch recorded while profiling
+
+
 def profile(enable: bool):
     """Per-launch CUDA-event timing on the launching stream (bench.py's roofline leg). Returns the record list."""
-    global _profile
+    global _profile, _profile_shapes
     _profile = [] if enable else None
+    _profile_shapes = []
     return _profile
 
 
@@ -42,6 +46,8 @@ def _call(name: str, work: float, *args) -> None:
     launches = lib.ltxb_kernel_launches()
     check(rc, name)
     _profile.append((name, work, e0, e1))
+    if name == "ltxb_gemm_bf16":  # (M, N, K) of the launch, for the weight-stream roofline of few-row steps
+        _profile_shapes.append(tuple(int(v) for v in args[6:9]))
 
 
 def _stream() -> int:

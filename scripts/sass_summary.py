@@ -9,7 +9,7 @@ import sys
 
 lib = sys.argv[1] if len(sys.argv) > 1 else "mlx-video_b200/csrc/libltxb.so"
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
-want = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMAPF", "UBLKCP", "SYNCS", "UCGABAR", "MUFU", "FFMA2", "HMMA", "ACQBULK", "USETMAXREG", "ELECT"]
+want = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTMAPF", "UBLKCP", "SYNCS", "UCGABAR", "MUFU", "FFMA2", "HMMA", "ACQBULK", "USETMAXREG", "ELECT"]
 kernels, cur = collections.OrderedDict(), None
 for line in txt.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
@@ -25,7 +25,7 @@ for line in txt.splitlines():
                 cur[w] += 1
 demangled = subprocess.run(["c++filt"], input="\n".join(kernels), capture_output=True, text=True).stdout.splitlines()
 print(f"SASS mnemonic counts per kernel, `cuobjdump -sass {lib}` (sm_100a).  UTCHMMA = tcgen05.mma, UTCBAR = tcgen05.commit, LDTM / STTM = "
-      "tcgen05.ld / st, UTMALDG = TMA tensor load, SYNCS = mbarrier ops, UCGABAR = cluster barrier, USETMAXREG = setmaxnreg; HMMA (mma.sync) must be 0.\n")
+      "tcgen05.ld / st, UTMALDG / UTMASTG / UTMAREDG = TMA tensor load / store / reduce-add, SYNCS = mbarrier ops, UCGABAR = cluster barrier, USETMAXREG = setmaxnreg; HMMA (mma.sync) must be 0.\n")
 print("| kernel | instructions | " + " | ".join(want) + " |")
 print("|---|---|" + "---|" * len(want))
 tot = collections.Counter()
