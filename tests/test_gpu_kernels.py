@@ -132,7 +132,7 @@ def test_gemm_small_m_kernel(M, N, K):
         a = gemm_case(M, N, K, _lib.EPI_BIAS_F32, pair=4, bn=splits)
         b = gemm_case(M, N, K, _lib.EPI_BIAS_F32, pair=4, bn=splits)
         assert torch.equal(a, b), f"small-M kernel with {splits} splits differs between two runs"
-        assert rel_l2(a, auto) < 2e-5
+        assert rel_l2(a, auto) < 2e-5 * max(1.0, (K / 16384) ** 0.5)  # summation order only
     if M <= 512:  # what the library picks on its own for few rows
         assert torch.equal(auto, gemm_case(M, N, K, _lib.EPI_BIAS_F32))
 
