@@ -19,6 +19,9 @@ LIB_PATH = Path(os.environ["LTXB_LIB"]) if os.environ.get("LTXB_LIB") else CSRC 
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 
+ABI_VERSION = 4  # include/ltxb.h: ltxb_abi_version()
+
+
 class PeerSync(C.Structure):
     """Mirror of ``struct ltxb_peer_sync`` (the folded cross-GPU flag barrier)."""
 
@@ -134,6 +137,8 @@ def _load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
         fn.restype = restype
         fn.argtypes = argtypes
+    if lib.ltxb_abi_version() != ABI_VERSION:  # struct layouts below (Epilogue, PeerSync) belong to exactly this version
+        raise ImportError(f"{LIB_PATH} has ABI version {lib.ltxb_abi_version()}, this binding is for {ABI_VERSION}: rebuild it (make -C {CSRC})")
     return lib
 
 

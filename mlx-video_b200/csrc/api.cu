@@ -97,7 +97,7 @@ int num_sms() {
 
 extern "C" const char* ltxb_last_error(void) { return ltxb::g_err; }
 
-extern "C" int ltxb_abi_version(void) { return 3; }
+extern "C" int ltxb_abi_version(void) { return 4; }  // 4: ltxb_epilogue grew flags + peer_sync, ltxb_gemm_qw_bf16, ltxb_attention_fwd_peers_sync
 
 extern "C" int64_t ltxb_kernel_launches(void) { return ltxb::g_kernel_launches.load(std::memory_order_relaxed); }
 

@@ -151,16 +151,16 @@ def test_gemm_small_m_kernel_group_major_rows_and_strides():
     """The A operand as the Ulysses gather all-to-all delivers it ([K / g][M][g], read in place through a 3-D map), a
     gate looked up through a row index, and outputs / residuals that are column slices of wider tensors."""
     g = torch.Generator(device=DEV).manual_seed(11)
-    M, N, K, gc = 160, 4096, 4096, 512
-    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
-    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
-    bias = torch.randn(N, device=DEV, generator=g)
-    a_grouped = a.view(M, K // gc, gc).permute(1, 0, 2).contiguous()
-    ref = a.float() @ w.float().T + bias
-    for pair in (4, -1):
-        out = torch.empty(M, N, device=DEV, dtype=torch.float32)
-        ops.gemm(a_grouped, w, bias, out, mode=_lib.EPI_BIAS_F32, a_group_cols=gc, cta_pair=pair)
-        assert rel_l2(out, ref) < 2e-5
+    for M, N, K, gc in [(320, 4096, 4096, 1024), (160, 4096, 4096, 512)]:  # 4 / 8 sequence-parallel ranks (two MMAs per k-slice at 320)
+        a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+        w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+        bias = torch.randn(N, device=DEV, generator=g)
+        a_grouped = a.view(M, K // gc, gc).permute(1, 0, 2).contiguous()
+        ref = a.float() @ w.float().T + bias
+        for pair in (4, -1):
+            out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+            ops.gemm(a_grouped, w, bias, out, mode=_lib.EPI_BIAS_F32, a_group_cols=gc, cta_pair=pair)
+            assert rel_l2(out, ref) < 2e-5
     wide = torch.randn(M, 3 * N, device=DEV, generator=g)
     resid = wide[:, N:2 * N]
     before = wide.clone()
