@@ -13,13 +13,18 @@
 //   * each CTA of the pair stages its own 128 weight rows (16 KB per k-block, from HBM) and HALF of the token rows
 //     (from L2) — the pair MMA reads the B operand from both CTAs' shared memory, which halves the L2 -> SM traffic of
 //     re-reading the activations per weight tile;
-//   * one (weight tile, k-range) per CTA pair, no persistence: grid = tiles x splits pairs, all co-resident, two CTAs
-//     per SM when the token count fits 256 TMEM columns (2 x 4 stages x 16 KB of weights in flight per SM);
+//   * one (weight tile, k-range) per CTA pair, no persistence: grid = tiles x splits pairs, all co-resident; one CTA per SM
+//     with all of its shared memory as stages (8 x 26 KB at 160 tokens) when that still fills the machine, else two per SM
+//     (the accumulators of both fit 2 x 256 TMEM columns) for twice the pair slots, i.e. more k-range splits;
 //   * split-K is a reduce-scatter through L2: every pair parks the 8-token chunks it does not own, all pairs of a tile
 //     meet at a counter, and each adds the others' parts to the chunks it owns, in split order (run-to-run
 //     reproducible), then applies the fused epilogue;
-//   * in the epilogue a thread owns one OUTPUT COLUMN (its TMEM lane) and walks the tokens, so the 32 lanes of a warp
-//     store 32 consecutive columns of one row: coalesced 64 / 128-byte stores instead of one row per lane.
+//   * in the epilogue (eight warps) a thread owns one OUTPUT COLUMN (its TMEM lane) and walks the tokens; the finished
+//     8-token chunks are staged in the operand stages (idle by then) and handed to the TMA: a plain tensor store, or for
+//     the residual epilogue an element-wise ADD into the residual stream (out += (acc + bias) * gate, one add per element);
+//   * weights the host marks constant (LTXB_GEMM_CONST_W) are requested before the programmatic-launch wait, so the first
+//     stages fill under the stream predecessor's tail; the MMA issuer is a warp-uniform loop with one elected lane.
+// gemm_small_m_packed_kernel (further down) is the same product over MLX affine-quantised weights kept packed in HBM.
 #include "common.cuh"
 #include "gemm_small_m.cuh"
 #include "peer_sync.cuh"
