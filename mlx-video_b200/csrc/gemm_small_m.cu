@@ -908,15 +908,15 @@ int launch_gemm_small_m(const void* A, int64_t lda, const void* W, int64_t ldw, 
     return s;
   };
   // One CTA per SM with all of its shared memory as stages (8 x 26 KB at 160 tokens), or two per SM with half each (when
-  // both accumulators fit 256 TMEM columns): two per SM doubles the pair slots, i.e. allows more k-range splits, but every
-  // split adds reduce-scatter traffic and the deeper pipeline streams faster.  Measured at 160 tokens
-  // (profiles/r2/gemm_small_m.md): one per SM wins whenever it still fills the machine (>= 85 % of the SM pairs busy).
+  // both accumulators fit 256 TMEM columns).  Two per SM doubles the pair slots, i.e. allows more k-range splits, but every
+  // split adds reduce-scatter traffic and a meeting point, and the deeper pipeline streams faster: measured at 68 / 160
+  // tokens (profiles/r2/gemm/few_row_kernel_per_sm_sweep.txt) one per SM wins or ties on every shape whose weight tiles fit
+  // the SM pairs in one go — even the qkv shape, 48 tiles on 74 pairs without any split: 25.4 us against 27.6 with three
+  // splits on two CTAs per SM — and two per SM only when there are more tiles than pairs (AdaLN, 144 tiles: 48.7 against 51.9).
   const int pairs = sms / 2;
   int per_sm = 1;
   if (p.tmem_cols <= 256 && (113 * 1024 - 1024 - kWsHeader) / stage_bytes >= 3) {
-    const int s1 = splits_for(pairs);
-    const bool fills = tiles <= pairs && tiles * s1 * 100 >= pairs * 85;
-    per_sm = (env_per_sm == 1 || env_per_sm == 2) ? env_per_sm : (fills ? 1 : 2);
+    per_sm = (env_per_sm == 1 || env_per_sm == 2) ? env_per_sm : (tiles <= pairs ? 1 : 2);
   }
   const size_t budget = (per_sm == 2 ? 113 * 1024 : 232448) - 1024 - kWsHeader;
   p.num_stages = static_cast<int>(std::min<size_t>(w_bits != 16 ? kPkMaxStages : kWsMaxStages, budget / stage_bytes));
