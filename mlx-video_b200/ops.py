@@ -194,7 +194,7 @@ def gemm_qw(
     const_w: bool = False,
     peer_sync=None,
 ) -> torch.Tensor:
-    """out = epilogue(a @ dequant(packed, scales, biases).T) for FEW rows (M <= 512) with the MLX affine-quantised weight
+    """out = epilogue(a @ dequant(packed, scales, biases).T) for FEW rows (M <= 256) with the MLX affine-quantised weight
     kept packed in HBM (``ltxb_gemm_qw_bf16``): uint32 / int32 [N, K*bits/32], scales / biases bf16 or f32 [N, K/group_size].
     Bit-identical to ``dequant_affine`` followed by ``gemm(..., cta_pair=4, block_n=splits)``."""
     _prep(a)
