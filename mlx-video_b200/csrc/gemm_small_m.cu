@@ -449,24 +449,28 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 #endif
 
   if (warp == 0) {
-    // ===================== TMA producer: this CTA's 128 weight rows + its half of the token rows =====================
-    if (lane == 0) {
+    // ===================== TMA producer, weight stream: this CTA's 128 weight rows per k-block =====================
+    // Two producer warps — this one for the weights, warp 2 (an epilogue warp, idle during the main loop) for the token
+    // rows: one lone producer spent ~600 cycles per k-block on its own instruction stream (barrier poll, expect_tx, two TMA
+    // issues; LTXB_WS_DEBUG=64 role profile), which paced the kernel.  Warp-uniform loops, one elected lane issues, every
+    // operand a 32-bit shared-space address or a running counter.
+    {
+      const bool issuer = elect_one();
+      const uint32_t tiles_u32 = smem_u32(tiles), full_u32 = smem_u32(&hdr->full[0]);
+      const uint32_t full_leader = mapa_u32(full_u32, 0);  // both CTAs report their bytes on the leader's barrier
       uint32_t stage = 0, phase = 0;
-      const int n0 = n0_w;
+      int ka = kb0 * kWsBlockK;
       for (int kb = kb0; kb < kb1; ++kb) {
         const bool w_done = (kb - kb0) < prefetched;  // this stage's weight tile went out before the wait
-        if (!w_done) mbar_wait(&hdr->empty[stage], phase ^ 1);
-        uint8_t* sw = tiles + static_cast<size_t>(stage) * stage_bytes;
-        uint8_t* sx = sw + kWsWBytes;
-        const int ka = kb * kWsBlockK;
-        const uint32_t bar = mapa_u32(smem_u32(&hdr->full[stage]), 0);  // both CTAs report their bytes on the leader's barrier
-        if (is_leader && !w_done) mbar_arrive_expect_tx(&hdr->full[stage], stage_bytes * 2);
-        if (!w_done) tma_load_2d_pair(sw, &tmap_w, bar, ka, n0);
-        for (int j = 0; j < p.n_mma; ++j) {
-          const int row0 = j * mma_n + static_cast<int>(cta_rank) * box_rows;
-          if (p.a_group_cols > 0) tma_load_3d_pair(sx + j * x_box_bytes, &tmap_x, bar, ka % p.a_group_cols, row0, ka / p.a_group_cols);
-          else tma_load_2d_pair(sx + j * x_box_bytes, &tmap_x, bar, ka, row0);
+        if (!w_done) {
+          mbar_wait(&hdr->empty[stage], phase ^ 1);
+          if (issuer) {
+            if (is_leader) mbar_arrive_expect_tx_u32(full_u32 + stage * 8, stage_bytes * 2);
+            tma_load_2d_pair_u32(tiles_u32 + stage * stage_bytes, &tmap_w, full_leader + stage * 8, ka, n0_w);
+          }
+          __syncwarp();
         }
+        ka += kWsBlockK;
         if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
       }
       // neither CTA of the pair may retire while commit arrivals for its barriers are still in flight
@@ -507,6 +511,31 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       __syncwarp();
     }
   } else {
+    if (warp == 2) {
+      // ===================== TMA producer, token-row stream: this CTA's half of the token rows per k-block =====================
+      // (their bytes are counted on the leader's barrier by the weight stream's expect_tx; a complete_tx that lands before
+      // that arrive is fine — the phase cannot complete without it)
+      const bool issuer = elect_one();
+      const uint32_t tiles_u32 = smem_u32(tiles), full_leader = mapa_u32(smem_u32(&hdr->full[0]), 0);
+      uint32_t stage = 0, phase = 0;
+      int ka = kb0 * kWsBlockK, gcol = 0, ggrp = 0;  // head-group-major token rows: column inside the group, group index
+      if (p.a_group_cols > 0) gcol = ka % p.a_group_cols, ggrp = ka / p.a_group_cols;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&hdr->empty[stage], phase ^ 1);
+        if (issuer) {
+          const uint32_t sx = tiles_u32 + stage * stage_bytes + kWsWBytes, bar = full_leader + stage * 8;
+          for (int j = 0; j < p.n_mma; ++j) {
+            const int row0 = j * mma_n + static_cast<int>(cta_rank) * box_rows;
+            if (p.a_group_cols > 0) tma_load_3d_pair_u32(sx + j * x_box_bytes, &tmap_x, bar, gcol, row0, ggrp);
+            else tma_load_2d_pair_u32(sx + j * x_box_bytes, &tmap_x, bar, ka, row0);
+          }
+        }
+        __syncwarp();
+        ka += kWsBlockK;
+        if (p.a_group_cols > 0 && (gcol += kWsBlockK) == p.a_group_cols) gcol = 0, ++ggrp;
+        if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
+      }
+    }
     ws_epilogue<kEpi>(p, &tmap_out, &hdr->tmem_full, tiles, static_cast<uint32_t>(num_stages) * stage_bytes, tmem_base, tile, split,
                       cta_rank, warp, lane, dbg);
   }
@@ -545,11 +574,14 @@ constexpr int kPkMaxSlots = 14;  // ring slots: as many as fit behind the accumu
 constexpr int kPkSlotCols = kWsBlockK / 2;  // 64 bf16 of a weight row = 32 TMEM columns
 constexpr int kPkAccCols = 256;             // accumulator columns in front of the slot ring (m_pad <= 256)
 constexpr int kPkMaxStages = 20;
+constexpr int kPkGroups = 4;                           // expanding warp groups (four warps each), one k-block in flight per group
+constexpr int kPkTokenWarp = 2 + 4 * kPkGroups;        // warp 18: the token-row TMA stream
+constexpr int kPkThreads = (kPkTokenWarp + 1) * 32;    // warp 0 packed-weight TMA stream, warp 1 MMA issuer, warps 2..17 expand (2..9 also run the epilogue), warp 18
 struct PkSmemHeader {
   uint64_t full[kPkMaxStages];      // (leader's) the token rows of both CTAs have landed
   uint64_t raw_full[kPkMaxStages];  // this CTA's packed tile has landed
   uint64_t empty[kPkMaxStages];     // the MMAs that read the stage have completed (both CTAs; the tile was expanded before them)
-  uint64_t a_full[kPkMaxSlots];     // (leader's) the expanding warps of both CTAs have filled the slot: 16 arrivals
+  uint64_t a_full[kPkMaxSlots];     // (leader's) the owning group's four warps of both CTAs have filled the slot: 8 arrivals
   uint64_t a_empty[kPkMaxSlots];    // the MMAs that read the slot have completed (both CTAs)
   uint64_t tmem_full;
   uint32_t tmem_base;
@@ -557,7 +589,7 @@ struct PkSmemHeader {
 static_assert(sizeof(PkSmemHeader) <= kWsHeader, "header overflow");
 
 template <int kEpi, int kWBits>
-__global__ void __launch_bounds__(kWsThreads, 1)
+__global__ void __launch_bounds__(kPkThreads, 1)
 gemm_small_m_packed_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                            const __grid_constant__ CUtensorMap tmap_out, const WsParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -598,7 +630,7 @@ gemm_small_m_packed_kernel(const __grid_constant__ CUtensorMap tmap_x, const __g
         mbar_init(&hdr->empty[s], 1);
       }
       for (int s = 0; s < num_slots; ++s) {
-        mbar_init(&hdr->a_full[s], 2 * 8);
+        mbar_init(&hdr->a_full[s], 2 * 4);  // the four warps of the owning group, in both CTAs
         mbar_init(&hdr->a_empty[s], 1);
       }
       mbar_init(&hdr->tmem_full, 1);
@@ -627,32 +659,57 @@ gemm_small_m_packed_kernel(const __grid_constant__ CUtensorMap tmap_x, const __g
   long long dbg[2] = {0, 0};
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer, packed-weight stream (warp-uniform loop, one elected lane issues) =====================
+    {
+      const bool issuer = elect_one();
+      const uint32_t tiles_u32 = smem_u32(tiles), raw_full_u32 = smem_u32(&hdr->raw_full[0]);
       uint32_t stage = 0, phase = 0;
       long long w_empty = 0, t_loop = clock64();
       for (int kb = kb0; kb < kb1; ++kb) {
         const bool w_done = (kb - kb0) < prefetched;
-        if (!w_done) WS_TIMED_WAIT(w_empty, mbar_wait(&hdr->empty[stage], phase ^ 1));
-        uint8_t* sx = tiles + static_cast<size_t>(stage) * stage_bytes;
-        const int ka = kb * kWsBlockK;
         if (!w_done) {
-          mbar_arrive_expect_tx(&hdr->raw_full[stage], kRawBytes);
-          tma_load_2d(sx + x_bytes, &tmap_w, &hdr->raw_full[stage], kb * static_cast<int>(kRawRowBytes), n0_w);
+          WS_TIMED_WAIT(w_empty, mbar_wait(&hdr->empty[stage], phase ^ 1));
+          if (issuer) {
+            mbar_arrive_expect_tx_u32(raw_full_u32 + stage * 8, kRawBytes);
+            tma_load_2d_u32(tiles_u32 + stage * stage_bytes + x_bytes, &tmap_w, raw_full_u32 + stage * 8, kb * static_cast<int>(kRawRowBytes), n0_w);
+          }
+          __syncwarp();
         }
-        if (is_leader) mbar_arrive_expect_tx(&hdr->full[stage], x_bytes * 2);  // both CTAs report on the leader's barrier
-        const uint32_t bar = mapa_u32(smem_u32(&hdr->full[stage]), 0);
-        const int row0 = static_cast<int>(cta_rank) * box_rows;
-        if (p.a_group_cols > 0) tma_load_3d_pair(sx, &tmap_x, bar, ka % p.a_group_cols, row0, ka / p.a_group_cols);
-        else tma_load_2d_pair(sx, &tmap_x, bar, ka, row0);
         if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
       }
 #ifdef LTXB_WS_DEBUG
-      if (WS_DBG(64) && blockIdx.x == 0) printf("ws roles: producer loop %lld cycles, %lld waiting for empty stages (%d k-blocks)\n", clock64() - t_loop, w_empty, kb1 - kb0);
+      if (WS_DBG(64) && blockIdx.x == 0 && lane == 0) printf("ws roles: weight producer loop %lld cycles, %lld waiting for empty stages (%d k-blocks)\n", clock64() - t_loop, w_empty, kb1 - kb0);
 #endif
       (void)t_loop, (void)w_empty;
       for (int s = 0; s < num_stages; ++s) {  // no CTA retires while commit arrivals for its barriers are in flight
         mbar_wait(&hdr->empty[stage], phase ^ 1);
+        if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == kPkTokenWarp) {
+    // ===================== TMA producer, token-row stream (a warp of its own: one producer for both streams spent ~600
+    // cycles per k-block on its instruction stream and paced the kernel) =====================
+    {
+      const bool issuer = elect_one();
+      const uint32_t tiles_u32 = smem_u32(tiles), full_u32 = smem_u32(&hdr->full[0]);
+      const uint32_t full_leader = mapa_u32(full_u32, 0);  // both CTAs report their token-row bytes on the leader's barrier
+      const int row0 = static_cast<int>(cta_rank) * box_rows;
+      uint32_t stage = 0, phase = 0;
+      int ka = kb0 * kWsBlockK, gcol = 0, ggrp = 0;
+      if (p.a_group_cols > 0) gcol = ka % p.a_group_cols, ggrp = ka / p.a_group_cols;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&hdr->empty[stage], phase ^ 1);
+        if (issuer) {
+          const uint32_t sx = tiles_u32 + stage * stage_bytes;
+          const bool skip_x = WS_DBG(128) && kb != kb0;  // (timing experiment: token rows loaded once)
+          if (is_leader) mbar_arrive_expect_tx_u32(full_u32 + stage * 8, skip_x ? 0u : x_bytes * 2);
+          if (skip_x) {
+          } else if (p.a_group_cols > 0) tma_load_3d_pair_u32(sx, &tmap_x, full_leader + stage * 8, gcol, row0, ggrp);
+          else tma_load_2d_pair_u32(sx, &tmap_x, full_leader + stage * 8, ka, row0);
+        }
+        __syncwarp();
+        ka += kWsBlockK;
+        if (p.a_group_cols > 0 && (gcol += kWsBlockK) == p.a_group_cols) gcol = 0, ++ggrp;
         if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
       }
     }
@@ -691,18 +748,22 @@ gemm_small_m_packed_kernel(const __grid_constant__ CUtensorMap tmap_x, const __g
     }
   } else {
     // ===================== expanding warps: packed tile -> bf16 A-operand slot in TMEM =====================
-    const int quarter = warp & 3, khalf = (warp - 2) >> 2;
+    // Four GROUPS of four warps (one per TMEM lane quarter); group g expands every fourth k-block, whole weight rows (64
+    // levels per thread), into that k-block's slot.  A trip is a chain of barrier polls, a shared-memory read, the
+    // arithmetic, tcgen05.st + wait, fences and a remote arrive: ~1 000 cycles per k-block however few levels a thread
+    // expands (measured with 8 and with 16 warps sharing ONE k-block: same time) — four k-blocks in flight overlap it.
+    const int quarter = warp & 3, grp = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;  // weight row of the tile = TMEM lane
     const long long row_abs = static_cast<long long>(n0_w) + row;
     const bool row_ok = row_abs < p.N;
-    // (scale, bias) of this thread's 32 columns: 16 bytes (8 bf16 / 4 f32 groups of the row) at a time, one chunk AHEAD
+    // (scale, bias) of the row: 16 bytes (8 bf16 / 4 f32 groups) at a time; the chunk of the group's NEXT k-block is requested
+    // one trip ahead (a load issued under a saturated HBM stream takes microseconds to come back)
     const int esz = p.aux_f32 ? 4 : 2;
     const int chunk_groups = 16 / esz;
     const int groups_per_row = p.K / p.group;
     const bool chunked = (groups_per_row % chunk_groups == 0) && ((p.lds * esz) % 16 == 0) &&
                          ((reinterpret_cast<uintptr_t>(p.scales) | reinterpret_cast<uintptr_t>(p.biases)) % 16 == 0);
     const int group_shift = p.group == 32 ? 5 : (p.group == 64 ? 6 : 7);
-    auto group_of = [&](int kb) { return (kb * kWsBlockK + khalf * 32) >> group_shift; };
     auto load_chunk = [&](int c, uint4& S, uint4& B) {
       S = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0, 0);
       if (!row_ok || c * chunk_groups >= groups_per_row) return;
@@ -719,10 +780,10 @@ gemm_small_m_packed_kernel(const __grid_constant__ CUtensorMap tmap_x, const __g
       const uint32_t wd = (i & 4) ? b : a;
       return __uint_as_float((i & 1) ? (wd & 0xffff0000u) : (wd << 16));
     };
-    auto load_scalar = [&](int kb, float& sc, float& bi) {  // layouts the 16-byte chunks do not fit
+    auto load_scalar = [&](int g, float& sc, float& bi) {  // layouts the 16-byte chunks do not fit
       sc = 0.f, bi = 0.f;
       if (!row_ok) return;
-      const long long a = row_abs * p.lds + group_of(kb);
+      const long long a = row_abs * p.lds + g;
       if (p.aux_f32) {
         sc = __ldg(static_cast<const float*>(p.scales) + a);
         bi = __ldg(static_cast<const float*>(p.biases) + a);
@@ -732,116 +793,93 @@ gemm_small_m_packed_kernel(const __grid_constant__ CUtensorMap tmap_x, const __g
       }
     };
     const uint32_t tiles_u32 = smem_u32(tiles);
-    const uint32_t raw_thread_off = x_bytes + row * kRawRowBytes + khalf * (kRawRowBytes / 2);
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ring_col + khalf * (kPkSlotCols / 2);
+    const uint32_t raw_thread_off = x_bytes + row * kRawRowBytes;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ring_col;
     const uint32_t magic = p.magic;  // 0x4B000000 from a kernel parameter, i.e. in a REGISTER: PRMT then takes its selector as the
                                      // immediate (one instruction per level; a literal makes ptxas re-materialise the selectors)
-    uint32_t stage = 0, phase = 0, slot = 0, sphase = 0;
+    const int nkb = kb1 - kb0;
     uint4 s_cur, b_cur, s_next, b_next;
-    int cur_chunk = group_of(kb0) / chunk_groups;
-    if (chunked) {
+    int cur_chunk = -1, next_chunk = -1;
+    if (chunked && grp < nkb) {
+      cur_chunk = ((kb0 + grp) * kWsBlockK >> group_shift) / chunk_groups;
       load_chunk(cur_chunk, s_cur, b_cur);
-      load_chunk(cur_chunk + 1, s_next, b_next);
     }
     long long w_raw = 0, w_aempty = 0, w_st = 0, t_loop = clock64();
-    auto aux_of = [&](int kb, float& sc, float& bi) {
+    for (int i = grp; i < nkb; i += kPkGroups) {
+      const int kb = kb0 + i;
+      const uint32_t stage = i % num_stages, phase = (i / num_stages) & 1, slot = i % num_slots, sphase = (i / num_slots) & 1;
+      const int ga = (kb * kWsBlockK) >> group_shift, gb = (kb * kWsBlockK + 32) >> group_shift;  // groups of columns 0-31 / 32-63
+      float sca, bia, scb, bib;
       if (chunked) {
-        const int g = group_of(kb);
-        if (g / chunk_groups != cur_chunk) {
-          s_cur = s_next, b_cur = b_next;
-          ++cur_chunk;
-          load_chunk(cur_chunk + 1, s_next, b_next);
-        }
-        const int gi = g - cur_chunk * chunk_groups;
-        sc = pick(s_cur, gi), bi = pick(b_cur, gi);
-      } else {
-        load_scalar(kb, sc, bi);
-      }
-    };
-    // level -> float through the 2^23 trick (bits 0x4B0000qq = 8388608 + q, exact), then scales * q + biases with the
-    // roundings of ltxb_dequant_affine_bf16: the product of a bf16 scale and an 8-bit level is exact in f32, so one fused
-    // multiply-add rounds like its multiply + add; f32 scales keep the two instructions
-    auto expand = [&](const uint32_t (&w)[kWBits], float sc, float bi, uint32_t (&packed)[16], auto fused) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float v[8];
-        if constexpr (kWBits == 4) {
-          const uint32_t lo = w[j] & 0x0F0F0F0Fu, hi = (w[j] >> 4) & 0x0F0F0F0Fu;  // even / odd levels, one per byte
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float q = __uint_as_float(__byte_perm((e & 1) ? hi : lo, magic, 0x7540u | (e >> 1))) - 8388608.0f;
-            v[e] = decltype(fused)::value ? __fmaf_rn(sc, q, bi) : __fadd_rn(__fmul_rn(sc, q), bi);
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float q = __uint_as_float(__byte_perm(w[2 * j + (e >> 2)], magic, 0x7540u | (e & 3))) - 8388608.0f;
-            v[e] = decltype(fused)::value ? __fmaf_rn(sc, q, bi) : __fadd_rn(__fmul_rn(sc, q), bi);
+        const int c = ga / chunk_groups;
+        if (c != cur_chunk) s_cur = s_next, b_cur = b_next, cur_chunk = c;  // (requested one trip ago)
+        if (i + kPkGroups < nkb) {
+          const int cn = (((kb + kPkGroups) * kWsBlockK) >> group_shift) / chunk_groups;
+          if (cn != cur_chunk && cn != next_chunk) {
+            load_chunk(cn, s_next, b_next);
+            next_chunk = cn;
           }
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) packed[4 * j + e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
-      }
-    };
-    auto load_raw = [&](uint32_t stg, uint32_t (&w)[kWBits]) {
-      const uint32_t st = tiles_u32 + stg * stage_bytes;
-      lds128(st + raw_thread_off, w[0], w[1], w[2], w[3]);
-      if constexpr (kWBits == 8) lds128(st + raw_thread_off + 16, w[4], w[5], w[6], w[7]);
-    };
-    // TWO k-blocks per trip: one trip is a chain of barrier polls, a shared-memory read, the expansion, a tensor-memory
-    // store and an arrive (~600 cycles of latency before any arithmetic, measured with LTXB_WS_DEBUG=64) — paired, the
-    // two chains overlap and the 64 independent level -> bf16 chains give the schedulers something to interleave
-    for (int kb = kb0; kb < kb1; kb += 2) {
-      const bool two = kb + 1 < kb1;
-      float sc0, bi0, sc1 = 0.f, bi1 = 0.f;
-      aux_of(kb, sc0, bi0);
-      if (two) aux_of(kb + 1, sc1, bi1);
-      const uint32_t stage0 = stage, phase0 = phase, slot0 = slot, sphase0 = sphase;
-      if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
-      if (++slot == static_cast<uint32_t>(num_slots)) slot = 0, sphase ^= 1;
-      const uint32_t stage1 = stage, phase1 = phase, slot1 = slot, sphase1 = sphase;
-      if (two) {
-        if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
-        if (++slot == static_cast<uint32_t>(num_slots)) slot = 0, sphase ^= 1;
-      }
-      uint32_t w0[kWBits], w1[kWBits], packed0[16], packed1[16];
-      WS_TIMED_WAIT(w_raw, mbar_wait(&hdr->raw_full[stage0], phase0));
-      load_raw(stage0, w0);
-      if (two) {
-        WS_TIMED_WAIT(w_raw, mbar_wait(&hdr->raw_full[stage1], phase1));
-        load_raw(stage1, w1);
+        sca = pick(s_cur, ga - c * chunk_groups), bia = pick(b_cur, ga - c * chunk_groups);
+        scb = pick(s_cur, gb - c * chunk_groups), bib = pick(b_cur, gb - c * chunk_groups);
       } else {
-#pragma unroll
-        for (int i = 0; i < kWBits; ++i) w1[i] = 0;
+        load_scalar(ga, sca, bia);
+        load_scalar(gb, scb, bib);
       }
+      WS_TIMED_WAIT(w_raw, mbar_wait(&hdr->raw_full[stage], phase));
+      constexpr int kWords = kWBits * 2;  // packed words of one weight row per k-block: 8 (4-bit) or 16 (8-bit)
+      uint32_t w[kWords], packed[32];
+      const uint32_t st = tiles_u32 + stage * stage_bytes + raw_thread_off;
+#pragma unroll
+      for (int v = 0; v < kWords / 4; ++v) lds128(st + 16 * v, w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
 #ifdef LTXB_WS_DEBUG
       if (WS_DBG(32)) {  // timing experiment: no expansion arithmetic
 #pragma unroll
-        for (int i = 0; i < 16; ++i) packed0[i] = w0[i % kWBits], packed1[i] = w1[i % kWBits];
+        for (int v = 0; v < 32; ++v) packed[v] = w[v % kWords];
       } else
 #endif
-      if (p.aux_f32) {
-        expand(w0, sc0, bi0, packed0, std::false_type{});
-        expand(w1, sc1, bi1, packed1, std::false_type{});
-      } else {
-        expand(w0, sc0, bi0, packed0, std::true_type{});
-        expand(w1, sc1, bi1, packed1, std::true_type{});
+      {
+        // level -> float through the 2^23 trick (bits 0x4B0000qq = 8388608 + q, exact), then scales * q + biases with the
+        // roundings of ltxb_dequant_affine_bf16: the product of a bf16 scale and an 8-bit level is exact in f32, so one fused
+        // multiply-add rounds like its multiply + add; f32 scales keep the two instructions
+        auto expand = [&](auto fused) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {  // 8 levels per j
+            const float sc = j < 4 ? sca : scb, bi = j < 4 ? bia : bib;
+            float v[8];
+            if constexpr (kWBits == 4) {
+              const uint32_t lo = w[j] & 0x0F0F0F0Fu, hi = (w[j] >> 4) & 0x0F0F0F0Fu;  // even / odd levels, one per byte
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float q = __uint_as_float(__byte_perm((e & 1) ? hi : lo, magic, 0x7540u | (e >> 1))) - 8388608.0f;
+                v[e] = decltype(fused)::value ? __fmaf_rn(sc, q, bi) : __fadd_rn(__fmul_rn(sc, q), bi);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float q = __uint_as_float(__byte_perm(w[2 * j + (e >> 2)], magic, 0x7540u | (e & 3))) - 8388608.0f;
+                v[e] = decltype(fused)::value ? __fmaf_rn(sc, q, bi) : __fadd_rn(__fmul_rn(sc, q), bi);
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) packed[4 * j + e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+          }
+        };
+        if (p.aux_f32) expand(std::false_type{}); else expand(std::true_type{});
       }
-      // the MMAs that read these slots one ring turn ago have completed
-      WS_TIMED_WAIT(w_aempty, mbar_wait(&hdr->a_empty[slot0], sphase0 ^ 1); if (two) mbar_wait(&hdr->a_empty[slot1], sphase1 ^ 1));
+      // the MMAs that read this slot one ring turn ago have completed
+      WS_TIMED_WAIT(w_aempty, mbar_wait(&hdr->a_empty[slot], sphase ^ 1));
       tc_fence_after_sync();
-      WS_TIMED_WAIT(w_st, tmem_st_x16(t_lane + slot0 * kPkSlotCols, packed0); if (two) tmem_st_x16(t_lane + slot1 * kPkSlotCols, packed1);
-                    tmem_wait_st(); tc_fence_before_sync(); __syncwarp(); if (lane == 0) {
-                      mbar_arrive_remote(&hdr->a_full[slot0], 0);
-                      if (two) mbar_arrive_remote(&hdr->a_full[slot1], 0);
-                    });
+      WS_TIMED_WAIT(w_st, tmem_st_x32(t_lane + slot * kPkSlotCols, packed); tmem_wait_st(); tc_fence_before_sync(); __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(&hdr->a_full[slot], 0));
     }
 #ifdef LTXB_WS_DEBUG
     if (WS_DBG(64) && blockIdx.x == 0 && threadIdx.x == 64) printf("ws roles: expanding warp loop %lld cycles, %lld waiting for packed tiles, %lld for free slots, %lld in tcgen05.st + arrive\n", clock64() - t_loop, w_raw, w_aempty, w_st);
 #endif
     (void)t_loop, (void)w_raw, (void)w_aempty, (void)w_st;
-    ws_epilogue<kEpi>(p, &tmap_out, &hdr->tmem_full, tiles, static_cast<uint32_t>(num_stages) * stage_bytes, tmem_base, tile, split,
-                      cta_rank, warp, lane, dbg);
+    if (warp < 10)  // the first two groups are the eight epilogue warps (two per TMEM lane quarter)
+      ws_epilogue<kEpi>(p, &tmap_out, &hdr->tmem_full, tiles, static_cast<uint32_t>(num_stages) * stage_bytes, tmem_base, tile, split,
+                        cta_rank, warp, lane, dbg);
   }
 
   if (p.out_tma != 0 && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) tma_store_wait_read();
@@ -869,7 +907,7 @@ static int launch_ws(const CUtensorMap& tx, const CUtensorMap& tw, const CUtenso
   } else {
     auto kernel = gemm_small_m_packed_kernel<kEpi, kWBits>;
     if (configured.first()) LTXB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    LTXB_CUDA(launch_kernel(kernel, dim3(grid), dim3(kWsThreads), smem, stream, 2, tx, tw, to, p));
+    LTXB_CUDA(launch_kernel(kernel, dim3(grid), dim3(kPkThreads), smem, stream, 2, tx, tw, to, p));
   }
   return LTXB_OK;
 }
