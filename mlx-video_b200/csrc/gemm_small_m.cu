@@ -565,10 +565,14 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 //     stages in flight per SM.  That depth is the point: with a bf16 copy of the tile in every stage (first cut) only 7
 //     stages fit, and at a ~3 us round trip per stage the pipeline, not HBM, paced the kernel (measured: 49 us against the
 //     bf16 kernel's 29 us at 160 x 16384 x 4096, profiles/r2/gemm_small_m.md);
-//   * the eight epilogue warps, idle during the main loop, expand a tile in the arithmetic of ltxb_dequant_affine_bf16
-//     (bit-identical to dequantise-then-GEMM) and write it with tcgen05.st into a ring of A-operand slots in TENSOR MEMORY
-//     (one thread = one weight row = one TMEM lane: 32 columns per k-block, 8 slots behind the accumulator's 256 columns);
-//     the MMA reads A from TMEM (the form the attention kernel uses for P.V) and only the token rows from shared memory.
+//   * sixteen expanding warps — four groups of four (one warp per TMEM lane quarter), group g owning every fourth k-block —
+//     expand the tiles in the arithmetic of ltxb_dequant_affine_bf16 (bit-identical to dequantise-then-GEMM) and write them
+//     with tcgen05.st into a ring of A-operand slots in TENSOR MEMORY (one thread = one weight row = one TMEM lane: 32
+//     columns per k-block, up to 14 slots behind the accumulator's columns); the MMA reads A from TMEM (the form the
+//     attention kernel uses for P.V) and only the token rows from shared memory.  Groups on different k-blocks because a
+//     trip (barrier polls, shared-memory read, arithmetic, tcgen05.st + wait, fences, remote arrive) has ~600 cycles of fixed
+//     latency that more warps on the SAME k-block do not shorten;
+//   * two TMA producer warps: warp 0 streams the packed tiles, warp 18 the token rows.
 // ------------------------------------------------------------------------------------------------
 constexpr int kPkMaxSlots = 14;  // ring slots: as many as fit behind the accumulator (512 - m_pad columns, 32 each)
 constexpr int kPkSlotCols = kWsBlockK / 2;  // 64 bf16 of a weight row = 32 TMEM columns
