@@ -169,6 +169,11 @@ __device__ __forceinline__ void tma_load_2d_u32(uint32_t dst, const CUtensorMap*
                "r"(bar), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_u32(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(map),
+               "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_pair_u32(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
                "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
