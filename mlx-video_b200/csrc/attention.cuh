@@ -28,6 +28,9 @@ struct AttnParams {
   // ws_o + i*cmb_part_o and ws_ml + i*cmb_part_ml (strides in floats)
   int part_rows;
   long long cmb_job_stride, cmb_part_o, cmb_part_ml;
+  // key-split merge inside attention_pair64_kernel (no separate combine launch): arrivals / departures per split job, zero
+  // between launches; nullptr = attention_combine_kernel merges
+  int* cmb_counters;
   // cross-GPU flag barrier before the first read of Q / K / V (they were stored by the peers): folded into the prologue of
   // attention_pair64_kernel; the launchers of the other kernels run the stand-alone barrier kernel first
   PeerSync sync;

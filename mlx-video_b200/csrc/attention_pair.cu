@@ -437,6 +437,10 @@ struct Pair64Header {
 };
 static_assert(sizeof(Pair64Header) <= kPairHeader, "header overflow");
 
+constexpr int kCmbJobs = 160;  // split jobs a launch can have (<= SM count): arrival counters, then departure counters
+template <int kDh>
+__device__ __forceinline__ void attention_combine_row(const AttnParams& p, int jl, int rr, int lane);
+
 template <int kDh>
 __global__ void __launch_bounds__(kPairThreads, 1)
 attention_pair64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -744,6 +748,36 @@ attention_pair64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             *reinterpret_cast<uint4*>(wo + c + 4 * k) = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
         }
       }
+      if (p.cmb_counters != nullptr) {
+        // ---- merge inside the kernel (no combine launch): the key ranges of a split job meet at a counter, then each
+        // merges ITS share of the job's 256 rows by log-sum-exp (attention_combine_row) and writes the bf16 output.  The
+        // split CTAs are the last n_left * n_split <= SM count blocks of the grid, so they are all resident together.
+        const int jl = job.slot / p.n_split, part = job.slot - jl * p.n_split;
+        int* arrive = p.cmb_counters + jl;
+        int* depart = p.cmb_counters + kCmbJobs + jl;
+        asm volatile("bar.sync 2, 256;" ::: "memory");  // all eight softmax warps have parked their rows
+        if (warp == 4 && lane == 0) {
+          __threadfence();
+          atomicAdd(arrive, 1);
+          const long long t0 = clock64();
+          while (*reinterpret_cast<volatile int*>(arrive) < p.n_split) {
+            if (clock64() - t0 > LTXB_WATCHDOG_CYCLES) {
+              printf("ltxb: attention key-split watchdog: job %d part %d sees %d of %d arrivals\n", jl, part, *reinterpret_cast<volatile int*>(arrive), p.n_split);
+              __trap();
+            }
+          }
+          __threadfence();
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const int rpp = (256 + p.n_split - 1) / p.n_split;
+        const int r_end = min(256, (part + 1) * rpp);
+        for (int rr = part * rpp + (warp - 4); rr < r_end; rr += 8) attention_combine_row<kDh>(p, jl, rr, lane);
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (warp == 4 && lane == 0 && atomicAdd(depart, 1) == p.n_split - 1) {  // the last range to leave re-arms the counters
+          *arrive = 0;
+          *depart = 0;
+        }
+      }
     }
   }
 
@@ -758,16 +792,12 @@ attention_pair64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   }
 }
 
-// One warp per query row of a split job: O = sum_i 2^(m_i - M) O_i / sum_i 2^(m_i - M) l_i.
+// One warp per query row of a split job: O = sum_i 2^(m_i - M) O_i / sum_i 2^(m_i - M) l_i.  (jl: index of the job among the
+// split ones, rr: row inside the job's partial block.)  Partials are read through L2 (__ldcg): inside the attention kernel
+// they were written by other SMs moments ago.
 template <int kDh>
-__global__ void __launch_bounds__(256) attention_combine_kernel(const AttnParams p, int n_left) {
-  pdl_launch_dependents();
-  pdl_wait();
+__device__ __forceinline__ void attention_combine_row(const AttnParams& p, int jl, int rr, int lane) {
   constexpr int kPer = kDh / 32;  // columns per lane
-  const int lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int jl = gw / p.part_rows, rr = gw - jl * p.part_rows;
-  if (jl >= n_left) return;
   const int jb = p.n_full + jl;
   const int bh = jb / p.n_qp;
   const int row = (jb - bh * p.n_qp) * 256 + rr;
@@ -775,21 +805,21 @@ __global__ void __launch_bounds__(256) attention_combine_kernel(const AttnParams
   const int b = bh / p.H, h = bh - b * p.H;
   const long long prow0 = static_cast<long long>(jl) * p.cmb_job_stride + rr;
   float M = -INFINITY;
-  for (int i = 0; i < p.n_split; ++i) M = fmaxf(M, p.ws_ml[i * p.cmb_part_ml + prow0 * 2]);
+  for (int i = 0; i < p.n_split; ++i) M = fmaxf(M, __ldcg(p.ws_ml + i * p.cmb_part_ml + prow0 * 2));
   float acc[kPer];
 #pragma unroll
   for (int u = 0; u < kPer; ++u) acc[u] = 0.f;
   float L = 0.f;
   for (int i = 0; i < p.n_split; ++i) {
-    const float2 ml = *reinterpret_cast<const float2*>(p.ws_ml + i * p.cmb_part_ml + prow0 * 2);
+    const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.ws_ml + i * p.cmb_part_ml + prow0 * 2));
     const float w = (ml.x == -INFINITY) ? 0.f : fast_exp2(ml.x - M);
     L += w * ml.y;
     const float* src = p.ws_o + i * p.cmb_part_o + prow0 * kDh + lane * kPer;
     if constexpr (kPer == 4) {
-      const float4 v = *reinterpret_cast<const float4*>(src);
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(src));
       acc[0] += w * v.x, acc[1] += w * v.y, acc[2] += w * v.z, acc[3] += w * v.w;
     } else {
-      const float2 v = *reinterpret_cast<const float2*>(src);
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(src));
       acc[0] += w * v.x, acc[1] += w * v.y;
     }
   }
@@ -802,6 +832,17 @@ __global__ void __launch_bounds__(256) attention_combine_kernel(const AttnParams
   }
 }
 
+template <int kDh>
+__global__ void __launch_bounds__(256) attention_combine_kernel(const AttnParams p, int n_left) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int jl = gw / p.part_rows, rr = gw - jl * p.part_rows;
+  if (jl >= n_left) return;
+  attention_combine_row<kDh>(p, jl, rr, lane);
+}
+
 // ---- split-KV workspace: registered by the host framework (the library never allocates) -----------
 constexpr int kMaxDevices = 16;
 constexpr int kMaxSlots = 160;  // <= SM count
@@ -810,7 +851,8 @@ struct AttnWorkspace {
   long long bytes = 0;
 };
 static AttnWorkspace g_attn_ws[kMaxDevices];
-static long long attn_ws_bytes_for(int slots, int dh) { return static_cast<long long>(slots) * 256 * (dh + 2) * sizeof(float); }
+constexpr long long kCmbCounterBytes = 2048;  // 2 x kCmbJobs ints in front of the partials, zeroed when the workspace is registered
+static long long attn_ws_bytes_for(int slots, int dh) { return kCmbCounterBytes + static_cast<long long>(slots) * 256 * (dh + 2) * sizeof(float); }
 
 template <int kDh>
 static int launch_pair(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, AttnParams p,
@@ -848,12 +890,18 @@ static int launch_pair(const void* Q, long long ldq, const void* K, long long ld
   if (n_split > 1) {
     p.n_full = static_cast<int>(jobs - n_left);
     p.n_split = n_split;
-    p.ws_o = g_attn_ws[dev].base;
+    p.ws_o = g_attn_ws[dev].base + kCmbCounterBytes / sizeof(float);
     p.ws_ml = p.ws_o + static_cast<long long>(n_split) * n_left * 256 * kDh;
     p.part_rows = 256;
     p.cmb_job_stride = static_cast<long long>(n_split) * 256;
     p.cmb_part_o = 256ll * kDh;
     p.cmb_part_ml = 512;
+    // LTXB_ATTN_FUSED_COMBINE=1: the 64-key kernel merges inside (every key range its share of the rows, after meeting the
+    // others at a counter) instead of leaving it to attention_combine_kernel.  Measured slower — 50.0 against 42.6 us at
+    // 1280 x 1280, 33.5 against 33.0 ms per step: the ranges wait for the slowest one and merge with eight warps each, where
+    // the second launch (its prologue already overlapped by PDL) uses the whole GPU — so the separate launch is the default.
+    static const bool fused = [] { const char* e = getenv("LTXB_ATTN_FUSED_COMBINE"); return e != nullptr && atoi(e) != 0; }();
+    if (fused && s64 && n_left <= kCmbJobs) p.cmb_counters = reinterpret_cast<int*>(g_attn_ws[dev].base);
   } else {
     p.n_full = static_cast<int>(jobs);
     p.n_split = 1;
@@ -874,7 +922,7 @@ static int launch_pair(const void* Q, long long ldq, const void* K, long long ld
   if ((rc = enc(&tv, V, ldv, p.Tk))) return rc;
   const int grid = p.n_full + (n_split > 1 ? n_left * n_split : 0);
   LTXB_CUDA(launch_kernel(kernel, dim3(grid), dim3(kPairThreads), smem, stream, 1, tq, tk, tv, p));
-  if (n_split > 1)
+  if (n_split > 1 && p.cmb_counters == nullptr)
     LTXB_CUDA(launch_kernel(attention_combine_kernel<kDh>, dim3(n_left * 256 / 8), dim3(256), 0, stream, 1, p, n_left));
   return LTXB_OK;
 }
@@ -958,6 +1006,8 @@ extern "C" int ltxb_attention_set_workspace(void* workspace, int64_t bytes) {
     return LTXB_OK;
   }
   LTXB_CHECK_ARG(aligned16(workspace) && bytes > 0, "ltxb_attention_set_workspace: need a 16-byte aligned, non-empty buffer");
+  LTXB_CHECK_ARG(bytes > kCmbCounterBytes, "ltxb_attention_set_workspace: buffer smaller than the counter block");
+  LTXB_CUDA(cudaMemset(workspace, 0, kCmbCounterBytes));  // arrival / departure counters of the in-kernel key-split merge
   g_attn_ws[dev].base = reinterpret_cast<float*>(workspace);
   g_attn_ws[dev].bytes = bytes;
   return LTXB_OK;
