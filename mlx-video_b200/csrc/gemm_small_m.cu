@@ -850,23 +850,32 @@ gemm_small_m_packed_kernel(const __grid_constant__ CUtensorMap tmap_x, const __g
 #pragma unroll
           for (int j = 0; j < 8; ++j) {  // 8 levels per j
             const float sc = j < 4 ? sca : scb, bi = j < 4 ? bia : bib;
-            float v[8];
+            uint32_t f[8];  // float bit patterns 2^23 + level
             if constexpr (kWBits == 4) {
               const uint32_t lo = w[j] & 0x0F0F0F0Fu, hi = (w[j] >> 4) & 0x0F0F0F0Fu;  // even / odd levels, one per byte
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float q = __uint_as_float(__byte_perm((e & 1) ? hi : lo, magic, 0x7540u | (e >> 1))) - 8388608.0f;
-                v[e] = decltype(fused)::value ? __fmaf_rn(sc, q, bi) : __fadd_rn(__fmul_rn(sc, q), bi);
+              for (int e = 0; e < 8; ++e) f[e] = __byte_perm((e & 1) ? hi : lo, magic, 0x7540u | (e >> 1));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __byte_perm(w[2 * j + (e >> 2)], magic, 0x7540u | (e & 3));
+            }
+            if constexpr (decltype(fused)::value) {
+              // bf16 scales: two levels per instruction (add / fma .f32x2 round each half exactly like the scalar forms)
+              const uint64_t sc2 = pack_f32x2(sc, sc), bi2 = pack_f32x2(bi, bi), neg2 = pack_f32x2(-8388608.0f, -8388608.0f);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint64_t q2 = add_f32x2(pack_f32x2(__uint_as_float(f[2 * e]), __uint_as_float(f[2 * e + 1])), neg2);
+                float v0, v1;
+                unpack_f32x2(fma_f32x2(sc2, q2, bi2), v0, v1);
+                packed[4 * j + e] = pack_bf16x2(v0, v1);
               }
             } else {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float q = __uint_as_float(__byte_perm(w[2 * j + (e >> 2)], magic, 0x7540u | (e & 3))) - 8388608.0f;
-                v[e] = decltype(fused)::value ? __fmaf_rn(sc, q, bi) : __fadd_rn(__fmul_rn(sc, q), bi);
+              for (int e = 0; e < 4; ++e) {
+                const float q0 = __uint_as_float(f[2 * e]) - 8388608.0f, q1 = __uint_as_float(f[2 * e + 1]) - 8388608.0f;
+                packed[4 * j + e] = pack_bf16x2(__fadd_rn(__fmul_rn(sc, q0), bi), __fadd_rn(__fmul_rn(sc, q1), bi));
               }
             }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) packed[4 * j + e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
           }
         };
         if (p.aux_f32) expand(std::false_type{}); else expand(std::true_type{});
