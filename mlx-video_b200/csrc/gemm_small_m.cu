@@ -205,7 +205,7 @@ __device__ __forceinline__ void ws_stage_chunk(const WsParams& p, const float* a
 // The epilogue shared by the bf16 and the packed-weight kernels (warps 2..9 of a CTA): accumulator [128 weight rows (lanes)]
 // [m_pad tokens (columns)] at `tmem_acc` -> reduce-scatter over the k-range splits -> fused epilogue -> global memory.
 // `stage_area`: the operand stages, idle once the accumulator is complete, reused for the TMA output tiles.
-template <int kEpi>
+template <int kEpi, int kOthers>  // kOthers: parts of how many other splits a reduce pass requests together (registers!)
 __device__ __forceinline__ void ws_epilogue(const WsParams& p, const CUtensorMap* tmap_out, uint64_t* tmem_full, uint8_t* stage_area,
                                             uint32_t stage_area_bytes, uint32_t tmem_acc, int tile, int split, uint32_t cta_rank,
                                             int warp, int lane, long long* dbg) {
@@ -328,22 +328,24 @@ __device__ __forceinline__ void ws_epilogue(const WsParams& p, const CUtensorMap
       bool own_pending = true;
       int o = 0;
       while (o < p.splits || own_pending) {
-        // next two OTHER splits in order
-        int oa = o;
-        if (oa == split) ++oa;
-        int ob = oa + 1;
-        if (ob == split) ++ob;
-        const bool has_a = oa < p.splits, has_b = ob < p.splits;
-        float4 ld[2][2][2];
-        if (has_a) {
-          const float4* src = tile_slots + static_cast<size_t>(oa) * 2 * slot_f4 + (c * 2) * kWsTileRows;
-          ld[0][0][0] = __ldcg(src), ld[0][0][1] = __ldcg(src + kWsTileRows);
-          if (two) ld[0][1][0] = __ldcg(src + 2 * kWsTileRows), ld[0][1][1] = __ldcg(src + 3 * kWsTileRows);
+        // the next kOthers other splits in order: their parts of both chunks are requested together — one L2 round trip per
+        // pass (three with the registers of the one-CTA-per-SM build: one pass per chunk pair at the usual four splits;
+        // two under the 96-register cap of the two-per-SM build, where three spill: 14.5 -> 17.3 us)
+        int oo[kOthers];
+        int q = o;
+#pragma unroll
+        for (int b = 0; b < kOthers; ++b) {
+          if (q == split) ++q;
+          oo[b] = q++;
         }
-        if (has_b) {
-          const float4* src = tile_slots + static_cast<size_t>(ob) * 2 * slot_f4 + (c * 2) * kWsTileRows;
-          ld[1][0][0] = __ldcg(src), ld[1][0][1] = __ldcg(src + kWsTileRows);
-          if (two) ld[1][1][0] = __ldcg(src + 2 * kWsTileRows), ld[1][1][1] = __ldcg(src + 3 * kWsTileRows);
+        float4 ld[kOthers][2][2];
+#pragma unroll
+        for (int b = 0; b < kOthers; ++b) {
+          if (oo[b] < p.splits) {
+            const float4* src = tile_slots + static_cast<size_t>(oo[b]) * 2 * slot_f4 + (c * 2) * kWsTileRows;
+            ld[b][0][0] = __ldcg(src), ld[b][0][1] = __ldcg(src + kWsTileRows);
+            if (two) ld[b][1][0] = __ldcg(src + 2 * kWsTileRows), ld[b][1][1] = __ldcg(src + 3 * kWsTileRows);
+          }
         }
         auto add_own = [&]() {
           tmem_wait_ld();
@@ -351,19 +353,20 @@ __device__ __forceinline__ void ws_epilogue(const WsParams& p, const CUtensorMap
           for (int i = 0; i < kWsChunk; ++i) v[0][i] += __uint_as_float(r[0][i]), v[1][i] += two ? __uint_as_float(r[1][i]) : 0.f;
           own_pending = false;
         };
-        auto add_part = [&](int b) {
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            if (q == 1 && !two) break;
-            v[q][0] += ld[b][q][0].x, v[q][1] += ld[b][q][0].y, v[q][2] += ld[b][q][0].z, v[q][3] += ld[b][q][0].w;
-            v[q][4] += ld[b][q][1].x, v[q][5] += ld[b][q][1].y, v[q][6] += ld[b][q][1].z, v[q][7] += ld[b][q][1].w;
+        for (int b = 0; b < kOthers; ++b) {
+          const bool has = oo[b] < p.splits;
+          if (own_pending && (!has || split < oo[b])) add_own();
+          if (has) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (h == 1 && !two) break;
+              v[h][0] += ld[b][h][0].x, v[h][1] += ld[b][h][0].y, v[h][2] += ld[b][h][0].z, v[h][3] += ld[b][h][0].w;
+              v[h][4] += ld[b][h][1].x, v[h][5] += ld[b][h][1].y, v[h][6] += ld[b][h][1].z, v[h][7] += ld[b][h][1].w;
+            }
           }
-        };
-        if (own_pending && (!has_a || split < oa)) add_own();
-        if (has_a) add_part(0);
-        if (own_pending && (!has_b || split < ob)) add_own();
-        if (has_b) add_part(1);
-        o = ob + 1;
+        }
+        o = oo[kOthers - 1] + 1;
       }
       emit(v[0], c);
       if (two) emit(v[1], c + 1);
@@ -381,8 +384,10 @@ __device__ __forceinline__ void ws_epilogue(const WsParams& p, const CUtensorMap
   }
 }
 
-template <int kEpi>
-__global__ void __launch_bounds__(kWsThreads, 2)
+// kPerSm: CTAs per SM the launch is sized for — 2 caps a thread at 96 registers, 1 (what most shapes run, see
+// launch_gemm_small_m) leaves the epilogue its registers (no spills, three parts per reduce pass)
+template <int kEpi, int kPerSm>
+__global__ void __launch_bounds__(kWsThreads, kPerSm)
 gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_out, const WsParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -536,8 +541,8 @@ gemm_small_m_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         if (++stage == static_cast<uint32_t>(num_stages)) stage = 0, phase ^= 1;
       }
     }
-    ws_epilogue<kEpi>(p, &tmap_out, &hdr->tmem_full, tiles, static_cast<uint32_t>(num_stages) * stage_bytes, tmem_base, tile, split,
-                      cta_rank, warp, lane, dbg);
+    ws_epilogue<kEpi, kPerSm == 1 ? 3 : 2>(p, &tmap_out, &hdr->tmem_full, tiles, static_cast<uint32_t>(num_stages) * stage_bytes, tmem_base,
+                                           tile, split, cta_rank, warp, lane, dbg);
   }
 
   if (p.out_tma != 0 && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) tma_store_wait_read();  // the staged tiles stay valid until read
@@ -891,8 +896,8 @@ gemm_small_m_packed_kernel(const __grid_constant__ CUtensorMap tmap_x, const __g
 #endif
     (void)t_loop, (void)w_raw, (void)w_aempty, (void)w_st;
     if (warp < 10)  // the first two groups are the eight epilogue warps (two per TMEM lane quarter)
-      ws_epilogue<kEpi>(p, &tmap_out, &hdr->tmem_full, tiles, static_cast<uint32_t>(num_stages) * stage_bytes, tmem_base, tile, split,
-                        cta_rank, warp, lane, dbg);
+      ws_epilogue<kEpi, 2>(p, &tmap_out, &hdr->tmem_full, tiles, static_cast<uint32_t>(num_stages) * stage_bytes, tmem_base, tile, split,
+                           cta_rank, warp, lane, dbg);
   }
 
   if (p.out_tma != 0 && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) tma_store_wait_read();
@@ -911,12 +916,15 @@ gemm_small_m_packed_kernel(const __grid_constant__ CUtensorMap tmap_x, const __g
 // ------------------------------------------------------------------------------------------------
 template <int kEpi, int kWBits>
 static int launch_ws(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& to, const WsParams& p, int grid, size_t smem,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int per_sm) {
   static PerDeviceOnce configured;
   if constexpr (kWBits == 16) {
-    auto kernel = gemm_small_m_kernel<kEpi>;
-    if (configured.first()) LTXB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    LTXB_CUDA(launch_kernel(kernel, dim3(grid), dim3(kWsThreads), smem, stream, 2, tx, tw, to, p));
+    if (configured.first()) {
+      LTXB_CUDA(cudaFuncSetAttribute(gemm_small_m_kernel<kEpi, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      LTXB_CUDA(cudaFuncSetAttribute(gemm_small_m_kernel<kEpi, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    }
+    if (per_sm == 1) LTXB_CUDA(launch_kernel(gemm_small_m_kernel<kEpi, 1>, dim3(grid), dim3(kWsThreads), smem, stream, 2, tx, tw, to, p));
+    else LTXB_CUDA(launch_kernel(gemm_small_m_kernel<kEpi, 2>, dim3(grid), dim3(kWsThreads), smem, stream, 2, tx, tw, to, p));
   } else {
     auto kernel = gemm_small_m_packed_kernel<kEpi, kWBits>;
     if (configured.first()) LTXB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -1055,11 +1063,11 @@ int launch_gemm_small_m(const void* A, int64_t lda, const void* W, int64_t ldw, 
   const int grid = tiles * splits * 2;
 #define LTXB_WS_DISPATCH(BITS)                                                                                         \
   switch (epi->mode) {                                                                                                 \
-    case LTXB_EPI_BIAS_BF16: return launch_ws<LTXB_EPI_BIAS_BF16, BITS>(tx, tw, to, p, grid, smem, stream);             \
-    case LTXB_EPI_GELU_BF16: return launch_ws<LTXB_EPI_GELU_BF16, BITS>(tx, tw, to, p, grid, smem, stream);             \
-    case LTXB_EPI_SILU_BF16: return launch_ws<LTXB_EPI_SILU_BF16, BITS>(tx, tw, to, p, grid, smem, stream);             \
-    case LTXB_EPI_BIAS_F32: return launch_ws<LTXB_EPI_BIAS_F32, BITS>(tx, tw, to, p, grid, smem, stream);               \
-    case LTXB_EPI_RESID_GATE_F32: return launch_ws<LTXB_EPI_RESID_GATE_F32, BITS>(tx, tw, to, p, grid, smem, stream);   \
+    case LTXB_EPI_BIAS_BF16: return launch_ws<LTXB_EPI_BIAS_BF16, BITS>(tx, tw, to, p, grid, smem, stream, per_sm);             \
+    case LTXB_EPI_GELU_BF16: return launch_ws<LTXB_EPI_GELU_BF16, BITS>(tx, tw, to, p, grid, smem, stream, per_sm);             \
+    case LTXB_EPI_SILU_BF16: return launch_ws<LTXB_EPI_SILU_BF16, BITS>(tx, tw, to, p, grid, smem, stream, per_sm);             \
+    case LTXB_EPI_BIAS_F32: return launch_ws<LTXB_EPI_BIAS_F32, BITS>(tx, tw, to, p, grid, smem, stream, per_sm);               \
+    case LTXB_EPI_RESID_GATE_F32: return launch_ws<LTXB_EPI_RESID_GATE_F32, BITS>(tx, tw, to, p, grid, smem, stream, per_sm);   \
     default: return set_error(LTXB_ERR_BAD_ARG, "ltxb_gemm: unknown epilogue mode %d", epi->mode);                     \
   }
   if (w_bits == 4) { LTXB_WS_DISPATCH(4) }
